@@ -1,0 +1,35 @@
+# Builds the C-ABI shared library (sm_100a only) and the CPU oracle.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
+CSRC      := border_b200/csrc
+OBJDIR    := build/obj
+LIB       := border_b200/libborder_b200.so
+SRCS      := common.cu replay.cu nn.cu agent.cu dqn.cu sac.cu iqn.cu tc_gemm.cu
+SRCS      := $(filter $(notdir $(wildcard $(CSRC)/*.cu)),$(SRCS)) $(if $(wildcard $(CSRC)/sac.cu),,stubs.cu)
+OBJS      := $(patsubst %.cu,$(OBJDIR)/%.o,$(SRCS))
+HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.inc) include/border_b200.h
+
+all: $(LIB) oracle
+
+$(OBJDIR)/replay.o: $(CSRC)/replay.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+oracle: oracle/_build/libreplay_oracle.so
+
+oracle/_build/libreplay_oracle.so: oracle/replay_oracle.c
+	@mkdir -p oracle/_build
+	gcc -O2 -fPIC -shared -o $@ $< -lm
+
+clean:
+	rm -rf build $(LIB) oracle/_build
+
+.PHONY: all oracle clean

@@ -1,0 +1,512 @@
+// agent.cu -- Agent/Model plumbing and the agent half of the C ABI.
+#include <errno.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+#include "agent.cuh"
+
+namespace bb {
+
+// ------------------------------------------------------------------------------- Model
+
+void Model::alloc(bool with_opt) {
+    has_opt = with_opt;
+    p = dev_alloc_zero<float>(n);
+    if (with_opt) {
+        g = dev_alloc_zero<float>(n);
+        m = dev_alloc_zero<float>(n);
+        v = dev_alloc_zero<float>(n);
+    }
+}
+void Model::release() {
+    cudaFree(p); cudaFree(g); cudaFree(m); cudaFree(v);
+    p = g = m = v = nullptr;
+}
+void Model::set_hyper(const bb_opt_cfg& o) {
+    if (o.kind == BB_OPT_ADAMW) {  // opt.rs:38-54
+        hyper = AdamHyper{o.lr, o.beta1, o.beta2, o.eps, o.wd, true};
+        BB_CHECK(!o.amsgrad, "AdamW amsgrad=true is not supported");
+    } else {  // Adam::default(), opt.rs:33-36
+        hyper = AdamHyper{o.lr, 0.9, 0.999, 1e-8, 0.0, false};
+    }
+}
+const ParamInfo* Model::find(const std::string& nm) const {
+    for (auto& pi : params)
+        if (pi.name == nm) return &pi;
+    return nullptr;
+}
+void Model::copy_params_from(const Model& src, cudaStream_t s) {
+    BB_CHECK(src.n == n, "VarStore size mismatch");
+    BB_CUDA(cudaMemcpyAsync(p, src.p, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+
+// ------------------------------------------------------------------------------- Agent base
+
+void Agent::init_base(int dev) {
+    device = dev;
+    int count = 0;
+    BB_CUDA(cudaGetDeviceCount(&count));
+    BB_CHECK(dev >= 0 && dev < count, "no such CUDA device");
+    DeviceGuard g(dev);
+    ctx.device = dev;
+    ctx.sms = num_sms(dev);
+    ctx.stream = device_stream(dev);
+    ctx.ws_floats = 8u << 20;  // 32 MB split-K / reduction workspace
+    ctx.ws = dev_alloc<float>(ctx.ws_floats);
+    BB_CUDA(cudaMallocHost(&h_scratch, 4096 * sizeof(float)));
+    d_scratch = dev_alloc<float>(1 << 20);
+}
+Agent::~Agent() {
+    cudaFree(ctx.ws);
+    cudaFree(d_scratch);
+    cudaFree(my_flags);
+    if (h_scratch) cudaFreeHost(h_scratch);
+}
+Model* Agent::model(const std::string& name) {
+    for (auto* m : models)
+        if (m->name == name) return m;
+    throw Error("no such model (VarStore): " + name);
+}
+void Agent::inject_noise(int, const float*, size_t) { throw Error("this agent takes no injected noise"); }
+void Agent::grad_buffer(void** p, uint64_t* n) { *p = nullptr; *n = 0; }
+
+// Cross-GPU barrier on flags in peer memory: rank r writes its epoch into slot r of every peer's
+// flag array (system-scope store over NVLink), then waits until all slots of its own array reach
+// the epoch.  Bounded spin: a missing peer cannot hang the GPU.
+__global__ void peer_barrier_kernel(unsigned int* mine, unsigned int* const* peers_unused, unsigned int* p0,
+                                    unsigned int* p1, unsigned int* p2, unsigned int* p3, unsigned int* p4,
+                                    unsigned int* p5, unsigned int* p6, unsigned int* p7, int rank, int world,
+                                    unsigned int epoch) {
+    (void)peers_unused;
+    unsigned int* peers[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
+    int t = threadIdx.x;
+    if (t < world) {
+        __threadfence_system();
+        volatile unsigned int* dst = peers[t] + rank;
+        *dst = epoch;
+        __threadfence_system();
+        volatile unsigned int* src = mine + t;
+        long long t0 = clock64();
+        while ((int)(*src - epoch) < 0) {
+            if (clock64() - t0 > 4000000000LL) break;  // ~2 s: give up instead of hanging
+        }
+    }
+}
+
+static void peer_barrier(Agent* a) {
+    a->sync_epoch += 1;
+    peer_barrier_kernel<<<1, 32, 0, a->ctx.stream>>>(a->my_flags, nullptr, a->peer_flag[0], a->peer_flag[1],
+                                                    a->peer_flag[2], a->peer_flag[3], a->peer_flag[4], a->peer_flag[5],
+                                                    a->peer_flag[6], a->peer_flag[7], a->rank, a->world, a->sync_epoch);
+    BB_LAUNCHED();
+}
+void Agent::grad_sync_begin() {
+    if (world > 1) peer_barrier(this);
+}
+void Agent::grad_sync_end() {
+    if (world > 1) peer_barrier(this);
+}
+
+// ------------------------------------------------------------------------------- checkpoints
+
+// One directory per save_params call, as in the reference (dqn/base.rs:348-362 writes
+// qnet.pt.tch / qnet_tgt.pt.tch).  Each VarStore becomes `<model>.pt.tch.b200`: a text manifest
+// line per tensor followed by raw little-endian f32 in the REFERENCE layout, plus (what the
+// reference lacks) the Adam moments and step for true resume.
+void Agent::save_params(const char* dir) {
+    DeviceGuard g(device);
+    BB_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (mkdir(dir, 0777) != 0 && errno != EEXIST) throw Error(std::string("cannot create directory ") + dir);
+    for (Model* m : models) {
+        std::string path = std::string(dir) + "/" + m->name + ".pt.tch.b200";
+        std::ofstream f(path, std::ios::binary);
+        if (!f) throw Error("cannot open " + path);
+        std::vector<float> hp(m->n), hm, hv;
+        BB_CUDA(cudaMemcpy(hp.data(), m->p, m->n * 4, cudaMemcpyDeviceToHost));
+        if (m->has_opt) {
+            hm.resize(m->n); hv.resize(m->n);
+            BB_CUDA(cudaMemcpy(hm.data(), m->m, m->n * 4, cudaMemcpyDeviceToHost));
+            BB_CUDA(cudaMemcpy(hv.data(), m->v, m->n * 4, cudaMemcpyDeviceToHost));
+        }
+        f << "BORDER_B200_VARSTORE 1 " << m->params.size() << " " << (m->has_opt ? 1 : 0) << " " << m->step << "\n";
+        for (auto& pi : m->params) {
+            f << pi.name << " " << pi.shape.size();
+            for (auto d : pi.shape) f << " " << d;
+            f << "\n";
+        }
+        std::vector<float> ref;
+        for (auto& pi : m->params) {
+            ref.resize(pi.numel);
+            param_to_reference(pi, hp.data() + pi.offset, ref.data());
+            f.write((const char*)ref.data(), pi.numel * 4);
+            if (m->has_opt) {
+                param_to_reference(pi, hm.data() + pi.offset, ref.data());
+                f.write((const char*)ref.data(), pi.numel * 4);
+                param_to_reference(pi, hv.data() + pi.offset, ref.data());
+                f.write((const char*)ref.data(), pi.numel * 4);
+            }
+        }
+        if (!f) throw Error("write failed: " + path);
+    }
+}
+
+void Agent::load_params(const char* dir) {
+    DeviceGuard g(device);
+    BB_CUDA(cudaStreamSynchronize(ctx.stream));
+    for (Model* m : models) {
+        std::string path = std::string(dir) + "/" + m->name + ".pt.tch.b200";
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw Error("cannot open " + path);
+        std::string magic;
+        int ver, has_opt;
+        size_t nt;
+        uint64_t step;
+        f >> magic >> ver >> nt >> has_opt >> step;
+        if (magic != "BORDER_B200_VARSTORE" || nt != m->params.size()) throw Error("bad checkpoint " + path);
+        for (auto& pi : m->params) {
+            std::string nm;
+            size_t nd;
+            f >> nm >> nd;
+            if (nm != pi.name || nd != pi.shape.size()) throw Error("checkpoint tensor mismatch: " + nm);
+            for (size_t i = 0; i < nd; ++i) {
+                int64_t d;
+                f >> d;
+                if (d != pi.shape[i]) throw Error("checkpoint shape mismatch: " + nm);
+            }
+        }
+        f.get();  // newline
+        std::vector<float> hp(m->n, 0.f), hm(m->n, 0.f), hv(m->n, 0.f), ref;
+        for (auto& pi : m->params) {
+            ref.resize(pi.numel);
+            f.read((char*)ref.data(), pi.numel * 4);
+            param_to_internal(pi, ref.data(), hp.data() + pi.offset);
+            if (has_opt) {
+                f.read((char*)ref.data(), pi.numel * 4);
+                param_to_internal(pi, ref.data(), hm.data() + pi.offset);
+                f.read((char*)ref.data(), pi.numel * 4);
+                param_to_internal(pi, ref.data(), hv.data() + pi.offset);
+            }
+        }
+        if (!f) throw Error("read failed: " + path);
+        BB_CUDA(cudaMemcpy(m->p, hp.data(), m->n * 4, cudaMemcpyHostToDevice));
+        if (m->has_opt && has_opt) {
+            BB_CUDA(cudaMemcpy(m->m, hm.data(), m->n * 4, cudaMemcpyHostToDevice));
+            BB_CUDA(cudaMemcpy(m->v, hv.data(), m->n * 4, cudaMemcpyHostToDevice));
+            m->step = step;
+        }
+    }
+}
+
+}  // namespace bb
+
+// =============================================================================== C ABI
+
+struct bb_agent { std::unique_ptr<bb::Agent> impl; };
+
+static bb::Agent& A(bb_agent* a) {
+    if (!a || !a->impl) throw bb::Error("null agent handle");
+    return *a->impl;
+}
+
+extern "C" {
+
+static void net_default(bb_net_cfg* n) {
+    memset(n, 0, sizeof(*n));
+    n->kind = BB_NET_MLP; n->in_dim = 4; n->n_units = 2; n->units[0] = 64; n->units[1] = 64; n->out_dim = 2;
+    n->n_stack = 4;
+}
+static void opt_default(bb_opt_cfg* o, double lr) {
+    memset(o, 0, sizeof(*o));
+    o->kind = BB_OPT_ADAM; o->lr = lr; o->beta1 = 0.9; o->beta2 = 0.999; o->eps = 1e-8; o->wd = 0.0;
+}
+
+void bb_dqn_cfg_default(bb_dqn_cfg* c) {  // dqn/config.rs:82-102
+    memset(c, 0, sizeof(*c));
+    net_default(&c->q_config);
+    opt_default(&c->opt_config, 0.0);
+    c->soft_update_interval = 1; c->n_updates_per_opt = 1; c->batch_size = 1; c->discount_factor = 0.99;
+    c->tau = 0.005; c->train = 0; c->explorer = BB_EXPLORER_SOFTMAX; c->eps_start = 1.0; c->eps_final = 0.02;
+    c->final_step = 100000; c->double_dqn = 0; c->critic_loss = BB_LOSS_MSE; c->record_verbose_level = 0;
+    c->device = 0; c->init_seed = 0; c->explorer_seed = 0x0123456789abcdefULL;
+}
+void bb_sac_cfg_default(bb_sac_cfg* c) {  // sac/config.rs:85-105
+    memset(c, 0, sizeof(*c));
+    net_default(&c->pi_config);
+    net_default(&c->q_config);
+    opt_default(&c->pi_opt_config, 3e-4);
+    opt_default(&c->q_opt_config, 3e-4);
+    c->gamma = 0.99; c->tau = 0.005; c->ent_coef_mode = BB_ENTCOEF_FIX; c->ent_coef_fix = 1.0;
+    c->epsilon = 1e-4; c->min_lstd = -20.0; c->max_lstd = 2.0; c->n_updates_per_opt = 1; c->batch_size = 1;
+    c->train = 0; c->critic_loss = BB_LOSS_MSE; c->reward_scale = 1.0; c->n_critics = 1; c->device = 0;
+    c->noise_seed = 0x5ac5ac5acULL;
+}
+void bb_iqn_cfg_default(bb_iqn_cfg* c) {  // iqn/config.rs:50-67
+    memset(c, 0, sizeof(*c));
+    net_default(&c->f_config);
+    net_default(&c->m_config);
+    opt_default(&c->opt_config, 0.0);
+    c->feature_dim = 64; c->embed_dim = 64;
+    c->soft_update_interval = 1; c->n_updates_per_opt = 1; c->batch_size = 1; c->discount_factor = 0.99;
+    c->tau = 0.005; c->train = 0; c->sample_percents_pred = BB_IQN_UNIFORM64; c->sample_percents_tgt = BB_IQN_UNIFORM64;
+    c->sample_percents_act = BB_IQN_UNIFORM32; c->eps_start = 1.0; c->eps_final = 0.02; c->final_step = 100000;
+    c->device = 0; c->explorer_seed = 0x0123456789abcdefULL; c->tau_seed = 0x7a07a0ULL;
+}
+
+int32_t bb_dqn_create(const bb_dqn_cfg* cfg, bb_agent** out) {
+    BB_API_BEGIN
+    BB_CHECK(cfg && out, "null argument");
+    BB_CHECK(cfg->device >= 0, "No device is given for DQN agent");  // dqn/base.rs:258
+    *out = new bb_agent{std::unique_ptr<bb::Agent>(bb::make_dqn(*cfg))};
+    BB_API_END
+}
+int32_t bb_sac_create(const bb_sac_cfg* cfg, bb_agent** out) {
+    BB_API_BEGIN
+    BB_CHECK(cfg && out, "null argument");
+    *out = new bb_agent{std::unique_ptr<bb::Agent>(bb::make_sac(*cfg))};
+    BB_API_END
+}
+int32_t bb_iqn_create(const bb_iqn_cfg* cfg, bb_agent** out) {
+    BB_API_BEGIN
+    BB_CHECK(cfg && out, "null argument");
+    *out = new bb_agent{std::unique_ptr<bb::Agent>(bb::make_iqn(*cfg))};
+    BB_API_END
+}
+int32_t bb_agent_destroy(bb_agent* a) {
+    BB_API_BEGIN
+    delete a;
+    BB_API_END
+}
+int32_t bb_agent_set_stream(bb_agent* a, void* s) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
+    ag.ctx.stream = s ? (cudaStream_t)s : bb::device_stream(ag.device);
+    BB_API_END
+}
+int32_t bb_agent_set_train(bb_agent* a, int32_t train) {
+    BB_API_BEGIN
+    A(a).train = train != 0;
+    BB_API_END
+}
+int32_t bb_agent_is_train(const bb_agent* a, int32_t* out) {
+    BB_API_BEGIN
+    BB_CHECK(a && a->impl && out, "null argument");
+    *out = a->impl->train ? 1 : 0;
+    BB_API_END
+}
+int32_t bb_agent_sample(bb_agent* a, const void* obs, size_t n, void* act_out) {
+    BB_API_BEGIN
+    BB_CHECK(obs && act_out, "null argument");
+    A(a).sample(obs, n, act_out);
+    BB_API_END
+}
+int32_t bb_agent_opt(bb_agent* a, bb_replay* rb, bb_record* record) {
+    BB_API_BEGIN
+    BB_CHECK(rb, "null replay handle");
+    A(a).opt(rb->impl, record);
+    BB_API_END
+}
+int32_t bb_agent_n_opts(const bb_agent* a, uint64_t* out) {
+    BB_API_BEGIN
+    BB_CHECK(a && a->impl && out, "null argument");
+    *out = a->impl->n_opts;
+    BB_API_END
+}
+int32_t bb_agent_save_params(bb_agent* a, const char* dir) {
+    BB_API_BEGIN
+    BB_CHECK(dir, "null path");
+    A(a).save_params(dir);
+    BB_API_END
+}
+int32_t bb_agent_load_params(bb_agent* a, const char* dir) {
+    BB_API_BEGIN
+    BB_CHECK(dir, "null path");
+    A(a).load_params(dir);
+    BB_API_END
+}
+int32_t bb_agent_param_count(bb_agent* a, const char* model, uint64_t* n_tensors, uint64_t* n_floats) {
+    BB_API_BEGIN
+    bb::Model* m = A(a).model(model);
+    uint64_t nf = 0;
+    for (auto& pi : m->params) nf += pi.numel;
+    if (n_tensors) *n_tensors = m->params.size();
+    if (n_floats) *n_floats = nf;
+    BB_API_END
+}
+int32_t bb_agent_param_info(bb_agent* a, const char* model, uint64_t index, char* name_out, size_t name_cap,
+                            int64_t* shape_out, int32_t* ndim_out) {
+    BB_API_BEGIN
+    bb::Model* m = A(a).model(model);
+    BB_CHECK(index < m->params.size(), "parameter index out of range");
+    const bb::ParamInfo& pi = m->params[index];
+    if (name_out && name_cap) {
+        strncpy(name_out, pi.name.c_str(), name_cap - 1);
+        name_out[name_cap - 1] = 0;
+    }
+    if (shape_out)
+        for (size_t i = 0; i < 4; ++i) shape_out[i] = i < pi.shape.size() ? pi.shape[i] : 1;
+    if (ndim_out) *ndim_out = (int32_t)pi.shape.size();
+    BB_API_END
+}
+
+static void get_tensor(bb::Agent& ag, const float* dev_base, const bb::ParamInfo& pi, float* host_out) {
+    std::vector<float> tmp(pi.numel);
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
+    BB_CUDA(cudaMemcpy(tmp.data(), dev_base + pi.offset, pi.numel * 4, cudaMemcpyDeviceToHost));
+    bb::param_to_reference(pi, tmp.data(), host_out);
+}
+
+int32_t bb_agent_get_param(bb_agent* a, const char* model, const char* name, float* host_out, size_t n) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    bb::Model* m = ag.model(model);
+    const bb::ParamInfo* pi = m->find(name);
+    BB_CHECK(pi, "no such parameter");
+    BB_CHECK(n == pi->numel, "parameter size mismatch");
+    get_tensor(ag, m->p, *pi, host_out);
+    BB_API_END
+}
+int32_t bb_agent_set_param(bb_agent* a, const char* model, const char* name, const float* host_in, size_t n) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    bb::Model* m = ag.model(model);
+    const bb::ParamInfo* pi = m->find(name);
+    BB_CHECK(pi, "no such parameter");
+    BB_CHECK(n == pi->numel, "parameter size mismatch");
+    std::vector<float> tmp(pi->numel);
+    bb::param_to_internal(*pi, host_in, tmp.data());
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
+    BB_CUDA(cudaMemcpy(m->p + pi->offset, tmp.data(), pi->numel * 4, cudaMemcpyHostToDevice));
+    BB_API_END
+}
+int32_t bb_agent_get_opt_state(bb_agent* a, const char* model, const char* name, float* host_m, float* host_v, size_t n,
+                               uint64_t* step) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    bb::Model* m = ag.model(model);
+    BB_CHECK(m->has_opt, "this VarStore has no optimizer state");
+    const bb::ParamInfo* pi = m->find(name);
+    BB_CHECK(pi, "no such parameter");
+    BB_CHECK(n == pi->numel, "parameter size mismatch");
+    if (host_m) get_tensor(ag, m->m, *pi, host_m);
+    if (host_v) get_tensor(ag, m->v, *pi, host_v);
+    if (step) *step = m->step;
+    BB_API_END
+}
+
+// SyncModel: NamedTensors::copy_from(var_store) (util/named_tensors.rs:11-36) as one flat blob in
+// reference layout, tensors in VarStore order.
+int32_t bb_agent_model_info_size(bb_agent* a, uint64_t* n_floats) {
+    BB_API_BEGIN
+    bb::Model* m = A(a).sync_model_src();
+    uint64_t nf = 0;
+    for (auto& pi : m->params) nf += pi.numel;
+    *n_floats = nf;
+    BB_API_END
+}
+int32_t bb_agent_model_info(bb_agent* a, float* host_out, size_t n, uint64_t* n_opts) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    bb::Model* m = ag.sync_model_src();
+    std::vector<float> h(m->n);
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
+    BB_CUDA(cudaMemcpy(h.data(), m->p, m->n * 4, cudaMemcpyDeviceToHost));
+    size_t off = 0;
+    for (auto& pi : m->params) {
+        BB_CHECK(off + pi.numel <= n, "model_info buffer too small");
+        bb::param_to_reference(pi, h.data() + pi.offset, host_out + off);
+        off += pi.numel;
+    }
+    if (n_opts) *n_opts = ag.n_opts;
+    BB_API_END
+}
+int32_t bb_agent_sync_model(bb_agent* a, const float* host_in, size_t n) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    bb::Model* m = ag.sync_model_src();
+    std::vector<float> h(m->n, 0.f);
+    size_t off = 0;
+    for (auto& pi : m->params) {
+        BB_CHECK(off + pi.numel <= n, "model_info blob too small");
+        bb::param_to_internal(pi, host_in + off, h.data() + pi.offset);
+        off += pi.numel;
+    }
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
+    BB_CUDA(cudaMemcpy(m->p, h.data(), m->n * 4, cudaMemcpyHostToDevice));
+    BB_API_END
+}
+int32_t bb_agent_sync_model_from(bb_agent* dst, bb_agent* src) {
+    BB_API_BEGIN
+    bb::Agent &d = A(dst), &s = A(src);
+    BB_CHECK(d.device == s.device, "sync_model_from needs both agents on one GPU");
+    bb::DeviceGuard g(d.device);
+    bb::Model *md = d.sync_model_src(), *ms = s.sync_model_src();
+    if (d.ctx.stream != s.ctx.stream) bb::stream_wait(d.ctx.stream, s.ctx.stream);
+    md->copy_params_from(*ms, d.ctx.stream);
+    BB_API_END
+}
+int32_t bb_agent_inject_noise(bb_agent* a, int32_t slot, const float* host, size_t n) {
+    BB_API_BEGIN
+    BB_CHECK(host, "null argument");
+    A(a).inject_noise(slot, host, n);
+    BB_API_END
+}
+int32_t bb_agent_grad_buffer(bb_agent* a, void** dev_ptr, uint64_t* n_floats) {
+    BB_API_BEGIN
+    BB_CHECK(dev_ptr && n_floats, "null argument");
+    A(a).grad_buffer(dev_ptr, n_floats);
+    BB_API_END
+}
+int32_t bb_agent_ipc_export(bb_agent* a, void* handle_out, void* flag_handle_out) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    void* gp;
+    uint64_t n;
+    ag.grad_buffer(&gp, &n);
+    BB_CHECK(gp, "agent has no gradient buffer to share");
+    if (!ag.my_flags) ag.my_flags = bb::dev_alloc_zero<unsigned int>(64);
+    BB_CUDA(cudaDeviceSynchronize());
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    BB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle_out, gp));
+    BB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)flag_handle_out, ag.my_flags));
+    BB_API_END
+}
+int32_t bb_agent_ipc_connect(bb_agent* a, int32_t rank, int32_t world, const void* handles, const void* flag_handles) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    BB_CHECK(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad rank/world");
+    void* gp;
+    uint64_t n;
+    ag.grad_buffer(&gp, &n);
+    BB_CHECK(ag.my_flags, "call bb_agent_ipc_export first");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            ag.peer_grad[r] = (const float*)gp;
+            ag.peer_flag[r] = ag.my_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        void* p = nullptr;
+        memcpy(&h, (const char*)handles + 64 * r, 64);
+        BB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ag.peer_grad[r] = (const float*)p;
+        memcpy(&h, (const char*)flag_handles + 64 * r, 64);
+        BB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ag.peer_flag[r] = (unsigned int*)p;
+    }
+    ag.rank = rank;
+    ag.world = world;
+    BB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// agent.cuh -- the object behind the opaque bb_agent handle: Policy + Agent + SyncModel
+// (border-core/src/base/{policy,agent}.rs, border-async-trainer/src/sync_model.rs).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include "nn.cuh"
+#include "replay_internal.cuh"
+
+namespace bb {
+
+// host-side fastrand (wyrand) used by the explorers, as in the reference (dqn/explorer.rs:71,82)
+struct FastRand {
+    uint64_t s;
+    explicit FastRand(uint64_t seed = 0) : s(seed) {}
+    uint64_t u64() {
+        s += 0xA0761D6478BD642FULL;
+        __uint128_t t = (__uint128_t)s * (__uint128_t)(s ^ 0xE7037ED1A0B428DBULL);
+        return (uint64_t)t ^ (uint64_t)(t >> 64);
+    }
+    uint32_t u32() { return (uint32_t)u64(); }
+    float f32() {
+        uint32_t b = 0x3F800000u | (u32() >> 9);
+        float f; memcpy(&f, &b, 4);
+        return f - 1.0f;
+    }
+    double f64() {
+        uint64_t b = 0x3FF0000000000000ULL | (u64() >> 12);
+        double f; memcpy(&f, &b, 8);
+        return f - 1.0;
+    }
+    uint32_t u32_below(uint32_t n) {
+        uint32_t x = u32();
+        uint64_t m = (uint64_t)x * n;
+        uint32_t hi = (uint32_t)(m >> 32), lo = (uint32_t)m;
+        if (lo < n) {
+            uint32_t t = (0u - n) % n;
+            while (lo < t) { x = u32(); m = (uint64_t)x * n; hi = (uint32_t)(m >> 32); lo = (uint32_t)m; }
+        }
+        return hi;
+    }
+    uint64_t u64_below(uint64_t n) {
+        uint64_t x = u64();
+        __uint128_t m = (__uint128_t)x * n;
+        uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
+        if (lo < n) {
+            uint64_t t = (0ull - n) % n;
+            while (lo < t) { x = u64(); m = (__uint128_t)x * n; hi = (uint64_t)(m >> 64); lo = (uint64_t)m; }
+        }
+        return hi;
+    }
+};
+
+// One VarStore + optimizer (DqnModel dqn/model/base.rs:20-39, Critic, Actor, EntCoef).
+struct Model {
+    std::string name;
+    std::vector<ParamInfo> params;
+    size_t n = 0;  // floats (padded)
+    float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+    uint64_t step = 0;
+    AdamHyper hyper{};
+    bool has_opt = true;
+    void alloc(bool with_opt);
+    void release();
+    void set_hyper(const bb_opt_cfg& o);
+    const ParamInfo* find(const std::string& nm) const;
+    void copy_params_from(const Model& src, cudaStream_t s);
+};
+
+struct Agent {
+    int device = 0;
+    Ctx ctx;
+    bool train = false;
+    uint64_t n_opts = 0;
+    std::vector<Model*> models;  // registered VarStores by name
+    // pinned scratch for records / policy outputs
+    float* h_scratch = nullptr;
+    float* d_scratch = nullptr;
+    // multi-GPU gradient exchange: peers' gradient buffers and barrier flags mapped
+    // with CUDA IPC; the fused all-reduce + Adam kernel reads them over NVLink.
+    int rank = 0, world = 1;
+    const float* peer_grad[8] = {nullptr};
+    unsigned int* peer_flag[8] = {nullptr};  // peer_flag[r] = rank r's flag array (8 slots)
+    unsigned int* my_flags = nullptr;
+    unsigned int sync_epoch = 0;
+    const float* const* peer_grads() const { return world > 1 ? peer_grad : nullptr; }
+    void grad_sync_begin();  // all ranks' gradients complete before anyone reads them
+    void grad_sync_end();    // everyone done reading before anyone overwrites
+
+    virtual ~Agent();
+    void init_base(int dev);
+    Model* model(const std::string& name);
+    virtual void opt(Replay& rb, bb_record* rec) = 0;
+    virtual void sample(const void* obs, size_t n, void* act_out) = 0;
+    virtual Model* sync_model_src() = 0;  // which VarStore SyncModel ships (DQN qnet, SAC pi)
+    virtual void inject_noise(int slot, const float* host, size_t n);
+    virtual void grad_buffer(void** p, uint64_t* n);
+    void save_params(const char* dir);
+    void load_params(const char* dir);
+};
+
+Agent* make_dqn(const bb_dqn_cfg& cfg);
+Agent* make_sac(const bb_sac_cfg& cfg);
+Agent* make_iqn(const bb_iqn_cfg& cfg);
+
+}  // namespace bb

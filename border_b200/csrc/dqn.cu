@@ -1,0 +1,288 @@
+// dqn.cu -- Dqn agent (border-tch-agent/src/dqn/base.rs) on the device.
+//
+//   update_critic   dqn/base.rs:60-160      opt_          dqn/base.rs:182-200
+//   Policy::sample  dqn/base.rs:211-241     explorers     dqn/explorer.rs:29-31,68-90
+//   build           dqn/base.rs:255-287     SyncModel     dqn/base.rs:377-402
+//
+// One update = replay sample+gather -> Q(obs) -> target Q(next_obs) -> loss/TD kernel ->
+// backward -> fused Adam -> (PER) priority update, all enqueued on one stream with no host
+// round trip; the loss scalar is copied back only for opt_with_record.
+#include <math.h>
+#include "agent.cuh"
+
+namespace bb {
+
+struct DqnLossParams {
+    const float* q;        // [B][A] online Q(obs)
+    const float* q_tgt;    // [B][A] target Q(next_obs)
+    const float* q_next;   // [B][A] online Q(next_obs) (double DQN) or null
+    const long long* act;  // [B] (act rows are [1] i64)
+    int act_stride;        // i64 elements per act row
+    const float* reward;
+    const int8_t* term;
+    const float* weight;   // PER IS weights or null
+    float* dq;             // [B][A] out: dLoss/dQ
+    float* td;             // [B] out: |pred - tgt| (clipped), only with PER
+    float* out;            // [8] loss, pred_mean, tgt_mean, reward_mean, tgt_minus_pred_mean
+    int B, A;
+    float gamma;
+    int loss_kind, clip, double_dqn;
+    float clip_min, clip_max;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* s) {
+    __syncthreads();
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) s[threadIdx.x] += s[threadIdx.x + k];
+        __syncthreads();
+    }
+    return s[0];
+}
+
+// dqn/base.rs:71-152 after the two forwards: gather, target, loss, and the loss gradient.
+__global__ void __launch_bounds__(1024) dqn_loss_kernel(DqnLossParams p) {
+    __shared__ float s[1024];
+    float l_sum = 0.f, pred_sum = 0.f, tgt_sum = 0.f, r_sum = 0.f;
+    const float invB = 1.0f / (float)p.B;
+    for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+        const float* q = p.q + (size_t)b * p.A;
+        const float* qt = p.q_tgt + (size_t)b * p.A;
+        int a = (int)p.act[(size_t)b * p.act_stride];
+        float pred = q[a];  // x.gather(-1, act).squeeze()
+        // argmax (first maximum, as torch.argmax on CPU)
+        const float* sel = p.double_dqn ? p.q_next + (size_t)b * p.A : qt;
+        int best = 0;
+        float bv = sel[0];
+        for (int j = 1; j < p.A; ++j)
+            if (sel[j] > bv) { bv = sel[j]; best = j; }
+        float qn = qt[best];
+        // reward + (1 - is_terminated) * discount_factor * q   (dqn/base.rs:104), f32, this order
+        float nt = (float)(1 - (int)p.term[b]);
+        float tgt = __fadd_rn(p.reward[b], __fmul_rn(__fmul_rn(nt, p.gamma), qn));
+        float d = pred - tgt;
+        float dpred, l;
+        if (p.weight) {  // dqn/base.rs:123-144
+            float td = fabsf(d);
+            float gate = 1.f;
+            if (p.clip) {
+                gate = (td >= p.clip_min && td <= p.clip_max) ? 1.f : 0.f;  // clamp backward
+                td = fminf(fmaxf(td, p.clip_min), p.clip_max);
+            }
+            p.td[b] = td;
+            float w = p.weight[b];
+            float x = w * td, dx;
+            if (p.loss_kind == BB_LOSS_SMOOTH_L1) {
+                float ax = fabsf(x);
+                l = ax < 1.f ? 0.5f * x * x : ax - 0.5f;
+                dx = ax < 1.f ? x : (x > 0.f ? 1.f : -1.f);
+            } else {
+                l = x * x;
+                dx = 2.f * x;
+            }
+            float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+            dpred = dx * invB * w * gate * sgn;
+        } else {  // dqn/base.rs:146-151
+            if (p.loss_kind == BB_LOSS_SMOOTH_L1) {
+                float ad = fabsf(d);
+                l = ad < 1.f ? 0.5f * d * d : ad - 0.5f;
+                dpred = (ad < 1.f ? d : (d > 0.f ? 1.f : -1.f)) * invB;
+            } else {
+                l = d * d;
+                dpred = 2.f * d * invB;
+            }
+        }
+        float* dq = p.dq + (size_t)b * p.A;
+        for (int j = 0; j < p.A; ++j) dq[j] = (j == a) ? dpred : 0.f;
+        l_sum += l; pred_sum += pred; tgt_sum += tgt; r_sum += p.reward[b];
+    }
+    float L = block_sum(l_sum, s), P = block_sum(pred_sum, s), T = block_sum(tgt_sum, s), R = block_sum(r_sum, s);
+    if (threadIdx.x == 0) {
+        p.out[0] = L * invB; p.out[1] = P * invB; p.out[2] = T * invB; p.out[3] = R * invB;
+        p.out[4] = (T - P) * invB;
+    }
+}
+
+struct Dqn : Agent {
+    bb_dqn_cfg cfg;
+    Net net;
+    Model qnet, qnet_tgt;
+    NetWorkspace ws_online, ws_tgt, ws_act;
+    int ws_batch = 0;
+    uint64_t soft_update_counter = 0;
+    uint64_t eps_n_opts = 0;  // EpsilonGreedy.n_opts (counts sample() calls)
+    FastRand fr;
+    float* d_td = nullptr;
+    float* d_out = nullptr;
+    uint8_t* d_obs_in = nullptr;  // policy input staging
+    uint8_t* h_obs_in = nullptr;
+    float* h_q = nullptr;
+    size_t obs_in_cap = 0;
+
+    explicit Dqn(const bb_dqn_cfg& c) : cfg(c), fr(c.explorer_seed) {
+        init_base(c.device);
+        DeviceGuard g(device);
+        train = c.train != 0;
+        net.build(c.q_config, "");
+        net.init_tables(device);
+        qnet.name = "qnet"; qnet.params = net.params; qnet.n = net.n_params; qnet.alloc(true); qnet.set_hyper(c.opt_config);
+        // qnet_tgt = qnet.clone(): own VarStore AND own optimizer in the reference (never stepped)
+        qnet_tgt.name = "qnet_tgt"; qnet_tgt.params = net.params; qnet_tgt.n = net.n_params; qnet_tgt.alloc(false);
+        net.init_params(ctx, qnet.p, c.init_seed);
+        qnet_tgt.copy_params_from(qnet, ctx.stream);
+        models = {&qnet, &qnet_tgt};
+        d_td = dev_alloc<float>(65536);
+        d_out = dev_alloc_zero<float>(8, ctx.stream);
+        net.alloc_workspace(ws_act, 1, false);
+        BB_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
+    ~Dqn() override {
+        DeviceGuard g(device);
+        cudaStreamSynchronize(ctx.stream);
+        ws_online.release(); ws_tgt.release(); ws_act.release();
+        qnet.release(); qnet_tgt.release();
+        net.free_tables();
+        cudaFree(d_td); cudaFree(d_out); cudaFree(d_obs_in);
+        if (h_obs_in) cudaFreeHost(h_obs_in);
+        if (h_q) cudaFreeHost(h_q);
+    }
+    Model* sync_model_src() override { return &qnet; }
+    void grad_buffer(void** p, uint64_t* n) override { *p = qnet.g; *n = qnet.n; }
+
+    void ensure_ws(int B) {
+        if (B <= ws_batch) return;
+        BB_CUDA(cudaStreamSynchronize(ctx.stream));
+        net.alloc_workspace(ws_online, B, true);
+        net.alloc_workspace(ws_tgt, B, false);
+        ws_batch = B;
+    }
+
+    void update_critic(Replay& rb, bb_record* rec) {
+        const int B = (int)cfg.batch_size;
+        BB_CHECK(B >= 1 && B <= 65536, "batch_size out of range");
+        ensure_ws(B);
+        BB_CHECK(rb.obs_row_bytes == (uint32_t)net.in_elems * (net.u8_input ? 1u : 4u),
+                 "replay obs rows do not match the Q network input");
+        BB_CHECK(rb.cfg.act_kind == BB_I64, "DQN needs i64 action rows");
+        if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
+        bb_batch_view bv;
+        rb.sample(B, &bv);  // buffer.batch(self.batch_size), dqn/base.rs:62
+        if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
+        const long ld_in = net.in_elems;
+        const float* q = net.forward(ctx, qnet.p, bv.obs, ld_in, B, ws_online);         // :71-74
+        const float* q_next = nullptr;
+        if (cfg.double_dqn) {                                                              // :93-99
+            // online net on next_obs: borrow the target workspace first, keep its Q in d_scratch
+            const float* qn = net.forward(ctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt);
+            BB_CUDA(cudaMemcpyAsync(d_scratch, qn, (size_t)B * net.out_dim * 4, cudaMemcpyDeviceToDevice, ctx.stream));
+            q_next = d_scratch;
+        }
+        const float* qt = net.forward(ctx, qnet_tgt.p, bv.next_obs, ld_in, B, ws_tgt);   // :100-103
+        DqnLossParams lp;
+        lp.q = q; lp.q_tgt = qt; lp.q_next = q_next; lp.act = (const long long*)bv.act;
+        lp.act_stride = (int)rb.cfg.act_elems; lp.reward = bv.reward; lp.term = bv.is_terminated;
+        lp.weight = bv.weight; lp.dq = ws_online.dact.back(); lp.td = d_td; lp.out = d_out; lp.B = B;
+        lp.A = net.out_dim; lp.gamma = (float)cfg.discount_factor; lp.loss_kind = cfg.critic_loss;
+        lp.clip = cfg.clip_td_err_some; lp.clip_min = (float)cfg.clip_td_err_min; lp.clip_max = (float)cfg.clip_td_err_max;
+        lp.double_dqn = cfg.double_dqn;
+        int threads = std::min(1024, (B + 31) / 32 * 32);
+        dqn_loss_kernel<<<1, threads, 0, ctx.stream>>>(lp);
+        BB_LAUNCHED();
+        // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
+        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0);
+        qnet.step += 1;
+        grad_sync_begin();
+        adam_step(ctx, qnet.p, qnet.g, qnet.m, qnet.v, qnet.n, qnet.hyper, qnet.step, peer_grads(), world);
+        grad_sync_end();
+        if (bv.weight) {  // :142-143
+            if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
+            rb.update_priority_dev((const unsigned long long*)bv.ix_sample, d_td, B);
+        }
+        if (rec) {
+            BB_CUDA(cudaMemcpyAsync(h_scratch, d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx.stream));
+            BB_CUDA(cudaStreamSynchronize(ctx.stream));
+            rec->loss = h_scratch[0];
+            if (cfg.record_verbose_level >= 2) {
+                rec->pred_mean = h_scratch[1]; rec->tgt_mean = h_scratch[2]; rec->reward_mean = h_scratch[3];
+                rec->tgt_minus_pred_mean = h_scratch[4];
+            }
+        }
+    }
+
+    void opt(Replay& rb, bb_record* rec) override {  // opt_, dqn/base.rs:182-200
+        DeviceGuard g(device);
+        if (rec) memset(rec, 0, sizeof(*rec));
+        for (uint64_t i = 0; i < cfg.n_updates_per_opt; ++i) update_critic(rb, rec);
+        soft_update_counter += 1;
+        if (soft_update_counter == cfg.soft_update_interval) {
+            soft_update_counter = 0;
+            track(ctx, qnet_tgt.p, qnet.p, qnet.n, cfg.tau);
+        }
+        n_opts += 1;
+        if (rec) rec->n_opts = n_opts;
+    }
+
+    // Policy::sample, dqn/base.rs:211-241
+    void sample(const void* obs, size_t n, void* act_out) override {
+        DeviceGuard g(device);
+        BB_CHECK(n >= 1 && n <= 4096, "sample: n out of range");
+        size_t row = (size_t)net.in_elems * (net.u8_input ? 1 : 4);
+        if (n * row > obs_in_cap || (int)n > ws_act.max_batch) {
+            BB_CUDA(cudaStreamSynchronize(ctx.stream));
+            cudaFree(d_obs_in);
+            if (h_obs_in) cudaFreeHost(h_obs_in);
+            if (h_q) cudaFreeHost(h_q);
+            obs_in_cap = n * row;
+            d_obs_in = dev_alloc<uint8_t>(obs_in_cap);
+            BB_CUDA(cudaMallocHost(&h_obs_in, obs_in_cap));
+            BB_CUDA(cudaMallocHost(&h_q, n * net.out_dim * sizeof(float)));
+            net.alloc_workspace(ws_act, (int)n, false);
+        }
+        memcpy(h_obs_in, obs, n * row);
+        BB_CUDA(cudaMemcpyAsync(d_obs_in, h_obs_in, n * row, cudaMemcpyHostToDevice, ctx.stream));
+        const float* q = net.forward(ctx, qnet.p, d_obs_in, net.in_elems, (int)n, ws_act);
+        BB_CUDA(cudaMemcpyAsync(h_q, q, n * net.out_dim * sizeof(float), cudaMemcpyDeviceToHost, ctx.stream));
+        BB_CUDA(cudaStreamSynchronize(ctx.stream));
+        int64_t* out = (int64_t*)act_out;
+        const int A = net.out_dim;
+        auto argmax = [&](size_t i) {
+            int best = 0;
+            for (int j = 1; j < A; ++j)
+                if (h_q[i * A + j] > h_q[i * A + best]) best = j;
+            return (int64_t)best;
+        };
+        if (train) {
+            if (cfg.explorer == BB_EXPLORER_EPS_GREEDY) {  // dqn/explorer.rs:68-90
+                double d = (cfg.eps_start - cfg.eps_final) / (double)cfg.final_step;
+                double eps = std::max(cfg.eps_start - d * (double)eps_n_opts, cfg.eps_final);
+                double r = fr.f64();
+                bool is_random = r < eps;
+                eps_n_opts += 1;
+                for (size_t i = 0; i < n; ++i) out[i] = is_random ? (int64_t)fr.u32_below((uint32_t)A) : argmax(i);
+            } else {  // Softmax: a.softmax(-1).multinomial(1)  (dqn/explorer.rs:29-31); inverse CDF on fastrand
+                for (size_t i = 0; i < n; ++i) {
+                    float mx = h_q[i * A];
+                    for (int j = 1; j < A; ++j) mx = std::max(mx, h_q[i * A + j]);
+                    double z = 0;
+                    for (int j = 0; j < A; ++j) z += exp((double)(h_q[i * A + j] - mx));
+                    double u = fr.f64() * z, acc = 0;
+                    int pick = A - 1;
+                    for (int j = 0; j < A; ++j) {
+                        acc += exp((double)(h_q[i * A + j] - mx));
+                        if (u < acc) { pick = j; break; }
+                    }
+                    out[i] = pick;
+                }
+            }
+        } else {  // eval: 1 % random actions (dqn/base.rs:229-236)
+            for (size_t i = 0; i < n; ++i) {
+                if (fr.f32() < 0.01f) out[i] = (int64_t)fr.u64_below((uint64_t)A);
+                else out[i] = argmax(i);
+            }
+        }
+    }
+};
+
+Agent* make_dqn(const bb_dqn_cfg& cfg) { return new Dqn(cfg); }
+}  // namespace bb

@@ -1,0 +1,550 @@
+// nn.cu -- see nn.cuh.  Layer primitives on top of gemm.cuh plus the elementwise kernels
+// (col2im, column sums, fused Adam, Polyak update, init).
+#include <math.h>
+#include <algorithm>
+#include "gemm.cuh"
+#include "nn.cuh"
+
+namespace bb {
+
+// ------------------------------------------------------------------------------- split-K reduce
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
+                                     int splits, const float* __restrict__ bias, int relu,
+                                     const float* __restrict__ mask) {
+    size_t total = (size_t)M * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int m = (int)(i / N), n = (int)(i % N);
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += ws[(size_t)z * total + i];
+        if (bias) s += bias[n];
+        if (relu) s = fmaxf(s, 0.f);
+        if (mask) s = mask[(size_t)m * ldc + n] > 0.f ? s : 0.f;
+        C[(size_t)m * ldc + n] = s;
+    }
+}
+
+enum GemmMode { G_FWD = 0, G_FWD_U8, G_NN, G_WGRAD, G_WGRAD_U8 };
+
+template <int BM, int BN, int TM, int TN>
+static void launch_cfg(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
+    switch (mode) {
+        case G_FWD: gemm_kernel<BM, BN, TM, TN, true, true, false, false><<<grid, 256, 0, s>>>(a); break;
+        case G_FWD_U8: gemm_kernel<BM, BN, TM, TN, true, true, true, false><<<grid, 256, 0, s>>>(a); break;
+        case G_NN: gemm_kernel<BM, BN, TM, TN, true, false, false, false><<<grid, 256, 0, s>>>(a); break;
+        case G_WGRAD: gemm_kernel<BM, BN, TM, TN, false, false, false, false><<<grid, 256, 0, s>>>(a); break;
+        case G_WGRAD_U8: gemm_kernel<BM, BN, TM, TN, false, false, false, true><<<grid, 256, 0, s>>>(a); break;
+    }
+    BB_LAUNCHED();
+}
+
+static void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
+    if (a.M <= 0 || a.N <= 0) return;
+    int BM, BN, cfg;
+    if (a.N <= 32) { cfg = 1; BM = 128; BN = 32; }
+    else if (a.M <= 32) { cfg = 2; BM = 32; BN = 128; }
+    else { cfg = 0; BM = 64; BN = 64; }
+    int tm = (a.M + BM - 1) / BM, tn = (a.N + BN - 1) / BN;
+    long tiles = (long)tm * tn;
+    int split = 1;
+    int kt = (a.K + kBK - 1) / kBK;  // k tiles
+    if (tiles < c.sms && kt >= 8) {
+        split = (int)std::min<long>((2L * c.sms + tiles - 1) / tiles, kt / 4);
+        size_t per = (size_t)a.M * a.N;
+        if (per * split > c.ws_floats) split = (int)(c.ws_floats / per);
+        if (split < 1) split = 1;
+    }
+    int kps = ((kt + split - 1) / split) * kBK;
+    split = (a.K + kps - 1) / kps;
+    a.split_k = split;
+    a.k_per_split = kps;
+    a.workspace = c.ws;
+    dim3 grid(tn, tm, split);
+    switch (cfg) {
+        case 0: launch_cfg<64, 64, 4, 4>(mode, a, grid, c.stream); break;
+        case 1: launch_cfg<128, 32, 4, 4>(mode, a, grid, c.stream); break;
+        case 2: launch_cfg<32, 128, 4, 4>(mode, a, grid, c.stream); break;
+    }
+    if (split > 1) {
+        size_t total = (size_t)a.M * a.N;
+        int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
+        splitk_reduce_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+        BB_LAUNCHED();
+    }
+}
+
+static GemmArgs zero_args() {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.split_k = 1;
+    return a;
+}
+
+// ------------------------------------------------------------------------------- column sums
+
+__global__ void colsum_partial_kernel(const float* __restrict__ Y, float* __restrict__ part, int M, int N,
+                                      int rows_per_block) {
+    __shared__ float s[8][33];
+    int n = blockIdx.x * 32 + threadIdx.x;
+    int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float acc = 0.f;
+    if (n < N)
+        for (int m = r0 + threadIdx.y; m < r1; m += 8) acc += Y[(size_t)m * N + n];
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x];
+        part[(size_t)blockIdx.y * N + n] = t;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int N, int R) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float t = 0.f;
+    for (int r = 0; r < R; ++r) t += part[(size_t)r * N + n];
+    out[n] = t;
+}
+
+void colsum(const Ctx& c, const float* dY, float* db, int M, int N) {
+    int R = std::max(1, std::min(256, (M + 63) / 64));
+    while ((size_t)R * N > c.ws_floats && R > 1) R /= 2;
+    int rpb = (M + R - 1) / R;
+    R = (M + rpb - 1) / rpb;
+    colsum_partial_kernel<<<dim3((N + 31) / 32, R), dim3(32, 8), 0, c.stream>>>(dY, c.ws, M, N, rpb);
+    BB_LAUNCHED();
+    colsum_final_kernel<<<(N + 127) / 128, 128, 0, c.stream>>>(c.ws, db, N, R);
+    BB_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------- linear
+
+void linear_fwd(const Ctx& c, const float* X, long ldx, const float* W, const float* b, float* Y, int M, int N, int K,
+                bool relu) {
+    GemmArgs a = zero_args();
+    a.A = X; a.lda = ldx; a.B = W; a.ldb = K; a.C = Y; a.ldc = N; a.M = M; a.N = N; a.K = K;
+    a.bias = b; a.relu = relu;
+    gemm(c, G_FWD, a);
+}
+
+void linear_bwd_data(const Ctx& c, const float* dY, const float* W, float* dX, long lddx, int M, int N, int K,
+                     const float* mask) {
+    // dX[M][K] = dY[M][N] * W[N][K]
+    GemmArgs a = zero_args();
+    a.A = dY; a.lda = N; a.B = W; a.ldb = K; a.C = dX; a.ldc = (int)lddx; a.M = M; a.N = K; a.K = N;
+    a.mask = mask;
+    gemm(c, G_NN, a);
+}
+
+void linear_bwd_weight(const Ctx& c, const float* dY, const float* X, long ldx, float* dW, float* db, int M, int N,
+                       int K) {
+    // dW[N][K] = sum_m dY[m][N]^T X[m][K]
+    GemmArgs a = zero_args();
+    a.A = dY; a.lda = N; a.B = X; a.ldb = ldx; a.C = dW; a.ldc = K; a.M = N; a.N = K; a.K = M;
+    gemm(c, G_WGRAD, a);
+    if (db) colsum(c, dY, db, M, N);
+}
+
+// ------------------------------------------------------------------------------- conv
+
+void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu) {
+    GemmArgs a = zero_args();
+    a.A = X; a.a_rowbase = g.rowbase; a.a_koff = g.koff; a.B = W; a.ldb = g.K(); a.C = Y; a.ldc = g.OC;
+    a.M = g.M(); a.N = g.OC; a.K = g.K(); a.bias = b; a.relu = relu;
+    gemm(c, g.u8_chw ? G_FWD_U8 : G_FWD, a);
+}
+
+void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW, float* db) {
+    // dW[OC][K] = sum_m dY[m][OC]^T im2col(X)[m][K]
+    GemmArgs a = zero_args();
+    a.A = dY; a.lda = g.OC; a.B = X; a.b_rowbase = g.rowbase; a.b_noff = g.koff; a.C = dW; a.ldc = g.K();
+    a.M = g.OC; a.N = g.K(); a.K = g.M();
+    gemm(c, g.u8_chw ? G_WGRAD_U8 : G_WGRAD, a);
+    if (db) colsum(c, dY, db, g.M(), g.OC);
+}
+
+// dX[b][h][w][c] = sum over the kernel taps that touch (h, w) of col[(b,oh,ow)][(kh,kw,c)]
+__global__ void col2im_nhwc_kernel(const float* __restrict__ col, float* __restrict__ dX, const float* __restrict__ mask,
+                                   int B, int C, int H, int W, int KH, int KW, int S, int OH, int OW) {
+    const int C4 = C / 4;
+    size_t total = (size_t)B * H * W * C4;
+    const int K = KH * KW * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4);
+        size_t t = i / C4;
+        int w = (int)(t % W); t /= W;
+        int h = (int)(t % H);
+        int b = (int)(t / H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kh = h % S; kh < KH; kh += S) {
+            int oh = (h - kh) / S;
+            if (h - kh < 0 || oh >= OH) continue;
+            for (int kw = w % S; kw < KW; kw += S) {
+                int ow = (w - kw) / S;
+                if (w - kw < 0 || ow >= OW) continue;
+                size_t m = ((size_t)b * OH + oh) * OW + ow;
+                float4 v = __ldg(reinterpret_cast<const float4*>(col + m * K + (kh * KW + kw) * C) + c4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        size_t o = (((size_t)b * H + h) * W + w) * C + c4 * 4;
+        if (mask) {
+            float4 mk = __ldg(reinterpret_cast<const float4*>(mask + o));
+            acc.x = mk.x > 0.f ? acc.x : 0.f; acc.y = mk.y > 0.f ? acc.y : 0.f;
+            acc.z = mk.z > 0.f ? acc.z : 0.f; acc.w = mk.w > 0.f ? acc.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(dX + o) = acc;
+    }
+}
+
+void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float* W, float* col, float* dX,
+                   const float* mask) {
+    BB_CHECK(!g.u8_chw && g.C % 4 == 0, "conv_bwd_data expects an NHWC float input with C % 4 == 0");
+    GemmArgs a = zero_args();
+    a.A = dY; a.lda = g.OC; a.B = W; a.ldb = g.K(); a.C = col; a.ldc = g.K(); a.M = g.M(); a.N = g.K(); a.K = g.OC;
+    gemm(c, G_NN, a);
+    size_t total = (size_t)g.B * g.H * g.W * (g.C / 4);
+    int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 16);
+    col2im_nhwc_kernel<<<blocks, 256, 0, c.stream>>>(col, dX, mask, g.B, g.C, g.H, g.W, g.KH, g.KW, g.S, g.OH, g.OW);
+    BB_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------- Adam / track
+
+struct PeerPtrs { const float* p[8]; };
+
+// torch::optim::Adam::step (what tch's nn::Adam binds, opt.rs:35,77):
+//   m = m*b1 + (1-b1) g ; v = v*b2 + (1-b2) g*g ; denom = sqrt(v)/sqrt(1-b2^t) + eps ;
+//   p = p - lr/(1-b1^t) * m/denom.     AdamW: p *= (1 - lr*wd) first; Adam: g += wd*p.
+// With world > 1 the gradient is the mean over the ranks' buffers read through peer pointers
+// (NVLink P2P loads): all-reduce and optimizer step in one kernel, no parameter broadcast needed.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float b1, float b2, float one_m_b1, float one_m_b2,
+                            float eps, float bc2_sqrt, float neg_step, float wd, float decay, int adamw,
+                            PeerPtrs peers, int world) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float gi;
+        if (world > 1) {
+            gi = 0.f;
+            for (int r = 0; r < world; ++r) gi += peers.p[r][i];
+            gi = gi / (float)world;
+        } else {
+            gi = g[i];
+        }
+        float pi = p[i];
+        if (adamw) pi = pi * decay;
+        else if (wd != 0.f) gi = gi + wd * pi;
+        float mi = m[i] * b1 + one_m_b1 * gi;
+        float vi = v[i] * b2 + one_m_b2 * gi * gi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi = pi + neg_step * (mi / denom);
+        m[i] = mi; v[i] = vi; p[i] = pi;
+    }
+}
+
+void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
+               uint64_t step, const float* const* peer_grads, int world) {
+    double bc1 = 1.0 - pow(h.beta1, (double)step);
+    double bc2 = 1.0 - pow(h.beta2, (double)step);
+    double step_size = h.lr / bc1;
+    PeerPtrs pp;
+    for (int r = 0; r < 8; ++r) pp.p[r] = (peer_grads && r < world) ? peer_grads[r] : nullptr;
+    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)c.sms * 8);
+    adam_kernel<<<blocks, 256, 0, c.stream>>>(p, g, m, v, n, (float)h.beta1, (float)h.beta2, (float)(1.0 - h.beta1),
+                                              (float)(1.0 - h.beta2), (float)h.eps, (float)sqrt(bc2),
+                                              (float)(-step_size), (float)h.wd, (float)(1.0 - h.lr * h.wd),
+                                              h.adamw ? 1 : 0, pp, peer_grads ? world : 1);
+    BB_LAUNCHED();
+}
+
+__global__ void track_kernel(float* __restrict__ dest, const float* __restrict__ src, size_t n, float tau,
+                             float one_m_tau) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dest[i] = __fadd_rn(__fmul_rn(tau, src[i]), __fmul_rn(one_m_tau, dest[i]));
+}
+void track(const Ctx& c, float* dest, const float* src, size_t n, double tau) {
+    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)c.sms * 8);
+    track_kernel<<<blocks, 256, 0, c.stream>>>(dest, src, n, (float)tau, (float)(1.0 - tau));
+    BB_LAUNCHED();
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void fill_uniform_kernel(float* p, size_t n, float bound, unsigned long long seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float u = (float)(uint32_t)(mix64(seed + i) >> 40) * (1.0f / 16777216.0f);
+        p[i] = (2.f * u - 1.f) * bound;
+    }
+}
+__global__ void fill_const_kernel(float* p, size_t n, float v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void fill_uniform(const Ctx& c, float* p, size_t n, float bound, uint64_t seed) {
+    if (!n) return;
+    fill_uniform_kernel<<<(int)std::min<size_t>((n + 255) / 256, 1024), 256, 0, c.stream>>>(p, n, bound, seed);
+    BB_LAUNCHED();
+}
+void fill_const(const Ctx& c, float* p, size_t n, float v) {
+    if (!n) return;
+    fill_const_kernel<<<(int)std::min<size_t>((n + 255) / 256, 1024), 256, 0, c.stream>>>(p, n, v);
+    BB_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------- Net
+
+void NetWorkspace::release() {
+    for (auto p : act) cudaFree(p);
+    for (auto p : dact) cudaFree(p);
+    for (auto p : rowbase) cudaFree(p);
+    cudaFree(col);
+    act.clear(); dact.clear(); rowbase.clear(); col = nullptr;
+}
+
+static void add_param(Net& n, const std::string& name, std::vector<int64_t> shape, int perm, int pc, int ph, int pw,
+                      int fan_in) {
+    ParamInfo pi;
+    pi.name = name; pi.shape = shape; pi.offset = n.n_params; pi.perm = perm; pi.pc = pc; pi.ph = ph; pi.pw = pw;
+    pi.fan_in = fan_in;
+    pi.numel = 1;
+    for (auto d : shape) pi.numel *= (size_t)d;
+    n.n_params += (pi.numel + 3) / 4 * 4;  // keep every tensor 16 B aligned
+    n.params.push_back(pi);
+}
+
+static void add_linear(Net& n, const std::string& name, int in, int out, bool relu, int perm = 0, int pc = 0, int ph = 0,
+                       int pw = 0) {
+    Layer l{};
+    l.type = 0; l.in_dim = in; l.out_dim = out; l.relu = relu; l.out_elems_per_sample = out;
+    l.w_off = n.n_params;
+    add_param(n, name + ".weight", {out, in}, perm, pc, ph, pw, in);
+    l.b_off = n.n_params;
+    add_param(n, name + ".bias", {out}, 0, 0, 0, 0, in);
+    n.layers.push_back(l);
+}
+
+static void add_conv(Net& n, const std::string& name, int C, int H, int W, int OC, int k, int s, bool u8) {
+    Layer l{};
+    l.type = 1; l.relu = true;
+    ConvGeom& g = l.geom;
+    g.B = 0; g.C = C; g.H = H; g.W = W; g.OC = OC; g.KH = k; g.KW = k; g.S = s;
+    g.OH = (H - k) / s + 1; g.OW = (W - k) / s + 1; g.u8_chw = u8; g.rowbase = nullptr; g.koff = nullptr;
+    l.out_elems_per_sample = (size_t)g.OH * g.OW * OC;
+    l.w_off = n.n_params;
+    add_param(n, name + ".weight", {OC, C, k, k}, u8 ? 0 : 1, C, k, k, C * k * k);
+    l.b_off = n.n_params;
+    add_param(n, name + ".bias", {OC}, 0, 0, 0, 0, C * k * k);
+    n.layers.push_back(l);
+}
+
+void Net::build(const bb_net_cfg& cfg, const std::string& prefix) {
+    layers.clear(); params.clear(); n_params = 0;
+    if (cfg.kind == BB_NET_ATARI_CNN) {  // cnn/base.rs:23-48
+        u8_input = true;
+        in_elems = cfg.n_stack * 84 * 84;
+        add_conv(*this, prefix + "c1", cfg.n_stack, 84, 84, 32, 8, 4, true);
+        add_conv(*this, prefix + "c2", 32, 20, 20, 64, 4, 2, false);
+        add_conv(*this, prefix + "c3", 64, 9, 9, 64, 3, 1, false);
+        if (!cfg.skip_linear) {
+            add_linear(*this, prefix + "l1", 3136, 512, true, 2, 64, 7, 7);
+            add_linear(*this, prefix + "l2", 512, cfg.out_dim, false);
+            out_dim = cfg.out_dim;
+        } else {
+            out_dim = 3136;
+        }
+    } else if (cfg.kind == BB_NET_MLP) {  // mlp/base.rs:13-41, var names mlp.ln{i}
+        u8_input = false;
+        in_elems = cfg.in_dim;
+        int in = cfg.in_dim;
+        BB_CHECK(cfg.n_units >= 0 && cfg.n_units <= 8, "MlpConfig.units: at most 8 hidden layers");
+        for (int i = 0; i < cfg.n_units; ++i) {
+            add_linear(*this, prefix + "mlp.ln" + std::to_string(i), in, cfg.units[i], true);
+            in = cfg.units[i];
+        }
+        add_linear(*this, prefix + "mlp.ln" + std::to_string(cfg.n_units), in, cfg.out_dim, cfg.activation_out != 0);
+        out_dim = cfg.out_dim;
+    } else {
+        throw Error("unknown network kind");
+    }
+}
+
+void Net::init_tables(int device) {
+    (void)device;
+    free_tables();
+    for (auto& l : layers) {
+        if (l.type != 1) continue;
+        ConvGeom& g = l.geom;
+        std::vector<int> h(g.K());
+        if (g.u8_chw) {
+            for (int c = 0; c < g.C; ++c)
+                for (int kh = 0; kh < g.KH; ++kh)
+                    for (int kw = 0; kw < g.KW; ++kw) h[(c * g.KH + kh) * g.KW + kw] = c * g.H * g.W + kh * g.W + kw;
+        } else {
+            for (int kh = 0; kh < g.KH; ++kh)
+                for (int kw = 0; kw < g.KW; ++kw)
+                    for (int c = 0; c < g.C; ++c) h[(kh * g.KW + kw) * g.C + c] = (kh * g.W + kw) * g.C + c;
+        }
+        int* d = dev_alloc<int>(h.size());
+        BB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+        koff.push_back(d);
+        g.koff = d;
+    }
+}
+
+void Net::free_tables() {
+    for (auto p : koff) cudaFree(p);
+    koff.clear();
+}
+
+void Net::alloc_workspace(NetWorkspace& w, int max_batch, bool with_grad) const {
+    w.release();
+    w.max_batch = max_batch;
+    w.with_grad = with_grad;
+    size_t col = 0;
+    for (size_t i = 0; i < layers.size(); ++i) {
+        const Layer& l = layers[i];
+        size_t n = (size_t)max_batch * l.out_elems_per_sample;
+        w.act.push_back(dev_alloc<float>(n));
+        w.dact.push_back(with_grad ? dev_alloc<float>(n) : nullptr);
+        if (l.type == 1) {
+            const ConvGeom& g = l.geom;
+            size_t M = (size_t)max_batch * g.OH * g.OW;
+            BB_CHECK(M * 4 < (1ull << 31) && (size_t)max_batch * g.C * g.H * g.W < (1ull << 31), "batch too large for int32 gather tables");
+            std::vector<int> h(M);
+            for (int b = 0; b < max_batch; ++b)
+                for (int oh = 0; oh < g.OH; ++oh)
+                    for (int ow = 0; ow < g.OW; ++ow) {
+                        size_t m = ((size_t)b * g.OH + oh) * g.OW + ow;
+                        h[m] = g.u8_chw ? b * g.C * g.H * g.W + oh * g.S * g.W + ow * g.S
+                                        : ((b * g.H + oh * g.S) * g.W + ow * g.S) * g.C;
+                    }
+            int* d = dev_alloc<int>(M);
+            BB_CUDA(cudaMemcpy(d, h.data(), M * sizeof(int), cudaMemcpyHostToDevice));
+            w.rowbase.push_back(d);
+            if (with_grad && i > 0) col = std::max(col, M * (size_t)g.K());
+        } else {
+            w.rowbase.push_back(nullptr);
+        }
+    }
+    w.col_floats = col;
+    w.col = col ? dev_alloc<float>(col) : nullptr;
+}
+
+void Net::init_params(const Ctx& c, float* p, uint64_t seed) const {
+    // tch defaults: weights Kaiming-uniform(fan_in, ReLU gain) = U(+-sqrt(6/fan_in)); linear bias
+    // U(+-1/sqrt(fan_in)); conv bias 0.  (The reference draws from libtorch's global generator, so
+    // initial weights are never reproducible across implementations: parity tests load weights.)
+    fill_const(c, p, n_params, 0.f);
+    for (size_t i = 0; i < params.size(); ++i) {
+        const ParamInfo& pi = params[i];
+        bool is_w = pi.shape.size() > 1;
+        bool conv = pi.shape.size() == 4;
+        if (is_w) fill_uniform(c, p + pi.offset, pi.numel, sqrtf(6.0f / (float)pi.fan_in), seed * 1315423911ull + i * 0x51ed27ull);
+        else if (!conv && !(i > 0 && params[i - 1].shape.size() == 4))
+            fill_uniform(c, p + pi.offset, pi.numel, 1.0f / sqrtf((float)pi.fan_in), seed * 1315423911ull + i * 0x51ed27ull);
+    }
+}
+
+const float* Net::forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w) const {
+    BB_CHECK(B <= w.max_batch, "batch larger than the workspace");
+    const void* x = input;
+    long ldx = ld_in;
+    for (size_t i = 0; i < layers.size(); ++i) {
+        const Layer& l = layers[i];
+        if (l.type == 1) {
+            ConvGeom g = l.geom;
+            g.B = B; g.rowbase = w.rowbase[i];
+            conv_fwd(c, g, x, p + l.w_off, p + l.b_off, w.act[i], l.relu);
+        } else {
+            linear_fwd(c, (const float*)x, ldx, p + l.w_off, p + l.b_off, w.act[i], B, l.out_dim, l.in_dim, l.relu);
+        }
+        x = w.act[i];
+        ldx = (long)l.out_elems_per_sample;
+    }
+    return w.act.back();
+}
+
+__global__ void relu_mask_kernel(float* __restrict__ d, const float* __restrict__ y, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = y[i] > 0.f ? d[i] : 0.f;
+}
+
+void Net::backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
+                   float* d_input, long ld_din) const {
+    BB_CHECK(w.with_grad, "workspace was allocated without gradient buffers");
+    int L = (int)layers.size();
+    // d(output) arrives in w.dact[L-1] as the gradient wrt the post-activation output
+    if (layers[L - 1].relu) {
+        size_t n = (size_t)B * layers[L - 1].out_elems_per_sample;
+        relu_mask_kernel<<<(int)std::min<size_t>((n + 255) / 256, (size_t)c.sms * 8), 256, 0, c.stream>>>(w.dact[L - 1], w.act[L - 1], n);
+        BB_LAUNCHED();
+    }
+    for (int i = L - 1; i >= 0; --i) {
+        const Layer& l = layers[i];
+        const void* x = i ? (const void*)w.act[i - 1] : input;
+        long ldx = i ? (long)layers[i - 1].out_elems_per_sample : ld_in;
+        float* dx = i ? w.dact[i - 1] : d_input;
+        long lddx = i ? (long)layers[i - 1].out_elems_per_sample : ld_din;
+        // the mask folds the previous layer's ReLU backward into this layer's data-grad epilogue
+        const float* mask = (i && layers[i - 1].relu) ? w.act[i - 1] : nullptr;
+        if (l.type == 1) {
+            ConvGeom cg = l.geom;
+            cg.B = B; cg.rowbase = w.rowbase[i];
+            conv_bwd_weight(c, cg, w.dact[i], x, g + l.w_off, g + l.b_off);
+            if (dx) conv_bwd_data(c, cg, w.dact[i], p + l.w_off, w.col, dx, mask);
+        } else {
+            linear_bwd_weight(c, w.dact[i], (const float*)x, ldx, g + l.w_off, g + l.b_off, B, l.out_dim, l.in_dim);
+            if (dx) linear_bwd_data(c, w.dact[i], p + l.w_off, dx, lddx, B, l.out_dim, l.in_dim, mask);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- layout conversion
+
+void param_to_internal(const ParamInfo& pi, const float* ref, float* internal) {
+    if (pi.perm == 1) {  // OIHW -> O(HWI)
+        int O = (int)pi.shape[0], I = pi.pc, H = pi.ph, W = pi.pw;
+        for (int o = 0; o < O; ++o)
+            for (int i = 0; i < I; ++i)
+                for (int h = 0; h < H; ++h)
+                    for (int w = 0; w < W; ++w)
+                        internal[((size_t)(o * H + h) * W + w) * I + i] = ref[((size_t)(o * I + i) * H + h) * W + w];
+    } else if (pi.perm == 2) {  // [out][C*H*W] -> [out][H*W*C]
+        int O = (int)pi.shape[0], C = pi.pc, H = pi.ph, W = pi.pw;
+        size_t in = (size_t)C * H * W;
+        for (int o = 0; o < O; ++o)
+            for (int ch = 0; ch < C; ++ch)
+                for (int h = 0; h < H; ++h)
+                    for (int w = 0; w < W; ++w)
+                        internal[o * in + ((size_t)h * W + w) * C + ch] = ref[o * in + ((size_t)ch * H + h) * W + w];
+    } else {
+        std::copy(ref, ref + pi.numel, internal);
+    }
+}
+
+void param_to_reference(const ParamInfo& pi, const float* internal, float* ref) {
+    if (pi.perm == 1) {
+        int O = (int)pi.shape[0], I = pi.pc, H = pi.ph, W = pi.pw;
+        for (int o = 0; o < O; ++o)
+            for (int i = 0; i < I; ++i)
+                for (int h = 0; h < H; ++h)
+                    for (int w = 0; w < W; ++w)
+                        ref[((size_t)(o * I + i) * H + h) * W + w] = internal[((size_t)(o * H + h) * W + w) * I + i];
+    } else if (pi.perm == 2) {
+        int O = (int)pi.shape[0], C = pi.pc, H = pi.ph, W = pi.pw;
+        size_t in = (size_t)C * H * W;
+        for (int o = 0; o < O; ++o)
+            for (int ch = 0; ch < C; ++ch)
+                for (int h = 0; h < H; ++h)
+                    for (int w = 0; w < W; ++w)
+                        ref[o * in + ((size_t)ch * H + h) * W + w] = internal[o * in + ((size_t)h * W + w) * C + ch];
+    } else {
+        std::copy(internal, internal + pi.numel, ref);
+    }
+}
+
+}  // namespace bb

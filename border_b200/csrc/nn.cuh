@@ -1,0 +1,126 @@
+// nn.cuh -- layer primitives (linear / conv2d forward, data-grad, weight-grad), fused Adam,
+// Polyak update and the Net container that mirrors border-tch-agent's SubModels.
+//
+// Reference: AtariCnn border-tch-agent/src/cnn/base.rs:23-48, Mlp mlp/base.rs:13-41,
+// Optimizer::backward_step opt.rs:74-83 (tch nn::Adam / AdamW = torch::optim::Adam[W]),
+// track util.rs:31-45.
+//
+// Internal layouts (device): activations NHWC ([B*OH*OW][C] row-major matrices), conv weights
+// [OC][KH][KW][IC] (c1, which reads the u8 CHW frame stack straight from the replay batch, keeps
+// the reference's [OC][IC][KH][KW]), linear weights [out][in]; the first linear after the conv
+// stack has its input columns permuted from the reference's (c,h,w) flat_view order to (h,w,c).
+// Import/export (get_param/set_param, checkpoints, SyncModel) convert to/from the reference layout.
+#pragma once
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "../../include/border_b200.h"
+
+namespace bb {
+
+struct Ctx {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    float* ws = nullptr;  // split-K / reduction workspace
+    size_t ws_floats = 0;
+};
+
+// ---- primitives (all row-major fp32) -------------------------------------------------------
+// Y[M][N] = act(X[M][K] W[N][K]^T + b)
+void linear_fwd(const Ctx& c, const float* X, long ldx, const float* W, const float* b, float* Y, int M, int N, int K,
+                bool relu);
+// dX[M][K] = (dY[M][N] W[N][K]) * (mask > 0)
+void linear_bwd_data(const Ctx& c, const float* dY, const float* W, float* dX, long lddx, int M, int N, int K,
+                     const float* mask);
+// dW[N][K] = dY^T X ; db[N] = colsum(dY)
+void linear_bwd_weight(const Ctx& c, const float* dY, const float* X, long ldx, float* dW, float* db, int M, int N,
+                       int K);
+void colsum(const Ctx& c, const float* dY, float* db, int M, int N);
+
+struct ConvGeom {
+    int B, C, H, W, OC, KH, KW, S, OH, OW;
+    bool u8_chw;         // input is the u8 [B][C][H][W] frame stack (scaled by 1/255 on load)
+    const int* rowbase;  // [B*OH*OW] device
+    const int* koff;     // [K] device
+    int M() const { return B * OH * OW; }
+    int K() const { return C * KH * KW; }
+};
+void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu);
+void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW, float* db);
+// dX[B][H][W][C] = col2im(dY W) * (mask > 0); `col` is [M][K] scratch
+void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float* W, float* col, float* dX,
+                   const float* mask);
+
+// torch::optim::Adam / AdamW step over a flat parameter vector (one launch).
+struct AdamHyper {
+    double lr, beta1, beta2, eps, wd;
+    bool adamw;
+};
+void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
+               uint64_t step /* 1-based */, const float* const* peer_grads = nullptr, int world = 1);
+// dest = tau*src + (1-tau)*dest  (util.rs:43)
+void track(const Ctx& c, float* dest, const float* src, size_t n, double tau);
+void fill_uniform(const Ctx& c, float* p, size_t n, float bound, uint64_t seed);
+void fill_const(const Ctx& c, float* p, size_t n, float v);
+
+// ---- Net -----------------------------------------------------------------------------------
+
+struct ParamInfo {
+    std::string name;            // tch VarStore name, e.g. "c1.weight", "mlp.ln0.bias"
+    std::vector<int64_t> shape;  // reference shape
+    size_t offset, numel;        // into the flat parameter vector (internal layout)
+    int perm;                    // 0 none, 1 conv OIHW<->OHWI, 2 linear [out][C,H,W]<->[out][H,W,C]
+    int pc, ph, pw;              // dims for the permutation
+    int fan_in;
+};
+
+struct Layer {
+    int type;  // 0 linear, 1 conv
+    int in_dim, out_dim;  // linear
+    ConvGeom geom;        // conv (B, rowbase filled per workspace)
+    bool relu;
+    size_t w_off, b_off;
+    size_t out_elems_per_sample;
+};
+
+// Per-(net, max batch) device buffers: activations, activation grads, col scratch, gather tables.
+struct NetWorkspace {
+    int max_batch = 0;
+    bool with_grad = false;
+    std::vector<float*> act;    // output of each layer [B][out]
+    std::vector<float*> dact;   // grad wrt output of each layer
+    std::vector<int*> rowbase;  // per conv layer
+    float* col = nullptr;
+    size_t col_floats = 0;
+    void release();
+};
+
+class Net {
+  public:
+    Net() = default;
+    void build(const bb_net_cfg& cfg, const std::string& prefix);  // prefix: "" or "mlp."
+    size_t n_params = 0;
+    int in_elems = 0, out_dim = 0;
+    bool u8_input = false;
+    std::vector<Layer> layers;
+    std::vector<ParamInfo> params;
+    std::vector<int*> koff;  // per conv layer (device), shared by all workspaces
+
+    void init_tables(int device);
+    void alloc_workspace(NetWorkspace& w, int max_batch, bool with_grad) const;
+    void init_params(const Ctx& c, float* p, uint64_t seed) const;
+    // forward: input [B][in] (u8 CHW frames or float rows); returns ws.act.back()
+    const float* forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w) const;
+    // backward from d(output) in w.dact.back(); accumulates nothing: grads are overwritten.
+    // d_input (may be null) receives the gradient wrt a float input [B][in].
+    void backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
+                  float* d_input, long ld_din) const;
+    void free_tables();
+};
+
+// reference layout <-> internal layout of one parameter tensor (host side)
+void param_to_internal(const ParamInfo& pi, const float* ref, float* internal);
+void param_to_reference(const ParamInfo& pi, const float* internal, float* ref);
+
+}  // namespace bb

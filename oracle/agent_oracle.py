@@ -1,0 +1,197 @@
+"""CPU restatement of border-tch-agent's agents with the same ATen ops in the same order.
+
+TEST INFRASTRUCTURE ONLY: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module, as the checker / CPU baseline.  The product never does.
+
+The reference's arithmetic lives in libtorch, reached through tch 0.16 (not under
+/root/reference); this file calls the same operators through Python torch (fp32, CPU):
+  AtariCnn            border-tch-agent/src/cnn/base.rs:23-36
+  Mlp / Mlp2          border-tch-agent/src/mlp/base.rs:13-41, mlp/mlp2.rs:23-50
+  Dqn::update_critic  border-tch-agent/src/dqn/base.rs:60-160, opt_ :182-200
+  Optimizer           border-tch-agent/src/opt.rs:74-83 -> torch::optim::Adam (C++ frontend form)
+  track               border-tch-agent/src/util.rs:31-45
+  Sac                 border-tch-agent/src/sac/base.rs:73-198, ent_coef.rs:27-75
+  Iqn                 border-tch-agent/src/iqn/base.rs:63-170, iqn/model/base.rs:162-234,
+                      util/quantile_loss.rs:7-12
+Parity pinning: the reference holds no golden vectors for these paths, so
+the numerics are "parity unpinned" against Rust-tch itself; they are pinned by construction to
+the ATen operators tch binds.  The C++-frontend Adam is restated op by op below because Python's
+torch.optim.Adam uses a different (lerp / fused) formulation.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------ models
+
+def atari_cnn_params(n_stack, out_dim, gen, skip_linear=False):
+    """Named tensors in tch VarStore naming/layout (conv OIHW, linear [out,in])."""
+    def u(shape, bound):
+        return (torch.rand(shape, generator=gen) * 2 - 1) * bound
+    p = OrderedDict()
+    for name, (o, i, k) in (("c1", (32, n_stack, 8)), ("c2", (64, 32, 4)), ("c3", (64, 64, 3))):
+        fan = i * k * k
+        p[name + ".weight"] = u((o, i, k, k), math.sqrt(6.0 / fan))
+        p[name + ".bias"] = u((o,), 0.05)  # non-zero so that bias paths are exercised
+    if not skip_linear:
+        for name, (o, i) in (("l1", (512, 3136)), ("l2", (out_dim, 512))):
+            p[name + ".weight"] = u((o, i), math.sqrt(6.0 / i))
+            p[name + ".bias"] = u((o,), 1.0 / math.sqrt(i))
+    return p
+
+
+def atari_cnn_forward(p, x, skip_linear=False):
+    """cnn/base.rs:23-36.  x: [B, n_stack, 1, 84, 84] or [B, n_stack, 84, 84], any dtype."""
+    if x.dim() == 5:
+        x = x.squeeze(2)
+    x = x.to(torch.float32) / 255
+    x = F.relu(F.conv2d(x, p["c1.weight"], p["c1.bias"], stride=4))
+    x = F.relu(F.conv2d(x, p["c2.weight"], p["c2.bias"], stride=2))
+    x = F.relu(F.conv2d(x, p["c3.weight"], p["c3.bias"], stride=1)).flatten(1)
+    if skip_linear:
+        return x
+    x = F.relu(F.linear(x, p["l1.weight"], p["l1.bias"]))
+    return F.linear(x, p["l2.weight"], p["l2.bias"])
+
+
+def mlp_params(in_dim, units, out_dim, gen, prefix="mlp.ln"):
+    p = OrderedDict()
+    dims = [in_dim] + list(units) + [out_dim]
+    for i in range(len(dims) - 1):
+        bound = 1.0 / math.sqrt(dims[i])
+        p["%s%d.weight" % (prefix, i)] = (torch.rand((dims[i + 1], dims[i]), generator=gen) * 2 - 1) * math.sqrt(6.0 / dims[i])
+        p["%s%d.bias" % (prefix, i)] = (torch.rand((dims[i + 1],), generator=gen) * 2 - 1) * bound
+    return p
+
+
+def mlp_forward(p, x, n_layers, activation_out=False, prefix="mlp.ln"):
+    """mlp/base.rs:13-41: Linear+ReLU per hidden layer, final Linear (+ReLU iff activation_out)."""
+    for i in range(n_layers):
+        x = F.linear(x, p["%s%d.weight" % (prefix, i)], p["%s%d.bias" % (prefix, i)])
+        if i < n_layers - 1 or activation_out:
+            x = F.relu(x)
+    return x
+
+
+# ------------------------------------------------------------------------------------ optimizer
+
+class CppAdam:
+    """torch::optim::Adam / AdamW step (torch/csrc/api/src/optim/adam.cpp, adamw.cpp), which is
+    what tch::nn::Adam / AdamW bind (opt.rs:32-57).  Adam::default(): betas (0.9, 0.999), eps 1e-8,
+    wd 0."""
+
+    def __init__(self, params, lr, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0, adamw=False):
+        self.params = params  # OrderedDict name -> leaf tensor (requires_grad)
+        self.lr, self.b1, self.b2, self.eps, self.wd, self.adamw = lr, beta1, beta2, eps, wd, adamw
+        self.m = {k: torch.zeros_like(v) for k, v in params.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in params.items()}
+        self.t = 0
+
+    def zero_grad(self):
+        for v in self.params.values():
+            v.grad = None
+
+    @torch.no_grad()
+    def step(self):
+        self.t += 1
+        bc1 = 1 - self.b1 ** self.t
+        bc2 = 1 - self.b2 ** self.t
+        for k, p in self.params.items():
+            if p.grad is None:
+                continue
+            g = p.grad
+            if self.adamw:
+                p.mul_(1 - self.lr * self.wd)
+            elif self.wd != 0:
+                g = g.add(p, alpha=self.wd)
+            m, v = self.m[k], self.v[k]
+            m.mul_(self.b1).add_(g, alpha=1 - self.b1)
+            v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+            denom = (v.sqrt() / math.sqrt(bc2)).add_(self.eps)
+            p.addcdiv_(m, denom, value=-(self.lr / bc1))
+
+    def backward_step(self, loss):  # tch nn::Optimizer::backward_step: zero_grad; backward; step
+        self.zero_grad()
+        loss.backward()
+        self.step()
+
+
+@torch.no_grad()
+def track(dest, src, tau):
+    """util.rs:31-45: dest.copy_(tau * src + (1.0 - tau) * dest) per named variable."""
+    for k in src:
+        dest[k].copy_(tau * src[k] + (1.0 - tau) * dest[k])
+
+
+def leafify(p):
+    return OrderedDict((k, v.clone().detach().requires_grad_(True)) for k, v in p.items())
+
+
+# ------------------------------------------------------------------------------------ DQN
+
+class DqnOracle:
+    """Dqn (dqn/base.rs) for Q in {AtariCnn, Mlp}."""
+
+    def __init__(self, params, forward, lr, batch_size, discount_factor=0.99, tau=0.005, soft_update_interval=1,
+                 n_updates_per_opt=1, double_dqn=False, clip_td_err=None, critic_loss="Mse", opt_kwargs=None):
+        self.forward = forward
+        self.qnet = leafify(params)
+        self.qnet_tgt = OrderedDict((k, v.clone().detach()) for k, v in params.items())
+        self.opt = CppAdam(self.qnet, lr, **(opt_kwargs or {}))
+        self.batch_size, self.gamma, self.tau = batch_size, discount_factor, tau
+        self.soft_update_interval, self.n_updates_per_opt = soft_update_interval, n_updates_per_opt
+        self.soft_update_counter = 0
+        self.double_dqn, self.clip_td_err, self.critic_loss = double_dqn, clip_td_err, critic_loss
+        self.n_opts = 0
+
+    def update_critic(self, batch):
+        """batch: dict(obs, act [B,1] int64, next_obs, reward [B] f32, is_terminated [B] int8, weight or None).
+        Returns (loss, td_errs or None) as in dqn/base.rs:60-160."""
+        obs, act, next_obs = batch["obs"], batch["act"], batch["next_obs"]
+        reward, is_terminated, weight = batch["reward"], batch["is_terminated"], batch.get("weight")
+        pred = self.forward(self.qnet, obs).gather(-1, act).squeeze()
+        with torch.no_grad():
+            if self.double_dqn:
+                x = self.forward(self.qnet, next_obs)
+                y = x.argmax(-1, False).unsqueeze(-1)
+                q = self.forward(self.qnet_tgt, next_obs).gather(-1, y).squeeze()
+            else:
+                x = self.forward(self.qnet_tgt, next_obs)
+                y = x.argmax(-1, False).unsqueeze(-1)
+                q = x.gather(-1, y).squeeze()
+            tgt = reward + (1 - is_terminated) * self.gamma * q
+        td = None
+        if weight is not None:
+            td_errs = (pred - tgt).abs()
+            if self.clip_td_err is not None:
+                td_errs = td_errs.clip(self.clip_td_err[0], self.clip_td_err[1])
+            loss = weight * td_errs
+            zeros = torch.zeros(len(weight))
+            loss = F.smooth_l1_loss(loss, zeros, reduction="mean", beta=1.0) if self.critic_loss == "SmoothL1" \
+                else F.mse_loss(loss, zeros, reduction="mean")
+            self.opt.backward_step(loss)
+            td = td_errs.detach().clone()
+        else:
+            loss = F.smooth_l1_loss(pred, tgt, reduction="mean", beta=1.0) if self.critic_loss == "SmoothL1" \
+                else F.mse_loss(pred, tgt, reduction="mean")
+            self.opt.backward_step(loss)
+        self.last = dict(pred=pred.detach(), tgt=tgt)
+        return float(loss), td
+
+    def opt_(self, sample_fn, update_priority_fn=None):
+        """dqn/base.rs:182-200. sample_fn() -> batch dict (with 'ix_sample'); returns last loss."""
+        loss = None
+        for _ in range(self.n_updates_per_opt):
+            batch = sample_fn()
+            loss, td = self.update_critic(batch)
+            if td is not None and update_priority_fn is not None:
+                update_priority_fn(batch["ix_sample"], td.numpy())
+        self.soft_update_counter += 1
+        if self.soft_update_counter == self.soft_update_interval:
+            self.soft_update_counter = 0
+            track(self.qnet_tgt, self.qnet, self.tau)
+        self.n_opts += 1
+        return loss

@@ -1,0 +1,57 @@
+"""Generates the committed golden fixtures from the CPU oracle.
+
+The reference ships no vectors for these paths (only test_sum_tree_odd), and the Rust
+reference cannot be built in this image, so these are oracle-derived regression fixtures:
+    python -m tests.golden.make_golden
+"""
+import json
+import os
+
+import numpy as np
+
+from oracle import replay_oracle as ro
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def run_per_trace(normalize, capacity=1000, pushes=1500, rounds=40, batch=64):
+    """pushes (with wrap) then rounds x (sample with injected uniforms -> update_priority)."""
+    rng = np.random.default_rng(2024)
+    per = dict(alpha=0.6, beta_0=0.4, beta_final=1.0, n_opts_final=30, normalize=normalize)
+    r = ro.ReplayOracle(capacity, 42, (4,), np.float32, (1,), np.int64, per=per)
+    out = {}
+    done = 0
+    while done < pushes:
+        n = int(rng.integers(1, 8))
+        obs = rng.standard_normal((n, 4)).astype(np.float32)
+        r.push(obs, rng.integers(0, 3, (n, 1)), obs + 1, rng.standard_normal(n).astype(np.float32),
+               np.zeros(n, np.int8), np.zeros(n, np.int8))
+        done += n
+    out["tree_after_push"], _ = r.sum_tree()
+    ixs, ws, trees = [], [], []
+    for k in range(rounds):
+        u = rng.random(batch, dtype=np.float32)
+        ix, w = r.sample_indices(batch, u)
+        td = np.abs(rng.standard_normal(batch)).astype(np.float32) * (3.0 if k % 3 else 0.01)
+        if k % 5 == 0:
+            ix2 = ix.copy()
+            ix2[1::2] = ix2[0::2][: len(ix2[1::2])]  # duplicates inside one update batch
+            r.update_priority(ix2, td)
+        else:
+            r.update_priority(ix, td)
+        ixs.append(ix); ws.append(w); trees.append(r.sum_tree()[0][:64].copy())
+    out["ixs"] = np.stack(ixs); out["ws"] = np.stack(ws); out["tree_heads"] = np.stack(trees)
+    out["tree_final"], _ = r.sum_tree()
+    return out
+
+
+def main():
+    r = ro.StdRng(42)
+    json.dump({"seed": 42, "words": [r.next_u32() for _ in range(64)]},
+              open(os.path.join(HERE, "stdrng_seed42.json"), "w"))
+    for norm in ("All", "Batch"):
+        np.savez_compressed(os.path.join(HERE, "per_trace_%s.npz" % norm.lower()), **run_per_trace(norm))
+
+
+if __name__ == "__main__":
+    main()
