@@ -18,7 +18,7 @@ BB_EXPLORER_SOFTMAX, BB_EXPLORER_EPS_GREEDY = 0, 1
 BB_NET_MLP, BB_NET_ATARI_CNN = 0, 1
 BB_ENTCOEF_FIX, BB_ENTCOEF_AUTO = 0, 1
 (BB_IQN_CONST10, BB_IQN_UNIFORM8, BB_IQN_UNIFORM10, BB_IQN_UNIFORM32, BB_IQN_UNIFORM64, BB_IQN_MEDIAN,
- BB_IQN_CONST1) = range(7)
+ BB_IQN_CONST32) = range(7)
 
 
 class bb_replay_cfg(C.Structure):
@@ -117,6 +117,7 @@ _SIGS = {
     "bb_agent_sample": (C.c_int32, [_P, _P, C.c_size_t, _P]),
     "bb_agent_opt": (C.c_int32, [_P, _P, C.POINTER(bb_record)]),
     "bb_agent_n_opts": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
+    "bb_agent_opt_profiled": (C.c_int32, [_P, _P, C.c_char_p, C.c_size_t]),
     "bb_agent_save_params": (C.c_int32, [_P, C.c_char_p]),
     "bb_agent_load_params": (C.c_int32, [_P, C.c_char_p]),
     "bb_agent_param_count": (C.c_int32, [_P, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -179,7 +179,7 @@ class SacConfig:
 
 _IQN_SAMPLE = {"Const10": L.BB_IQN_CONST10, "Uniform8": L.BB_IQN_UNIFORM8, "Uniform10": L.BB_IQN_UNIFORM10,
                "Uniform32": L.BB_IQN_UNIFORM32, "Uniform64": L.BB_IQN_UNIFORM64, "Median": L.BB_IQN_MEDIAN,
-               "Const1": L.BB_IQN_CONST1}
+               "Const32": L.BB_IQN_CONST32}
 
 
 @dataclass
@@ -281,6 +281,16 @@ class Agent:
 
     def _record(self, rec):
         return {"loss": rec.loss}
+
+    def opt_profiled(self, buffer: SimpleReplayBuffer):
+        """One opt() with per-kernel CUDA-event timing: list of (label, ms)."""
+        buf = C.create_string_buffer(1 << 16)
+        L.check(L.lib().bb_agent_opt_profiled(self._h, buffer.handle, buf, len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            k, v = line.rsplit(" ", 1)
+            out.append((k, float(v)))
+        return out
 
     def n_opts(self):
         out = C.c_uint64()

@@ -309,6 +309,40 @@ int32_t bb_agent_opt(bb_agent* a, bb_replay* rb, bb_record* record) {
     A(a).opt(rb->impl, record);
     BB_API_END
 }
+// One opt() call with a CUDA event after every kernel; writes "label ms\n" lines (label =
+// phase:layer:kernel) into text_out.  Measurement aid for bench.py's roofline, not a hot path.
+int32_t bb_agent_opt_profiled(bb_agent* a, bb_replay* rb, char* text_out, size_t cap) {
+    BB_API_BEGIN
+    BB_CHECK(rb && text_out && cap > 0, "null argument");
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    bb::Profiler prof;
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
+    ag.ctx.prof = &prof;
+    ag.ctx.phase = "start"; ag.ctx.layer = "";
+    ag.ctx.mark("begin");
+    try {
+        ag.opt(rb->impl, nullptr);
+    } catch (...) {
+        ag.ctx.prof = nullptr;
+        prof.clear();
+        throw;
+    }
+    ag.ctx.prof = nullptr;
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
+    std::string out;
+    for (size_t i = 1; i < prof.marks.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, prof.marks[i - 1].second, prof.marks[i].second);
+        char line[256];
+        snprintf(line, sizeof(line), "%s %.6f\n", prof.marks[i].first.c_str(), ms);
+        out += line;
+    }
+    prof.clear();
+    BB_CHECK(out.size() + 1 <= cap, "profile text buffer too small");
+    memcpy(text_out, out.c_str(), out.size() + 1);
+    BB_API_END
+}
 int32_t bb_agent_n_opts(const bb_agent* a, uint64_t* out) {
     BB_API_BEGIN
     BB_CHECK(a && a->impl && out, "null argument");

@@ -169,9 +169,13 @@ struct Dqn : Agent {
         bb_batch_view bv;
         rb.sample(B, &bv);  // buffer.batch(self.batch_size), dqn/base.rs:62
         if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
+        ctx.phase = "replay"; ctx.layer = "batch";
+        ctx.mark("sample_gather");
+        ctx.phase = "fwd_online";
         const long ld_in = net.in_elems;
         const float* q = net.forward(ctx, qnet.p, bv.obs, ld_in, B, ws_online);         // :71-74
         const float* q_next = nullptr;
+        ctx.phase = "fwd_target";
         if (cfg.double_dqn) {                                                              // :93-99
             // online net on next_obs: borrow the target workspace first, keep its Q in d_scratch
             const float* qn = net.forward(ctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt);
@@ -189,15 +193,22 @@ struct Dqn : Agent {
         int threads = std::min(1024, (B + 31) / 32 * 32);
         dqn_loss_kernel<<<1, threads, 0, ctx.stream>>>(lp);
         BB_LAUNCHED();
+        ctx.phase = "loss"; ctx.layer = "td";
+        ctx.mark("dqn_loss");
+        ctx.phase = "backward";
         // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
         net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0);
         qnet.step += 1;
+        ctx.phase = "optimizer";
         grad_sync_begin();
         adam_step(ctx, qnet.p, qnet.g, qnet.m, qnet.v, qnet.n, qnet.hyper, qnet.step, peer_grads(), world);
         grad_sync_end();
         if (bv.weight) {  // :142-143
             if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
             rb.update_priority_dev((const unsigned long long*)bv.ix_sample, d_td, B);
+            if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
+            ctx.phase = "replay"; ctx.layer = "per";
+            ctx.mark("update_priority");
         }
         if (rec) {
             BB_CUDA(cudaMemcpyAsync(h_scratch, d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx.stream));
@@ -217,6 +228,7 @@ struct Dqn : Agent {
         soft_update_counter += 1;
         if (soft_update_counter == cfg.soft_update_interval) {
             soft_update_counter = 0;
+            ctx.phase = "target_update";
             track(ctx, qnet_tgt.p, qnet.p, qnet.n, cfg.tau);
         }
         n_opts += 1;

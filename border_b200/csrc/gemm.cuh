@@ -48,8 +48,9 @@ struct GemmArgs {
 constexpr int kBK = 16;
 
 template <int BM, int BN, int TM, int TN, bool A_KMAJOR, bool B_KMAJOR, bool A_U8, bool B_U8>
-__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
-    static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmArgs g) {
+    constexpr int NT = (BM / TM) * (BN / TN);  // threads per CTA
+    static_assert(NT % 32 == 0 && NT <= 1024, "whole warps");
     static_assert(TM % 4 == 0 && TN % 4 == 0, "float4 register tiles");
     constexpr int BK = kBK;
     constexpr int PAD = 4;
@@ -60,8 +61,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     const int k_begin = blockIdx.z * g.k_per_split;
     const int k_end = min(g.K, k_begin + g.k_per_split);
 
-    constexpr int A_LD = (BM * BK / 4 + 255) / 256;  // float4 groups per thread
-    constexpr int B_LD = (BN * BK / 4 + 255) / 256;
+    constexpr int A_LD = (BM * BK / 4 + NT - 1) / NT;  // float4 groups per thread
+    constexpr int B_LD = (BN * BK / 4 + NT - 1) / NT;
     float4 a_reg[A_LD], b_reg[B_LD];
 
     const float* Af = reinterpret_cast<const float*>(g.A);
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     if (A_KMAJOR) {
 #pragma unroll
         for (int i = 0; i < A_LD; ++i) {
-            int l = tid + i * 256;
+            int l = tid + i * NT;
             int m = m0 + l / (BK / 4);
             a_base[i] = -1;
             if (l < BM * BK / 4 && m < g.M) a_base[i] = g.a_rowbase ? (long)g.a_rowbase[m] : (long)m * g.lda;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     if (B_KMAJOR) {
 #pragma unroll
         for (int i = 0; i < B_LD; ++i) {
-            int l = tid + i * 256;
+            int l = tid + i * NT;
             int n = n0 + l / (BK / 4);
             b_base[i] = -1;
             if (l < BN * BK / 4 && n < g.N) b_base[i] = (long)n * g.ldb;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
         // ---- A
 #pragma unroll
         for (int i = 0; i < A_LD; ++i) {
-            int l = tid + i * 256;
+            int l = tid + i * NT;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (l < BM * BK / 4) {
                 if (A_KMAJOR) {
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
         // ---- B
 #pragma unroll
         for (int i = 0; i < B_LD; ++i) {
-            int l = tid + i * 256;
+            int l = tid + i * NT;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (l < BN * BK / 4) {
                 if (B_KMAJOR) {  // B(k,n) = B[n*ldb + k]
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     auto store_tiles = [&](int buf) {
 #pragma unroll
         for (int i = 0; i < A_LD; ++i) {
-            int l = tid + i * 256;
+            int l = tid + i * NT;
             if (l < BM * BK / 4) {
                 if (A_KMAJOR) {
                     int k = (l % (BK / 4)) * 4, m = l / (BK / 4);
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
         }
 #pragma unroll
         for (int i = 0; i < B_LD; ++i) {
-            int l = tid + i * 256;
+            int l = tid + i * NT;
             if (l < BN * BK / 4) {
                 if (B_KMAJOR) {
                     int k = (l % (BK / 4)) * 4, n = l / (BK / 4);

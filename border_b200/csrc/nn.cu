@@ -1,22 +1,45 @@
 // nn.cu -- see nn.cuh.  Layer primitives on top of gemm.cuh plus the elementwise kernels
 // (col2im, column sums, fused Adam, Polyak update, init).
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 #include "gemm.cuh"
 #include "nn.cuh"
 
 namespace bb {
 
+void Profiler::clear() {
+    for (auto& m : marks) cudaEventDestroy(m.second);
+    marks.clear();
+}
+void Ctx::mark(const char* kernel) const {
+    if (!prof) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, stream);
+    prof->marks.emplace_back(phase + ":" + layer + ":" + kernel, e);
+}
+
 // ------------------------------------------------------------------------------- split-K reduce
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                      int splits, const float* __restrict__ bias, int relu,
                                      const float* __restrict__ mask) {
+    // 8 lanes per output element: lane g sums splits g, g+8, ... then a fixed-order shuffle tree
+    // (deterministic; keeps many loads in flight when there are ~150 splits of a small tile)
     size_t total = (size_t)M * N;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        int m = (int)(i / N), n = (int)(i % N);
+    const int g = threadIdx.x & 7;
+    for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3; i < ((total + 31) & ~(size_t)31);
+         i += ((size_t)gridDim.x * blockDim.x) >> 3) {
+        const bool ok = i < total;
         float s = 0.f;
-        for (int z = 0; z < splits; ++z) s += ws[(size_t)z * total + i];
+        if (ok)
+            for (int z = g; z < splits; z += 8) s += ws[(size_t)z * total + i];
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (!ok || g != 0) continue;
+        int m = (int)(i / N), n = (int)(i % N);
         if (bias) s += bias[n];
         if (relu) s = fmaxf(s, 0.f);
         if (mask) s = mask[(size_t)m * ldc + n] > 0.f ? s : 0.f;
@@ -28,28 +51,40 @@ enum GemmMode { G_FWD = 0, G_FWD_U8, G_NN, G_WGRAD, G_WGRAD_U8 };
 
 template <int BM, int BN, int TM, int TN>
 static void launch_cfg(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
+    constexpr int NT = (BM / TM) * (BN / TN);
     switch (mode) {
-        case G_FWD: gemm_kernel<BM, BN, TM, TN, true, true, false, false><<<grid, 256, 0, s>>>(a); break;
-        case G_FWD_U8: gemm_kernel<BM, BN, TM, TN, true, true, true, false><<<grid, 256, 0, s>>>(a); break;
-        case G_NN: gemm_kernel<BM, BN, TM, TN, true, false, false, false><<<grid, 256, 0, s>>>(a); break;
-        case G_WGRAD: gemm_kernel<BM, BN, TM, TN, false, false, false, false><<<grid, 256, 0, s>>>(a); break;
-        case G_WGRAD_U8: gemm_kernel<BM, BN, TM, TN, false, false, false, true><<<grid, 256, 0, s>>>(a); break;
+        case G_FWD: gemm_kernel<BM, BN, TM, TN, true, true, false, false><<<grid, NT, 0, s>>>(a); break;
+        case G_FWD_U8: gemm_kernel<BM, BN, TM, TN, true, true, true, false><<<grid, NT, 0, s>>>(a); break;
+        case G_NN: gemm_kernel<BM, BN, TM, TN, true, false, false, false><<<grid, NT, 0, s>>>(a); break;
+        case G_WGRAD: gemm_kernel<BM, BN, TM, TN, false, false, false, false><<<grid, NT, 0, s>>>(a); break;
+        case G_WGRAD_U8: gemm_kernel<BM, BN, TM, TN, false, false, false, true><<<grid, NT, 0, s>>>(a); break;
     }
     BB_LAUNCHED();
 }
 
+// Tuning knobs (read once): BB_GEMM_VARIANT selects the register-tile shape per CTA-tile family,
+// BB_GEMM_FILL the number of CTAs per SM that split-K aims for.
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 static void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
     if (a.M <= 0 || a.N <= 0) return;
+    static const int variant = env_int("BB_GEMM_VARIANT", 0);  // A/B on B200 (profiles/r01_summary.md): 0 wins
+    static const int fill = env_int("BB_GEMM_FILL", 3);
     int BM, BN, cfg;
     if (a.N <= 32) { cfg = 1; BM = 128; BN = 32; }
     else if (a.M <= 32) { cfg = 2; BM = 32; BN = 128; }
+    else if (variant == 3 && a.M >= 4096) { cfg = 3; BM = 128; BN = 64; }
     else { cfg = 0; BM = 64; BN = 64; }
     int tm = (a.M + BM - 1) / BM, tn = (a.N + BN - 1) / BN;
     long tiles = (long)tm * tn;
     int split = 1;
     int kt = (a.K + kBK - 1) / kBK;  // k tiles
-    if (tiles < c.sms && kt >= 8) {
-        split = (int)std::min<long>((2L * c.sms + tiles - 1) / tiles, kt / 4);
+    long want = (long)fill * c.sms;
+    if (tiles < want && kt >= 8) {
+        split = (int)std::min<long>((want + tiles - 1) / tiles, kt / 4);
         size_t per = (size_t)a.M * a.N;
         if (per * split > c.ws_floats) split = (int)(c.ws_floats / per);
         if (split < 1) split = 1;
@@ -60,16 +95,34 @@ static void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
     a.k_per_split = kps;
     a.workspace = c.ws;
     dim3 grid(tn, tm, split);
-    switch (cfg) {
-        case 0: launch_cfg<64, 64, 4, 4>(mode, a, grid, c.stream); break;
-        case 1: launch_cfg<128, 32, 4, 4>(mode, a, grid, c.stream); break;
-        case 2: launch_cfg<32, 128, 4, 4>(mode, a, grid, c.stream); break;
+    const char* tag = "gemm";
+    if (variant == 0) {
+        switch (cfg) {
+            case 0: launch_cfg<64, 64, 4, 4>(mode, a, grid, c.stream); tag = "gemm64x64"; break;
+            case 1: launch_cfg<128, 32, 4, 4>(mode, a, grid, c.stream); tag = "gemm128x32"; break;
+            case 2: launch_cfg<32, 128, 4, 4>(mode, a, grid, c.stream); tag = "gemm32x128"; break;
+        }
+    } else if (variant == 2) {
+        switch (cfg) {
+            case 0: launch_cfg<64, 64, 8, 8>(mode, a, grid, c.stream); tag = "gemm64x64"; break;
+            case 1: launch_cfg<128, 32, 8, 8>(mode, a, grid, c.stream); tag = "gemm128x32"; break;
+            case 2: launch_cfg<32, 128, 8, 8>(mode, a, grid, c.stream); tag = "gemm32x128"; break;
+        }
+    } else {
+        switch (cfg) {
+            case 0: launch_cfg<64, 64, 8, 4>(mode, a, grid, c.stream); tag = "gemm64x64"; break;
+            case 1: launch_cfg<128, 32, 8, 4>(mode, a, grid, c.stream); tag = "gemm128x32"; break;
+            case 2: launch_cfg<32, 128, 4, 8>(mode, a, grid, c.stream); tag = "gemm32x128"; break;
+            case 3: launch_cfg<128, 64, 8, 8>(mode, a, grid, c.stream); tag = "gemm128x64"; break;
+        }
     }
+    c.mark(tag);
     if (split > 1) {
         size_t total = (size_t)a.M * a.N;
-        int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
+        int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
         splitk_reduce_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
         BB_LAUNCHED();
+        c.mark("splitk_reduce");
     }
 }
 
@@ -99,23 +152,29 @@ __global__ void colsum_partial_kernel(const float* __restrict__ Y, float* __rest
         part[(size_t)blockIdx.y * N + n] = t;
     }
 }
+// one warp per column: lanes stride over the R partials, then a fixed-order shuffle tree
 __global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int N, int R) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x & 31;
     if (n >= N) return;
     float t = 0.f;
-    for (int r = 0; r < R; ++r) t += part[(size_t)r * N + n];
-    out[n] = t;
+    for (int r = lane; r < R; r += 32) t += part[(size_t)r * N + n];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) out[n] = t;
 }
 
 void colsum(const Ctx& c, const float* dY, float* db, int M, int N) {
-    int R = std::max(1, std::min(256, (M + 63) / 64));
+    int chunks = (N + 31) / 32;
+    int R = std::max(1, std::min(std::min(256, (M + 31) / 32), (2 * c.sms + chunks - 1) / chunks));
     while ((size_t)R * N > c.ws_floats && R > 1) R /= 2;
     int rpb = (M + R - 1) / R;
     R = (M + rpb - 1) / rpb;
-    colsum_partial_kernel<<<dim3((N + 31) / 32, R), dim3(32, 8), 0, c.stream>>>(dY, c.ws, M, N, rpb);
+    colsum_partial_kernel<<<dim3(chunks, R), dim3(32, 8), 0, c.stream>>>(dY, c.ws, M, N, rpb);
     BB_LAUNCHED();
-    colsum_final_kernel<<<(N + 127) / 128, 128, 0, c.stream>>>(c.ws, db, N, R);
+    colsum_final_kernel<<<(N + 7) / 8, 256, 0, c.stream>>>(c.ws, db, N, R);
     BB_LAUNCHED();
+    c.mark("colsum");
 }
 
 // ------------------------------------------------------------------------------- linear
@@ -208,6 +267,7 @@ void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float
     int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 16);
     col2im_nhwc_kernel<<<blocks, 256, 0, c.stream>>>(col, dX, mask, g.B, g.C, g.H, g.W, g.KH, g.KW, g.S, g.OH, g.OW);
     BB_LAUNCHED();
+    c.mark("col2im");
 }
 
 // ------------------------------------------------------------------------------- Adam / track
@@ -256,6 +316,8 @@ void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_
                                               (float)(-step_size), (float)h.wd, (float)(1.0 - h.lr * h.wd),
                                               h.adamw ? 1 : 0, pp, peer_grads ? world : 1);
     BB_LAUNCHED();
+    c.layer = "";
+    c.mark("adam");
 }
 
 __global__ void track_kernel(float* __restrict__ dest, const float* __restrict__ src, size_t n, float tau,
@@ -267,6 +329,8 @@ void track(const Ctx& c, float* dest, const float* src, size_t n, double tau) {
     int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)c.sms * 8);
     track_kernel<<<blocks, 256, 0, c.stream>>>(dest, src, n, (float)tau, (float)(1.0 - tau));
     BB_LAUNCHED();
+    c.layer = "";
+    c.mark("track");
 }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
@@ -339,6 +403,35 @@ static void add_conv(Net& n, const std::string& name, int C, int H, int W, int O
     l.b_off = n.n_params;
     add_param(n, name + ".bias", {OC}, 0, 0, 0, 0, C * k * k);
     n.layers.push_back(l);
+}
+
+void Net::add_linear_layer(const std::string& name, int in, int out, bool relu) {
+    if (layers.empty()) in_elems = in;
+    add_linear(*this, name, in, out, relu);
+    out_dim = out;
+}
+
+void Net::add_twin_heads(const std::string& name1, const std::string& name2, int in, int out) {
+    if (layers.empty()) in_elems = in;
+    Layer l{};
+    l.type = 0; l.in_dim = in; l.out_dim = 2 * out; l.relu = false; l.out_elems_per_sample = 2 * out;
+    auto push = [&](const std::string& nm, std::vector<int64_t> shape, size_t off) {
+        ParamInfo pi;
+        pi.name = nm; pi.shape = shape; pi.offset = off; pi.perm = 0; pi.pc = pi.ph = pi.pw = 0; pi.fan_in = in;
+        pi.numel = 1;
+        for (auto d : shape) pi.numel *= (size_t)d;
+        params.push_back(pi);
+    };
+    l.w_off = n_params;
+    push(name1 + ".weight", {out, in}, n_params);
+    push(name2 + ".weight", {out, in}, n_params + (size_t)out * in);
+    n_params += ((size_t)2 * out * in + 3) / 4 * 4;
+    l.b_off = n_params;
+    push(name1 + ".bias", {out}, n_params);
+    push(name2 + ".bias", {out}, n_params + out);
+    n_params += ((size_t)2 * out + 3) / 4 * 4;
+    layers.push_back(l);
+    out_dim = 2 * out;
 }
 
 void Net::build(const bb_net_cfg& cfg, const std::string& prefix) {
@@ -449,12 +542,20 @@ void Net::init_params(const Ctx& c, float* p, uint64_t seed) const {
     }
 }
 
+std::string Net::layer_name(size_t i) const {
+    // parameter names are "<layer>.weight": strip the suffix of the layer's weight tensor
+    for (auto& pi : params)
+        if (pi.offset == layers[i].w_off) return pi.name.substr(0, pi.name.rfind('.'));
+    return "layer" + std::to_string(i);
+}
+
 const float* Net::forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w) const {
     BB_CHECK(B <= w.max_batch, "batch larger than the workspace");
     const void* x = input;
     long ldx = ld_in;
     for (size_t i = 0; i < layers.size(); ++i) {
         const Layer& l = layers[i];
+        c.layer = layer_name(i) + ".fwd";
         if (l.type == 1) {
             ConvGeom g = l.geom;
             g.B = B; g.rowbase = w.rowbase[i];
@@ -494,10 +595,18 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
         if (l.type == 1) {
             ConvGeom cg = l.geom;
             cg.B = B; cg.rowbase = w.rowbase[i];
-            conv_bwd_weight(c, cg, w.dact[i], x, g + l.w_off, g + l.b_off);
+            if (g) {
+                c.layer = layer_name(i) + ".wgrad";
+                conv_bwd_weight(c, cg, w.dact[i], x, g + l.w_off, g + l.b_off);
+            }
+            c.layer = layer_name(i) + ".dgrad";
             if (dx) conv_bwd_data(c, cg, w.dact[i], p + l.w_off, w.col, dx, mask);
         } else {
-            linear_bwd_weight(c, w.dact[i], (const float*)x, ldx, g + l.w_off, g + l.b_off, B, l.out_dim, l.in_dim);
+            if (g) {
+                c.layer = layer_name(i) + ".wgrad";
+                linear_bwd_weight(c, w.dact[i], (const float*)x, ldx, g + l.w_off, g + l.b_off, B, l.out_dim, l.in_dim);
+            }
+            c.layer = layer_name(i) + ".dgrad";
             if (dx) linear_bwd_data(c, w.dact[i], p + l.w_off, dx, lddx, B, l.out_dim, l.in_dim, mask);
         }
     }
@@ -521,6 +630,14 @@ void param_to_internal(const ParamInfo& pi, const float* ref, float* internal) {
                 for (int h = 0; h < H; ++h)
                     for (int w = 0; w < W; ++w)
                         internal[o * in + ((size_t)h * W + w) * C + ch] = ref[o * in + ((size_t)ch * H + h) * W + w];
+    } else if (pi.perm == 3 || pi.perm == 4) {  // rows (or elements) of a [C*H*W][cols] tensor -> [H*W*C][cols]
+        int C = pi.pc, H = pi.ph, W = pi.pw;
+        size_t cols = pi.perm == 3 ? (size_t)pi.shape[1] : 1;
+        for (int ch = 0; ch < C; ++ch)
+            for (int h = 0; h < H; ++h)
+                for (int w = 0; w < W; ++w)
+                    std::copy(ref + (((size_t)ch * H + h) * W + w) * cols, ref + (((size_t)ch * H + h) * W + w + 1) * cols,
+                              internal + (((size_t)h * W + w) * C + ch) * cols);
     } else {
         std::copy(ref, ref + pi.numel, internal);
     }
@@ -542,6 +659,14 @@ void param_to_reference(const ParamInfo& pi, const float* internal, float* ref) 
                 for (int h = 0; h < H; ++h)
                     for (int w = 0; w < W; ++w)
                         ref[o * in + ((size_t)ch * H + h) * W + w] = internal[o * in + ((size_t)h * W + w) * C + ch];
+    } else if (pi.perm == 3 || pi.perm == 4) {
+        int C = pi.pc, H = pi.ph, W = pi.pw;
+        size_t cols = pi.perm == 3 ? (size_t)pi.shape[1] : 1;
+        for (int ch = 0; ch < C; ++ch)
+            for (int h = 0; h < H; ++h)
+                for (int w = 0; w < W; ++w)
+                    std::copy(internal + (((size_t)h * W + w) * C + ch) * cols, internal + (((size_t)h * W + w) * C + ch + 1) * cols,
+                              ref + (((size_t)ch * H + h) * W + w) * cols);
     } else {
         std::copy(internal, internal + pi.numel, ref);
     }

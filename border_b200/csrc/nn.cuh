@@ -18,12 +18,21 @@
 
 namespace bb {
 
+// Optional per-kernel timing (bb_agent_opt_profiled): an event after every kernel launch.
+struct Profiler {
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void clear();
+};
+
 struct Ctx {
     int device = 0;
     int sms = 148;
     cudaStream_t stream = nullptr;
     float* ws = nullptr;  // split-K / reduction workspace
     size_t ws_floats = 0;
+    Profiler* prof = nullptr;
+    mutable std::string phase, layer;
+    void mark(const char* kernel) const;  // no-op unless prof is set
 };
 
 // ---- primitives (all row-major fp32) -------------------------------------------------------
@@ -70,7 +79,8 @@ struct ParamInfo {
     std::string name;            // tch VarStore name, e.g. "c1.weight", "mlp.ln0.bias"
     std::vector<int64_t> shape;  // reference shape
     size_t offset, numel;        // into the flat parameter vector (internal layout)
-    int perm;                    // 0 none, 1 conv OIHW<->OHWI, 2 linear [out][C,H,W]<->[out][H,W,C]
+    int perm;                    // 0 none, 1 conv OIHW<->OHWI, 2 linear [out][C,H,W]<->[out][H,W,C],
+                                 // 3 rows [C,H,W][cols]<->[H,W,C][cols], 4 vector [C,H,W]<->[H,W,C]
     int pc, ph, pw;              // dims for the permutation
     int fan_in;
 };
@@ -107,16 +117,24 @@ class Net {
     std::vector<ParamInfo> params;
     std::vector<int*> koff;  // per conv layer (device), shared by all workspaces
 
+    // Custom stacks (SAC's Mlp2 actor, IQN sub-nets): append one linear layer; or two heads that
+    // share an input, stored as ONE [2*out][in] layer whose halves keep their own VarStore names.
+    void add_linear_layer(const std::string& name, int in, int out, bool relu);
+    void add_twin_heads(const std::string& name1, const std::string& name2, int in, int out);
+    void reset() { layers.clear(); params.clear(); n_params = 0; }
+
     void init_tables(int device);
     void alloc_workspace(NetWorkspace& w, int max_batch, bool with_grad) const;
     void init_params(const Ctx& c, float* p, uint64_t seed) const;
     // forward: input [B][in] (u8 CHW frames or float rows); returns ws.act.back()
     const float* forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w) const;
     // backward from d(output) in w.dact.back(); accumulates nothing: grads are overwritten.
+    // g == nullptr skips the weight gradients (data gradient only).
     // d_input (may be null) receives the gradient wrt a float input [B][in].
     void backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
                   float* d_input, long ld_din) const;
     void free_tables();
+    std::string layer_name(size_t i) const;
 };
 
 // reference layout <-> internal layout of one parameter tensor (host side)

@@ -48,7 +48,7 @@ enum { BB_NET_MLP = 0, BB_NET_ATARI_CNN = 1 };
 enum { BB_ENTCOEF_FIX = 0, BB_ENTCOEF_AUTO = 1 };
 /* IqnSample, border-tch-agent/src/iqn/model/base.rs:327-345 */
 enum { BB_IQN_CONST10 = 0, BB_IQN_UNIFORM8 = 1, BB_IQN_UNIFORM10 = 2, BB_IQN_UNIFORM32 = 3,
-       BB_IQN_UNIFORM64 = 4, BB_IQN_MEDIAN = 5, BB_IQN_CONST1 = 6 };
+       BB_IQN_UNIFORM64 = 4, BB_IQN_MEDIAN = 5, BB_IQN_CONST32 = 6 };
 
 const char* bb_last_error(void);
 int32_t bb_abi_version(void);
@@ -237,6 +237,9 @@ int32_t bb_agent_sample(bb_agent* a, const void* obs, size_t n, void* act_out);
 /* Agent::opt / opt_with_record (record may be NULL => no device->host copy at all). */
 int32_t bb_agent_opt(bb_agent* a, bb_replay* rb, bb_record* record);
 int32_t bb_agent_n_opts(const bb_agent* a, uint64_t* out);
+/* Measurement aid: one opt() with a CUDA event after every kernel of this library; text_out
+ * receives "phase:layer:kernel milliseconds" lines.  bench.py derives the roofline from it. */
+int32_t bb_agent_opt_profiled(bb_agent* a, bb_replay* rb, char* text_out, size_t cap);
 /* Agent::save_params / load_params (directory of raw named tensors + manifest). */
 int32_t bb_agent_save_params(bb_agent* a, const char* dir);
 int32_t bb_agent_load_params(bb_agent* a, const char* dir);

@@ -179,7 +179,7 @@ class DqnOracle:
                 else F.mse_loss(pred, tgt, reduction="mean")
             self.opt.backward_step(loss)
         self.last = dict(pred=pred.detach(), tgt=tgt)
-        return float(loss), td
+        return float(loss.detach()), td
 
     def opt_(self, sample_fn, update_priority_fn=None):
         """dqn/base.rs:182-200. sample_fn() -> batch dict (with 'ix_sample'); returns last loss."""
@@ -194,4 +194,178 @@ class DqnOracle:
             self.soft_update_counter = 0
             track(self.qnet_tgt, self.qnet, self.tau)
         self.n_opts += 1
+        return loss
+
+
+# ------------------------------------------------------------------------------------ SAC
+
+def mlp2_params(in_dim, units, out_dim, gen):
+    """Mlp2 (mlp/mlp2.rs:31-50): trunk mlp.al{i}, heads ml / sl."""
+    p = OrderedDict()
+    dims = [in_dim] + list(units)
+    for i in range(len(units)):
+        p["mlp.al%d.weight" % i] = (torch.rand((dims[i + 1], dims[i]), generator=gen) * 2 - 1) * math.sqrt(6.0 / dims[i])
+        p["mlp.al%d.bias" % i] = (torch.rand((dims[i + 1],), generator=gen) * 2 - 1) / math.sqrt(dims[i])
+    h = dims[-1]
+    for name in ("ml", "sl"):
+        p[name + ".weight"] = (torch.rand((out_dim, h), generator=gen) * 2 - 1) * math.sqrt(1.0 / h)
+        p[name + ".bias"] = (torch.rand((out_dim,), generator=gen) * 2 - 1) / math.sqrt(h)
+    return p
+
+
+def mlp2_forward(p, x, n_hidden):
+    """mlp2.rs:23-28: (head1(x), exp(head2(x)))."""
+    for i in range(n_hidden):
+        x = F.relu(F.linear(x, p["mlp.al%d.weight" % i], p["mlp.al%d.bias" % i]))
+    return F.linear(x, p["ml.weight"], p["ml.bias"]), F.linear(x, p["sl.weight"], p["sl.bias"]).exp()
+
+
+def normal_logp(x):
+    """sac/base.rs:25-29"""
+    tmp = torch.tensor(-0.5 * math.log(2.0 * 3.1415927410125732), dtype=torch.float32) - 0.5 * x.pow(2)
+    return tmp.sum(-1)
+
+
+class SacOracle:
+    """Sac (sac/base.rs:73-198) with Actor = Mlp2, Critic = Mlp over cat[obs, act]."""
+
+    def __init__(self, pi_params, q_params_list, n_pi_hidden, n_q_layers, lr_pi, lr_q, batch_size, gamma=0.99, tau=0.005,
+                 ent_coef_mode=("Fix", 1.0), epsilon=1e-4, min_lstd=-20.0, max_lstd=2.0, reward_scale=1.0,
+                 critic_loss="Mse"):
+        self.pi = leafify(pi_params)
+        self.qnets = [leafify(q) for q in q_params_list]
+        self.qnets_tgt = [OrderedDict((k, v.clone().detach()) for k, v in q.items()) for q in q_params_list]
+        self.opt_pi = CppAdam(self.pi, lr_pi)
+        self.opt_q = [CppAdam(q, lr_q) for q in self.qnets]
+        self.n_pi_hidden, self.n_q_layers = n_pi_hidden, n_q_layers
+        self.batch_size, self.gamma, self.tau = batch_size, gamma, tau
+        self.epsilon, self.min_lstd, self.max_lstd = epsilon, min_lstd, max_lstd
+        self.reward_scale, self.critic_loss = reward_scale, critic_loss
+        if ent_coef_mode[0] == "Fix":  # ent_coef.rs:31-36
+            self.log_alpha = torch.tensor([math.log(ent_coef_mode[1])], dtype=torch.float32)
+            self.target_entropy, self.opt_alpha = None, None
+        else:  # Auto(target_entropy, lr), ent_coef.rs:37-45
+            self.log_alpha = torch.zeros(1, dtype=torch.float32, requires_grad=True)
+            self.target_entropy = ent_coef_mode[1]
+            self.opt_alpha = CppAdam(OrderedDict(log_alpha=self.log_alpha), ent_coef_mode[2])
+        self.n_opts = 0
+
+    def alpha(self):
+        return self.log_alpha.detach().exp()
+
+    def action_logp(self, o, z):
+        mean, lstd = mlp2_forward(self.pi, o, self.n_pi_hidden)
+        std = lstd.clip(self.min_lstd, self.max_lstd).exp()
+        a = (std * z + mean).tanh()
+        log_p = normal_logp(z) - (torch.tensor(1.0) - a.pow(2.0) + torch.tensor(self.epsilon, dtype=torch.float32)).log().sum(-1)
+        return a, log_p
+
+    def qvals(self, qnets, obs, act):
+        return [mlp_forward(q, torch.cat([obs, act], -1), self.n_q_layers).squeeze() for q in qnets]
+
+    def update_actor(self, batch, z):
+        a, log_p = self.action_logp(batch["obs"], z)
+        if self.target_entropy is not None:  # ent_coef.update(&log_p.detach())
+            loss_a = -(self.log_alpha * (log_p.detach() + torch.tensor(self.target_entropy, dtype=torch.float64)).detach()).mean(dtype=torch.float32)
+            self.opt_alpha.backward_step(loss_a)
+        qval = torch.vstack(self.qvals(self.qnets, batch["obs"], a)).min(0)[0]
+        loss = (self.alpha() * log_p - qval).mean(dtype=torch.float32)
+        self.opt_pi.backward_step(loss)
+        return float(loss.detach())
+
+    def update_critic(self, batch, z):
+        reward, is_terminated = batch["reward"], batch["is_terminated"]
+        preds = self.qvals(self.qnets, batch["obs"], batch["act"])
+        with torch.no_grad():
+            next_a, next_log_p = self.action_logp(batch["next_obs"], z)
+            next_q = torch.vstack(self.qvals(self.qnets_tgt, batch["next_obs"], next_a)).min(0)[0]
+            next_q = next_q - self.alpha() * next_log_p
+        tgt = self.reward_scale * reward + (1.0 - is_terminated) * torch.tensor(self.gamma, dtype=torch.float64) * next_q
+        tgt = tgt.to(torch.float32)
+        if self.critic_loss == "Mse":
+            losses = [F.mse_loss(p, tgt, reduction="mean") for p in preds]
+        else:
+            losses = [F.smooth_l1_loss(p, tgt, reduction="mean", beta=1.0) for p in preds]
+        for opt, loss in zip(self.opt_q, losses):
+            opt.backward_step(loss)
+        return sum(float(l.detach()) for l in losses) / len(losses)
+
+    def opt_(self, batch, z_actor, z_critic):
+        """one update of sac/base.rs:175-198 (n_updates_per_opt = 1)"""
+        la = self.update_actor(batch, z_actor)
+        lc = self.update_critic(batch, z_critic)
+        for qt, q in zip(self.qnets_tgt, self.qnets):
+            track(qt, q, self.tau)
+        self.n_opts += 1
+        return dict(loss_critic=lc, loss_actor=la, ent_coef=float(self.alpha()[0]))
+
+
+# ------------------------------------------------------------------------------------ IQN
+
+def iqn_params(f_params, feature_dim, embed_dim, m_params, gen):
+    """One VarStore: psi vars, iqn_cos_to_feature, merge-net vars (iqn/model/base.rs:64-86)."""
+    p = OrderedDict(f_params)
+    p["iqn_cos_to_feature.weight"] = (torch.rand((feature_dim, embed_dim), generator=gen) * 2 - 1) * math.sqrt(6.0 / embed_dim)
+    p["iqn_cos_to_feature.bias"] = (torch.rand((feature_dim,), generator=gen) * 2 - 1) / math.sqrt(embed_dim)
+    p.update(m_params)
+    return p
+
+
+def iqn_forward(p, psi_fn, m_fn, x, tau, embed_dim):
+    """IqnModel::forward (iqn/model/base.rs:198-234) with cos_embed_nn (:162-191)."""
+    psi = psi_fn(p, x)
+    B, N = tau.shape
+    i = torch.arange(1, embed_dim + 1, dtype=torch.float32).unsqueeze(0).unsqueeze(0)
+    cos = torch.cos(tau.unsqueeze(-1) * (math.pi * i)).reshape(-1, embed_dim)
+    phi = F.relu(F.linear(cos, p["iqn_cos_to_feature.weight"], p["iqn_cos_to_feature.bias"]))
+    phi = phi.reshape(B, N, -1)
+    m = psi.unsqueeze(1) * phi
+    return m_fn(p, m)
+
+
+def quantile_huber_loss(x, tau):
+    """util/quantile_loss.rs:7-12"""
+    lt_0 = x.lt(0.0).detach()
+    loss = F.smooth_l1_loss(x, torch.zeros_like(x), reduction="none", beta=1.0)
+    return (tau - torch.where(lt_0, 1.0, 0.0)).abs() * loss
+
+
+class IqnOracle:
+    """Iqn::update_critic / opt_ (iqn/base.rs:63-190)."""
+
+    def __init__(self, params, psi_fn, m_fn, embed_dim, lr, batch_size, discount_factor=0.99, tau=0.005,
+                 soft_update_interval=1):
+        self.iqn = leafify(params)
+        self.iqn_tgt = OrderedDict((k, v.clone().detach()) for k, v in params.items())
+        self.opt = CppAdam(self.iqn, lr)
+        self.psi_fn, self.m_fn, self.embed_dim = psi_fn, m_fn, embed_dim
+        self.batch_size, self.gamma, self.tau = batch_size, discount_factor, tau
+        self.soft_update_interval, self.soft_update_counter = soft_update_interval, 0
+
+    def update_critic(self, batch, tau_pred, tau_tgt):
+        obs, act, next_obs = batch["obs"], batch["act"], batch["next_obs"]
+        reward = batch["reward"].unsqueeze(-1)
+        is_terminated = batch["is_terminated"].unsqueeze(-1)
+        n_pred, n_tgt = tau_pred.shape[1], tau_tgt.shape[1]
+        z = iqn_forward(self.iqn, self.psi_fn, self.m_fn, obs, tau_pred, self.embed_dim)
+        a = act.unsqueeze(1).repeat(1, n_pred, 1)
+        pred = z.gather(-1, a).squeeze(-1).unsqueeze(1)
+        with torch.no_grad():
+            zt = iqn_forward(self.iqn_tgt, self.psi_fn, self.m_fn, next_obs, tau_tgt, self.embed_dim)
+            y = zt.clone().mean(1)
+            a = y.argmax(-1, False).unsqueeze(-1).unsqueeze(-1).repeat(1, n_tgt, 1)
+            zt = zt.gather(2, a).squeeze(-1)
+            tgt = (reward + (1 - is_terminated) * self.gamma * zt).unsqueeze(-1)
+        diff = tgt - pred
+        tau = tau_pred.unsqueeze(1).repeat(1, n_tgt, 1)
+        loss = quantile_huber_loss(diff, tau).mean(dtype=torch.float32)
+        self.opt.backward_step(loss)
+        return float(loss.detach())
+
+    def opt_(self, batch, tau_pred, tau_tgt):
+        loss = self.update_critic(batch, tau_pred, tau_tgt)
+        self.soft_update_counter += 1
+        if self.soft_update_counter == self.soft_update_interval:
+            self.soft_update_counter = 0
+            track(self.iqn_tgt, self.iqn, self.tau)
         return loss
