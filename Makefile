@@ -10,7 +10,9 @@ SRCS      := $(filter $(notdir $(wildcard $(CSRC)/*.cu)),$(SRCS)) $(if $(wildcar
 OBJS      := $(patsubst %.cu,$(OBJDIR)/%.o,$(SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.inc) include/border_b200.h
 
-all: $(LIB) oracle
+HOSTLIB   := border_b200/libborder_host.so
+
+all: $(LIB) $(HOSTLIB) oracle
 
 $(OBJDIR)/replay.o: $(CSRC)/replay.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -23,6 +25,10 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
+# host-side loops (Trainer / train_async mirror) in plain C++ over the C ABI only
+$(HOSTLIB): border_b200/host/host_capi.cpp border_b200/host/border_host.hpp include/border_host.h include/border_b200.h $(LIB)
+	g++ -std=c++17 -O2 -fPIC -shared -Wall -Iinclude border_b200/host/host_capi.cpp -o $@ -Lborder_b200 -lborder_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
+
 oracle: oracle/_build/libreplay_oracle.so
 
 oracle/_build/libreplay_oracle.so: oracle/replay_oracle.c
@@ -30,6 +36,6 @@ oracle/_build/libreplay_oracle.so: oracle/replay_oracle.c
 	gcc -O2 -fPIC -shared -o $@ $< -lm
 
 clean:
-	rm -rf build $(LIB) oracle/_build
+	rm -rf build $(LIB) $(HOSTLIB) oracle/_build
 
 .PHONY: all oracle clean

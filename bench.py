@@ -165,6 +165,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (no version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = local
@@ -183,7 +184,8 @@ def run_b200(args):
     agent.set_stream(stream)
     sync_mode = "none"
     if world > 1 and args.sync == "allreduce":
-        sync_mode = connect_peers(agent, rank, world, dist, torch)
+        from border_b200 import dist as bd
+        sync_mode = bd.connect_gradient_peers(agent, dist, torch)
 
     def barrier():
         torch.cuda.synchronize()
@@ -319,23 +321,6 @@ def roofline_for(label, ms, step_ms, pk):
             "traffic": None, "ms_per_launch": ms, "share_of_step": ms / step_ms, "peak_source": pk["src"]}
 
 
-def connect_peers(agent, rank, world, dist, torch):
-    """Exchange CUDA IPC handles of the gradient buffers so the fused all-reduce + Adam kernel can
-    read every rank's gradients over NVLink."""
-    import ctypes as C
-    from border_b200 import _lib as L
-    h = (C.c_uint8 * 64)()
-    f = (C.c_uint8 * 64)()
-    L.check(L.lib().bb_agent_ipc_export(agent.handle, h, f))
-    mine = torch.tensor(list(bytes(h)) + list(bytes(f)), dtype=torch.uint8, device="cuda")
-    allh = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allh, mine)
-    hs = b"".join(bytes(t[:64].cpu().tolist()) for t in allh)
-    fs = b"".join(bytes(t[64:].cpu().tolist()) for t in allh)
-    L.check(L.lib().bb_agent_ipc_connect(agent.handle, rank, world, hs, fs))
-    return "fused P2P all-reduce + Adam over NVLink (CUDA IPC peer loads)"
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -344,7 +329,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--capacity", type=int, default=1 << 20)
     ap.add_argument("--sync", default="allreduce", choices=["allreduce", "replicas"])
-    ap.add_argument("--cpu-steps", type=int, default=100)
+    ap.add_argument("--cpu-steps", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

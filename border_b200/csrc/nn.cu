@@ -22,11 +22,27 @@ void Ctx::mark(const char* kernel) const {
 
 // ------------------------------------------------------------------------------- split-K reduce
 
+// Few splits of a large tile: one thread per output element, coalesced across elements.
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                      int splits, const float* __restrict__ bias, int relu,
                                      const float* __restrict__ mask) {
-    // 8 lanes per output element: lane g sums splits g, g+8, ... then a fixed-order shuffle tree
-    // (deterministic; keeps many loads in flight when there are ~150 splits of a small tile)
+    size_t total = (size_t)M * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int m = (int)(i / N), n = (int)(i % N);
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += ws[(size_t)z * total + i];
+        if (bias) s += bias[n];
+        if (relu) s = fmaxf(s, 0.f);
+        if (mask) s = mask[(size_t)m * ldc + n] > 0.f ? s : 0.f;
+        C[(size_t)m * ldc + n] = s;
+    }
+}
+
+// Many splits of a small tile (weight gradients): 8 lanes per output element, lane g sums splits
+// g, g+8, ... then a fixed-order shuffle tree (deterministic; keeps many loads in flight).
+__global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
+                                      int splits, const float* __restrict__ bias, int relu,
+                                      const float* __restrict__ mask) {
     size_t total = (size_t)M * N;
     const int g = threadIdx.x & 7;
     for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3; i < ((total + 31) & ~(size_t)31);
@@ -119,8 +135,13 @@ static void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
     c.mark(tag);
     if (split > 1) {
         size_t total = (size_t)a.M * a.N;
-        int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
-        splitk_reduce_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+        if (split >= 16) {
+            int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
+            splitk_reduce8_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+        } else {
+            int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
+            splitk_reduce_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+        }
         BB_LAUNCHED();
         c.mark("splitk_reduce");
     }

@@ -1,0 +1,83 @@
+"""ctypes binding of include/border_host.h: border's Trainer / train_async loops restated in C++
+(border_b200/host/border_host.hpp) over the C ABI, with synthetic environments."""
+import ctypes as C
+import os
+
+from . import _lib as L
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libborder_host.so")
+ALGO = {"dqn": 0, "iqn": 1, "sac": 2}
+
+
+class bbh_env_cfg(C.Structure):
+    _fields_ = [("obs_kind", C.c_int32), ("obs_elems", C.c_uint32), ("episode_len", C.c_uint64),
+                ("truncate_len", C.c_uint64)]
+
+
+class bbh_trainer_cfg(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("max_opts", "opt_interval", "eval_interval", "flush_record_interval",
+                                           "record_compute_cost_interval", "record_agent_info_interval", "warmup_period",
+                                           "save_interval", "sync_interval", "n_actors", "n_buffer", "env_seed")]
+
+
+class bbh_train_stat(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("env_steps", "opt_steps", "records", "saves", "buffer_len", "agent_n_opts",
+                                           "samples_total", "syncs")] + \
+               [(n, C.c_double) for n in ("opt_seconds", "sample_seconds", "total_seconds", "samples_per_sec", "opt_per_sec")] + \
+               [("last_loss", C.c_float)]
+
+
+_hl = None
+
+
+def host_lib():
+    global _hl
+    if _hl is None:
+        L.lib()  # libborder_b200.so first (RTLD_GLOBAL)
+        if not os.path.exists(HOST_LIB_PATH):
+            raise L.BorderB200Error("%s is missing: build it with `make`" % HOST_LIB_PATH)
+        l = C.CDLL(HOST_LIB_PATH)
+        l.bbh_last_error.restype = C.c_char_p
+        l.bbh_trainer_cfg_default.argtypes = [C.POINTER(bbh_trainer_cfg)]
+        l.bbh_train.restype = C.c_int32
+        l.bbh_train.argtypes = [C.c_int32, C.c_void_p, C.POINTER(L.bb_replay_cfg), C.POINTER(bbh_env_cfg),
+                                C.POINTER(bbh_trainer_cfg), C.c_char_p, C.POINTER(bbh_train_stat)]
+        l.bbh_train_async.restype = C.c_int32
+        l.bbh_train_async.argtypes = [C.c_int32, C.c_void_p, C.POINTER(L.bb_replay_cfg), C.POINTER(bbh_env_cfg),
+                                      C.POINTER(bbh_trainer_cfg), C.POINTER(bbh_train_stat)]
+        _hl = l
+    return _hl
+
+
+def _check(rc):
+    if rc != 0:
+        raise L.BorderB200Error(host_lib().bbh_last_error().decode("utf-8", "replace"))
+
+
+def trainer_cfg(**kw):
+    c = bbh_trainer_cfg()
+    host_lib().bbh_trainer_cfg_default(C.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def _stat(st):
+    return {n: getattr(st, n) for n, _ in bbh_train_stat._fields_}
+
+
+def train(algo, agent_cfg, replay_cfg, env_cfg, tcfg, save_dir=None):
+    """Trainer::train (border-core/src/trainer.rs:267-327)."""
+    st = bbh_train_stat()
+    _check(host_lib().bbh_train(ALGO[algo], C.cast(C.pointer(agent_cfg), C.c_void_p), C.byref(replay_cfg), C.byref(env_cfg),
+                                C.byref(tcfg), save_dir.encode() if save_dir else None, C.byref(st)))
+    return _stat(st)
+
+
+def train_async(algo, agent_cfg, replay_cfg, env_cfg, tcfg):
+    """train_async (border-async-trainer/src/util.rs:31-92)."""
+    st = bbh_train_stat()
+    _check(host_lib().bbh_train_async(ALGO[algo], C.cast(C.pointer(agent_cfg), C.c_void_p), C.byref(replay_cfg),
+                                      C.byref(env_cfg), C.byref(tcfg), C.byref(st)))
+    return _stat(st)

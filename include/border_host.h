@@ -1,0 +1,56 @@
+/*
+ * border_host.h -- C entry points of libborder_host.so: the reference's host-side training loops
+ * restated in C++ over border_b200.h (border_b200/host/border_host.hpp), runnable without a Rust
+ * toolchain.  These are NOT part of the drop-in boundary (that is border_b200.h); they exist so
+ * tests and benchmarks can drive the boundary exactly the way border_core::Trainer
+ * (border-core/src/trainer.rs:267-327) and border_async_trainer::train_async
+ * (border-async-trainer/src/util.rs:31-92) do.
+ */
+#ifndef BORDER_HOST_H
+#define BORDER_HOST_H
+#include <stdint.h>
+#include "border_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { BBH_ALGO_DQN = 0, BBH_ALGO_IQN = 1, BBH_ALGO_SAC = 2 };
+
+/* Synthetic zero-cost environment. */
+typedef struct {
+    int32_t obs_kind;        /* BB_U8 | BB_F32 */
+    uint32_t obs_elems;
+    uint64_t episode_len;    /* is_terminated every episode_len steps (0 = never) */
+    uint64_t truncate_len;   /* is_truncated every truncate_len steps (0 = never) */
+} bbh_env_cfg;
+
+/* TrainerConfig (border-core/src/trainer/config.rs:30-88) + AsyncTrainerConfig
+ * (border-async-trainer/src/async_trainer/config.rs:11-28) + ActorManagerConfig.n_buffer;
+ * 0 for an interval means usize::MAX ("never"), as in the reference defaults. */
+typedef struct {
+    uint64_t max_opts, opt_interval, eval_interval, flush_record_interval, record_compute_cost_interval,
+        record_agent_info_interval, warmup_period, save_interval;
+    uint64_t sync_interval, n_actors, n_buffer;
+    uint64_t env_seed;
+} bbh_trainer_cfg;
+
+typedef struct {
+    uint64_t env_steps, opt_steps, records, saves, buffer_len, agent_n_opts, samples_total, syncs;
+    double opt_seconds, sample_seconds, total_seconds, samples_per_sec, opt_per_sec;
+    float last_loss;
+} bbh_train_stat;
+
+const char* bbh_last_error(void);
+void bbh_trainer_cfg_default(bbh_trainer_cfg* cfg);
+/* Trainer::train with a SyntheticEnv, SimpleStepProcessor, a B200 agent (algo + its bb_*_cfg) and a
+ * B200 replay buffer. */
+int32_t bbh_train(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg, const bbh_env_cfg* env_cfg,
+                  const bbh_trainer_cfg* trainer_cfg, const char* save_dir, bbh_train_stat* out);
+/* train_async: n_actors actor threads (each its own agent + env, seed = actor id) -> learner. */
+int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg,
+                        const bbh_env_cfg* env_cfg, const bbh_trainer_cfg* trainer_cfg, bbh_train_stat* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -58,3 +58,13 @@ def test_errors_do_not_cross_the_abi():
         assert len(lib.bb_last_error()) > 0
     assert lib.bb_replay_len(None, None) != 0
     assert b"null" in lib.bb_last_error()
+
+
+def test_host_loop_library_loads():
+    from border_b200 import host_loops as H
+    lib = H.host_lib()
+    for name in ("bbh_last_error", "bbh_trainer_cfg_default", "bbh_train", "bbh_train_async"):
+        assert hasattr(lib, name)
+    c = H.trainer_cfg()
+    # TrainerConfig::default (trainer/config.rs:49-62), ActorManagerConfig::default n_buffer = 100
+    assert (c.max_opts, c.opt_interval, c.warmup_period, c.n_buffer, c.sync_interval) == (0, 1, 0, 100, 1)
