@@ -63,7 +63,6 @@ __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __res
     }
 }
 
-enum GemmMode { G_FWD = 0, G_FWD_U8, G_NN, G_WGRAD, G_WGRAD_U8 };
 
 template <int BM, int BN, int TM, int TN>
 static void launch_cfg(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
@@ -85,7 +84,16 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-static void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
+void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
+    if (a.M <= 0 || a.N <= 0) return;
+    const int use_tc = env_int("BB_TC", 0);  // read per call so tests can flip it; default = the faster path today
+    if (use_tc && a.M >= 64 && tc_gemm(c, mode, a)) return;  // tcgen05 path (tc_gemm.cu); tiny M stays on CUDA cores
+    gemm_simt(c, mode, a);
+}
+
+// fp32 CUDA-core path (gemm.cuh): the parity reference for the tensor-core path and the fallback
+// for tiny M.
+void gemm_simt(const Ctx& c, GemmMode mode, GemmArgs a) {
     if (a.M <= 0 || a.N <= 0) return;
     static const int variant = env_int("BB_GEMM_VARIANT", 0);  // A/B on B200 (profiles/r01_summary.md): 0 wins
     static const int fill = env_int("BB_GEMM_FILL", 3);
@@ -147,7 +155,7 @@ static void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
     }
 }
 
-static GemmArgs zero_args() {
+GemmArgs zero_args() {
     GemmArgs a;
     memset(&a, 0, sizeof(a));
     a.split_k = 1;

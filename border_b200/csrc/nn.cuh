@@ -35,6 +35,14 @@ struct Ctx {
     void mark(const char* kernel) const;  // no-op unless prof is set
 };
 
+// ---- GEMM dispatch ---------------------------------------------------------------------------
+struct GemmArgs;
+enum GemmMode { G_FWD = 0, G_FWD_U8, G_NN, G_WGRAD, G_WGRAD_U8 };
+void gemm(const Ctx& c, GemmMode mode, GemmArgs a);          // nn.cu: picks tcgen05 or CUDA-core tiles
+void gemm_simt(const Ctx& c, GemmMode mode, GemmArgs a);     // nn.cu: fp32 CUDA-core tiles only
+bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a);      // tc_gemm.cu: false => not handled
+GemmArgs zero_args();
+
 // ---- primitives (all row-major fp32) -------------------------------------------------------
 // Y[M][N] = act(X[M][K] W[N][K]^T + b)
 void linear_fwd(const Ctx& c, const float* X, long ldx, const float* W, const float* b, float* Y, int M, int N, int K,

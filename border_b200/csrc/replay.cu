@@ -15,6 +15,7 @@
 // mirror because all of them evolve deterministically.
 //
 // Compiled with -fmad=false: every float op here must round like the reference's scalar Rust.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "../../include/border_b200.h"
@@ -129,6 +130,42 @@ __device__ __forceinline__ void block_copy(uint8_t* __restrict__ dst, const uint
     }
 }
 
+// Two row chunks (obs and next_obs) at once: every thread issues up to 8 independent 16 B loads
+// (4 per array, streaming: no L1 allocation) before its first store, so a chunk of <= 16 KB costs
+// one memory round trip instead of one per 4 KB.
+__device__ __forceinline__ uint4 ld_stream16(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void block_copy2(uint8_t* __restrict__ d1, const uint8_t* __restrict__ s1,
+                                            uint8_t* __restrict__ d2, const uint8_t* __restrict__ s2, uint32_t bytes,
+                                            int vec) {
+    if (vec != 16) {
+        block_copy(d1, s1, bytes, vec);
+        block_copy(d2, s2, bytes, vec);
+        return;
+    }
+    const uint4* a = reinterpret_cast<const uint4*>(s1);
+    const uint4* b = reinterpret_cast<const uint4*>(s2);
+    uint4* da = reinterpret_cast<uint4*>(d1);
+    uint4* db = reinterpret_cast<uint4*>(d2);
+    const uint32_t n = bytes >> 4;
+    for (uint32_t base = 0; base < n; base += 4 * blockDim.x) {
+        uint4 ra[4], rb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t i = base + threadIdx.x + j * blockDim.x;
+            if (i < n) { ra[j] = ld_stream16(a + i); rb[j] = ld_stream16(b + i); }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t i = base + threadIdx.x + j * blockDim.x;
+            if (i < n) { da[i] = ra[j]; db[i] = rb[j]; }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- sample + gather
 
 struct SampleParams {
@@ -194,8 +231,8 @@ __global__ void __launch_bounds__(256) replay_sample_gather_kernel(SampleParams 
     const uint32_t off = c * p.chunk_bytes;
     if (off < p.obs_row_bytes) {
         uint32_t n = min(p.chunk_bytes, p.obs_row_bytes - off);
-        block_copy(p.b_obs + (size_t)b * p.obs_row_bytes + off, p.obs + ix * p.obs_row_bytes + off, n, p.vec);
-        block_copy(p.b_next_obs + (size_t)b * p.obs_row_bytes + off, p.next_obs + ix * p.obs_row_bytes + off, n, p.vec);
+        block_copy2(p.b_obs + (size_t)b * p.obs_row_bytes + off, p.obs + ix * p.obs_row_bytes + off,
+                    p.b_next_obs + (size_t)b * p.obs_row_bytes + off, p.next_obs + ix * p.obs_row_bytes + off, n, p.vec);
     }
     if (c == 0)
         for (uint32_t i = threadIdx.x; i < p.act_row_bytes; i += blockDim.x)
@@ -490,9 +527,11 @@ Replay::Replay(const bb_replay_cfg& c) : cfg(c) {
     obs_row_bytes = c.obs_elems * kind_size(c.obs_kind);
     act_row_bytes = c.act_elems * kind_size(c.act_kind);
     vec = (obs_row_bytes % 16 == 0) ? 16 : (obs_row_bytes % 4 == 0 ? 4 : 1);
-    // chunks: aim for ~4-8 KB per CTA and stream so that B=256 Atari rows give >= 1024 CTAs
-    uint32_t chunks = obs_row_bytes / 7056 ? obs_row_bytes / 7056 : 1;
-    if (chunks > 8) chunks = 8;
+    // chunks of <= 16 KB (= 4 x 16 B x 256 threads per array): one round trip per CTA; B=256 Atari
+    // rows give 2 x 256 = 512 CTAs, a single wave on 148 SMs x 4 resident CTAs
+    uint32_t chunks = (obs_row_bytes + 16383) / 16384;
+    if (const char* e = getenv("BB_REPLAY_CHUNKS")) chunks = (uint32_t)atoi(e) ? (uint32_t)atoi(e) : chunks;
+    if (chunks > 16) chunks = 16;
     chunk_bytes = (obs_row_bytes + chunks - 1) / chunks;
     chunk_bytes = (chunk_bytes + 15) / 16 * 16;
     n_chunks = (obs_row_bytes + chunk_bytes - 1) / chunk_bytes;
