@@ -43,6 +43,9 @@ struct GemmArgs {
     int split_k;           // >= 1
     int k_per_split;       // multiple of BK
     float* workspace;      // [split_k][M][N] when split_k > 1
+    // tcgen05 path: where the generic->async proxy fence runs (0 = in every producer thread after
+    // its st.shared, 1 = in the MMA-issuing thread after it has acquired the full barrier)
+    int fence_mode;
 };
 
 constexpr int kBK = 16;

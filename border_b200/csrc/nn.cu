@@ -86,7 +86,7 @@ static int env_int(const char* name, int dflt) {
 
 void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
     if (a.M <= 0 || a.N <= 0) return;
-    const int use_tc = env_int("BB_TC", 0);  // read per call so tests can flip it; default = the faster path today
+    const int use_tc = env_int("BB_TC", 1);  // read per call so tests can flip it (0 = fp32 CUDA-core tiles)
     if (use_tc && a.M >= 64 && tc_gemm(c, mode, a)) return;  // tcgen05 path (tc_gemm.cu); tiny M stays on CUDA cores
     gemm_simt(c, mode, a);
 }

@@ -4,21 +4,71 @@
 #include <vector>
 #include "nn.cuh"
 #include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
+#include "tc_gemm3.cuh"
 
 namespace bb {
 
-template <int BN>
+template <int BN, int STAGES, int PF, int MINB>
 static void tc_launch(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
-    constexpr size_t smem = (size_t)tc::STAGES * (2 * tc::BM * 128 + 2 * BN * 128) + 1024;
+    constexpr size_t smem = (size_t)STAGES * (2 * tc::BM * 128 + 2 * BN * 128) + 1024;
 #define BB_TC_LAUNCH(AK, BK_, AU, BU)                                                                           \
     do {                                                                                                        \
-        auto kern = tc_gemm_kernel<BN, AK, BK_, AU, BU>;                                                        \
+        auto kern = tc_gemm_kernel<BN, STAGES, PF, MINB, AK, BK_, AU, BU>;                                      \
         static bool configured = false;                                                                         \
         if (!configured) {                                                                                      \
             BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
             configured = true;                                                                                  \
         }                                                                                                       \
         kern<<<grid, tc::NTHREADS, smem, s>>>(a);                                                               \
+    } while (0)
+    switch (mode) {
+        case G_FWD: BB_TC_LAUNCH(true, true, false, false); break;
+        case G_FWD_U8: BB_TC_LAUNCH(true, true, true, false); break;
+        case G_NN: BB_TC_LAUNCH(true, false, false, false); break;
+        case G_WGRAD: BB_TC_LAUNCH(false, false, false, false); break;
+        case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true); break;
+    }
+#undef BB_TC_LAUNCH
+    BB_LAUNCHED();
+}
+
+template <int BN, int STAGES, int PF>
+static void tc_launch_persist(GemmMode mode, const GemmArgs& a, int tm, int tn, int total, int ctas, cudaStream_t s) {
+    constexpr size_t smem = (size_t)STAGES * (2 * tc::BM * 128 + 2 * BN * 128) + 1024;
+#define BB_TC_LAUNCH(AK, BK_, AU, BU)                                                                           \
+    do {                                                                                                        \
+        auto kern = tc_gemm_persist_kernel<BN, STAGES, PF, AK, BK_, AU, BU>;                                    \
+        static bool configured = false;                                                                         \
+        if (!configured) {                                                                                      \
+            BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+            configured = true;                                                                                  \
+        }                                                                                                       \
+        kern<<<ctas, tc2::NTHREADS, smem, s>>>(a, tm, tn, total);                                               \
+    } while (0)
+    switch (mode) {
+        case G_FWD: BB_TC_LAUNCH(true, true, false, false); break;
+        case G_FWD_U8: BB_TC_LAUNCH(true, true, true, false); break;
+        case G_NN: BB_TC_LAUNCH(true, false, false, false); break;
+        case G_WGRAD: BB_TC_LAUNCH(false, false, false, false); break;
+        case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true); break;
+    }
+#undef BB_TC_LAUNCH
+    BB_LAUNCHED();
+}
+
+template <int BN>
+static void tc_launch_tmem(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
+    constexpr size_t smem = (size_t)tc3::STAGES * (2 * BN * 128) + 1024;
+#define BB_TC_LAUNCH(AK, BK_, AU, BU)                                                                           \
+    do {                                                                                                        \
+        auto kern = tc_gemm_tmem_kernel<BN, AK, BK_, AU, BU>;                                                   \
+        static bool configured = false;                                                                         \
+        if (!configured) {                                                                                      \
+            BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+            configured = true;                                                                                  \
+        }                                                                                                       \
+        kern<<<grid, tc3::NTHREADS, smem, s>>>(a);                                                              \
     } while (0)
     switch (mode) {
         case G_FWD: BB_TC_LAUNCH(true, true, false, false); break;
@@ -38,7 +88,10 @@ __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __res
 
 bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     static const int fill_pct = getenv("BB_TC_FILL") ? atoi(getenv("BB_TC_FILL")) : 100;  // target CTAs, % of SMs
-    int BN = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : 128);
+    // 0: 3 stages, 1 CTA/SM; 1: two CTAs/SM for BN <= 64; 2 (default, fastest on B200): BN <= 64 always, two
+    // CTAs/SM; 3: persistent flat-pipelined kernel (tc_gemm2.cuh)
+    static const int cfg2 = getenv("BB_TC_CFG") ? atoi(getenv("BB_TC_CFG")) : 2;
+    int BN = a.N <= 32 ? 32 : ((a.N <= 64 || cfg2 >= 2) ? 64 : 128);
     int tm = (a.M + tc::BM - 1) / tc::BM, tn = (a.N + BN - 1) / BN;
     long tiles = (long)tm * tn;
     int kt = (a.K + tc::BK - 1) / tc::BK;
@@ -55,13 +108,32 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     a.split_k = split;
     a.k_per_split = kps;
     a.workspace = c.ws;
+    static const int fence_mode = getenv("BB_TC_FENCE") ? atoi(getenv("BB_TC_FENCE")) : 1;
+    static const int debug = getenv("BB_TC_DEBUG") ? atoi(getenv("BB_TC_DEBUG")) : 0;  // 1: no global loads, 2: no MMA
+    a.fence_mode = fence_mode | (debug << 4);
     dim3 grid(tn, tm, split);
-    switch (BN) {
-        case 32: tc_launch<32>(mode, a, grid, c.stream); break;
-        case 64: tc_launch<64>(mode, a, grid, c.stream); break;
-        default: tc_launch<128>(mode, a, grid, c.stream); break;
+    if (cfg2 == 4) {  // A operand in tensor memory (tc_gemm3.cuh)
+        if (BN == 32) tc_launch_tmem<32>(mode, a, grid, c.stream);
+        else tc_launch_tmem<64>(mode, a, grid, c.stream);
+    } else if (cfg2 == 3) {  // persistent, flat-pipelined kernel (tc_gemm2.cuh)
+        int total = tm * tn * split;
+        int ctas = std::min(total, c.sms);
+        if (BN == 32) tc_launch_persist<32, 4, 3>(mode, a, tm, tn, total, ctas, c.stream);
+        else tc_launch_persist<64, 4, 3>(mode, a, tm, tn, total, ctas, c.stream);
+    } else if (cfg2 >= 1) {
+        switch (BN) {
+            case 32: tc_launch<32, 2, 2, 2>(mode, a, grid, c.stream); break;
+            case 64: tc_launch<64, 2, 2, 2>(mode, a, grid, c.stream); break;
+            default: tc_launch<128, 3, 3, 1>(mode, a, grid, c.stream); break;
+        }
+    } else {
+        switch (BN) {
+            case 32: tc_launch<32, 3, 3, 1>(mode, a, grid, c.stream); break;
+            case 64: tc_launch<64, 3, 3, 1>(mode, a, grid, c.stream); break;
+            default: tc_launch<128, 3, 3, 1>(mode, a, grid, c.stream); break;
+        }
     }
-    c.mark(BN == 32 ? "tc_gemm128x32" : (BN == 64 ? "tc_gemm128x64" : "tc_gemm128x128"));
+    c.mark(cfg2 == 4 ? (BN == 32 ? "tc_tmem128x32" : "tc_tmem128x64") : cfg2 == 3 ? (BN == 32 ? "tc_persist128x32" : "tc_persist128x64") : (BN == 32 ? "tc_gemm128x32" : (BN == 64 ? "tc_gemm128x64" : "tc_gemm128x128")));
     if (split > 1) {
         size_t total = (size_t)a.M * a.N;
         if (split >= 16) {
@@ -124,5 +196,43 @@ extern "C" int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, in
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dbias); cudaFree(c.ws);
     BB_CUDA(e);
     BB_CHECK(flag == 0, "tcgen05 pipeline timed out (g_tc_error)");
+    BB_API_END
+}
+
+// Timing hook: `iters` back-to-back launches of one dense GEMM (device-resident operands),
+// CUDA events on the launching stream; returns the mean milliseconds per GEMM.
+extern "C" int32_t bb_bench_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, int32_t N, int32_t K,
+                                 int32_t iters, float* ms_out) {
+    BB_API_BEGIN
+    using namespace bb;
+    DeviceGuard g(device);
+    Ctx c;
+    c.device = device; c.sms = num_sms(device); c.stream = device_stream(device);
+    c.ws_floats = 8u << 20;
+    c.ws = dev_alloc<float>(c.ws_floats);
+    size_t na = (size_t)M * K, nb = (size_t)N * K, nc = (size_t)M * N;
+    float *dA = dev_alloc<float>(na), *dB = dev_alloc<float>(nb), *dC = dev_alloc_zero<float>(nc, c.stream);
+    fill_uniform(c, dA, na, 1.0f, 1);
+    fill_uniform(c, dB, nb, 1.0f, 2);
+    GemmArgs a = zero_args();
+    a.A = dA; a.B = dB; a.C = dC; a.M = M; a.N = N; a.K = K; a.ldc = N;
+    GemmMode gm;
+    if (mode == 0) { gm = G_FWD; a.lda = K; a.ldb = K; }
+    else if (mode == 2) { gm = G_NN; a.lda = K; a.ldb = N; }
+    else { gm = G_WGRAD; a.lda = M; a.ldb = N; }
+    cudaEvent_t e0, e1;
+    BB_CUDA(cudaEventCreate(&e0));
+    BB_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) { GemmArgs b = a; if (use_tc) tc_gemm(c, gm, b); else gemm_simt(c, gm, b); }
+    BB_CUDA(cudaEventRecord(e0, c.stream));
+    for (int i = 0; i < iters; ++i) { GemmArgs b = a; if (use_tc) tc_gemm(c, gm, b); else gemm_simt(c, gm, b); }
+    BB_CUDA(cudaEventRecord(e1, c.stream));
+    BB_CUDA(cudaStreamSynchronize(c.stream));
+    float ms = 0.f;
+    BB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(c.ws);
+    BB_CHECK(tc_error_flag() == 0, "tcgen05 pipeline timed out (g_tc_error)");
     BB_API_END
 }

@@ -29,7 +29,7 @@ __device__ int g_tc_error = 0;
 
 namespace tc {
 
-constexpr int BM = 128, BK = 32, STAGES = 3, NPROD = 256, NTHREADS = 288;
+constexpr int BM = 128, BK = 32, NPROD = 256, NTHREADS = 288;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -50,6 +50,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: returns false (and flags the error) instead of spinning forever
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 22); ++it)
         if (mbar_try_wait(bar, parity)) return true;
     atomicExch(&g_tc_error, 1);
@@ -106,8 +107,11 @@ __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 1
 
 // A_KSRC: A(m,k) is k-contiguous (dense rows or gather rowbase[m] + koff[k]); else A(m,k) = A[k*lda + m].
 // B_KSRC: B(k,n) = B[n*ldb + k]; else n-contiguous (dense B[k*ldb + n] or gather rowbase[k] + noff[n]).
-template <int BN, bool A_KSRC, bool B_KSRC, bool A_U8, bool B_U8>
-__global__ void __launch_bounds__(tc::NTHREADS, 1) tc_gemm_kernel(GemmArgs g) {
+// STAGES shared-memory stages, PF register sets of prefetched operand data per producer thread,
+// MINB co-resident CTAs per SM (two small CTAs overlap one's prologue/epilogue with the other's
+// main loop).
+template <int BN, int STAGES, int PF, int MINB, bool A_KSRC, bool B_KSRC, bool A_U8, bool B_U8>
+__global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g) {
     using namespace tc;
     constexpr uint32_t A_TILE = BM * 128, B_TILE = BN * 128;       // bytes per hi (or lo) tile
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) tc_gemm_kernel(GemmArgs g) {
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(smem_u32(&full_bar[s]), NPROD);
+            mbar_init(smem_u32(&full_bar[s]), NPROD / 32);  // one arrive per producer warp
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         mbar_init(smem_u32(&accum_bar), 1);
@@ -169,9 +173,41 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) tc_gemm_kernel(GemmArgs g) {
                 b_base[i] = (r < BN && n < g.N) ? (long)n * g.ldb : -1;
             }
         }
-        float4 ra[2][A_LD], rb[2][B_LD];
+        // The only per-stage table entries are a_koff[k] (k-contiguous gather A) and b_rowbase[k]
+        // (n-contiguous gather B); they are fetched two stages ahead of the data loads that depend on
+        // them, and the data loads run two stages ahead of the shared-memory stores (3 register sets).
+        long b_noff_r[B_LD];
+        if (!B_KSRC) {
+#pragma unroll
+            for (int i = 0; i < B_LD; ++i) {
+                int n = n0 + (warp + 8 * i) * 4;
+                b_noff_r[i] = (n < g.N) ? (g.b_noff ? (long)g.b_noff[n] : (long)n) : 0;
+            }
+        }
+        float4 ra[PF][A_LD], rb[PF][B_LD];
+        long ta[PF], tb[PF];
 
-        auto load = [&](float4* pa, float4* pb, int ks) {
+        auto load_tab = [&](long& oa, long& ob, int ks) {
+            const int k0 = k_begin + ks * BK;
+            oa = 0; ob = 0;
+            if (A_KSRC) {
+                int k = k0 + (tid & 7) * 4;
+                if (k < k_end) oa = g.a_koff ? (long)__ldg(g.a_koff + k) : (long)k;
+            }
+            if (!B_KSRC) {
+                int k = k0 + lane;
+                if (k < k_end) ob = g.b_rowbase ? (long)__ldg(g.b_rowbase + k) : (long)k * g.ldb;
+            }
+        };
+
+        auto load = [&](float4* pa, float4* pb, int ks, long tabA, long tabB) {
+            if (g.fence_mode & 16) {
+#pragma unroll
+                for (int i = 0; i < A_LD; ++i) pa[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                for (int i = 0; i < B_LD; ++i) pb[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                return;
+            }
             const int k0 = k_begin + ks * BK;
 #pragma unroll
             for (int i = 0; i < A_LD; ++i) {
@@ -179,9 +215,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) tc_gemm_kernel(GemmArgs g) {
                 if (A_KSRC) {
                     int k = k0 + (tid & 7) * 4;
                     if (a_base[i] >= 0 && k < k_end) {
-                        long off = a_base[i] + (g.a_koff ? (long)g.a_koff[k] : (long)k);
+                        long off = a_base[i] + tabA;
                         if (A_U8) {
-                            v = u8x4_to_float4(*reinterpret_cast<const uint32_t*>(Au + off));
+                            v = u8x4_to_float4(__ldg(reinterpret_cast<const uint32_t*>(Au + off)));
                             if (k + 1 >= k_end) v.y = 0.f;
                             if (k + 2 >= k_end) v.z = 0.f;
                             if (k + 3 >= k_end) v.w = 0.f;
@@ -230,10 +266,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) tc_gemm_kernel(GemmArgs g) {
                     int n4 = warp + 8 * i;          // group of 4 consecutive n
                     int n = n0 + n4 * 4;
                     if (n4 * 4 < BN && k < k_end && n < g.N) {
-                        long off = (g.b_rowbase ? (long)g.b_rowbase[k] : (long)k * g.ldb) +
-                                   (g.b_noff ? (long)g.b_noff[n] : (long)n);
+                        long off = tabB + b_noff_r[i];
                         if (B_U8) {
-                            v = u8x4_to_float4(*reinterpret_cast<const uint32_t*>(Bu + off));
+                            v = u8x4_to_float4(__ldg(reinterpret_cast<const uint32_t*>(Bu + off)));
                         } else if (b_vec && n + 3 < g.N && ((off & 3) == 0)) {
                             v = __ldg(reinterpret_cast<const float4*>(Bf + off));
                         } else {
@@ -289,17 +324,31 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) tc_gemm_kernel(GemmArgs g) {
                     }
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> async proxy (UMMA)
-            mbar_arrive(smem_u32(&full_bar[s]));
+            // generic stores -> async proxy (UMMA).  A fence waits for ALL of the thread's outstanding
+            // memory operations, including the prefetched global loads, so the writer-side fence
+            // serialises the load latency into every stage; fence_mode 1 moves it to the consumer.
+            if ((g.fence_mode & 1) == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();  // orders the warp's st.shared before lane 0's release-arrive (256 arrives/stage were costly)
+            if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
         };
 
-        if (nks > 0) load(ra[0], rb[0], 0);
-        for (int ks = 0; ks < nks; ks += 2) {
-            if (ks + 1 < nks) load(ra[1], rb[1], ks + 1);
-            store(ra[0], rb[0], ks);
-            if (ks + 1 < nks) {
-                if (ks + 2 < nks) load(ra[0], rb[0], ks + 2);
-                store(ra[1], rb[1], ks + 1);
+        // software pipeline: tables PF stages ahead, data PF-1 stages ahead, stores now
+#pragma unroll
+        for (int j = 0; j < PF; ++j)
+            if (j < nks) load_tab(ta[j], tb[j], j);
+#pragma unroll
+        for (int j = 0; j < PF - 1; ++j)
+            if (j < nks) load(ra[j], rb[j], j, ta[j], tb[j]);
+        for (int ks = 0; ks < nks; ks += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int k = ks + u;
+                if (k < nks) {
+                    if (k + PF - 1 < nks)
+                        load(ra[(u + PF - 1) % PF], rb[(u + PF - 1) % PF], k + PF - 1, ta[(u + PF - 1) % PF], tb[(u + PF - 1) % PF]);
+                    if (k + PF < nks) load_tab(ta[u], tb[u], k + PF);
+                    store(ra[u], rb[u], k);
+                }
             }
         }
 
@@ -368,12 +417,14 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) tc_gemm_kernel(GemmArgs g) {
             const int s = ks % STAGES;
             const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
             if (!mbar_wait(smem_u32(&full_bar[s]), ph)) { alive = false; break; }
+            if ((g.fence_mode & 1) == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = tiles + s * STAGE_BYTES, a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
             const uint64_t da_hi = make_desc(a_hi), da_lo = make_desc(a_lo), db_hi = make_desc(b_hi), db_lo = make_desc(b_lo);
 #pragma unroll
             for (int k4 = 0; k4 < BK / 8; ++k4) {
                 const uint64_t adv = (uint64_t)(k4 * 2);  // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle atom
+                if (g.fence_mode & 32) continue;
                 mma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, (ks | k4) ? 1u : 0u);
                 mma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
                 mma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);

@@ -62,6 +62,10 @@ int32_t bb_test_powf(int32_t device, const float* host_x, const float* host_y, f
 int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, int32_t N, int32_t K,
                      const float* A, const float* B, const float* bias, int32_t relu, float* C_out);
 
+/* Timing hook: mean milliseconds of `iters` back-to-back launches of one dense GEMM. */
+int32_t bb_bench_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, int32_t N, int32_t K,
+                      int32_t iters, float* ms_out);
+
 /* ------------------------------------------------------------------------------------------
  * Replay buffer: SimpleReplayBuffer<O, A> (border-core/src/generic_replay_buffer/base.rs:86-426)
  * with TensorBatch storage (border-tch-agent/src/tensor_batch.rs:44-120), as a ring of SoA

@@ -61,3 +61,11 @@ def test_dqn_parity_holds_on_the_tensor_core_path(monkeypatch):
     _run("cnn", 32, "Mse", False, per=False, clip=False, steps=3, lr=1e-4)
     _run("cnn", 256, "SmoothL1", True, per=False, clip=False, steps=1, lr=1e-4)
     _run("mlp", 64, "Mse", False, per=False, clip=False, steps=3)
+
+
+def test_dqn_parity_holds_on_the_cuda_core_path(monkeypatch):
+    """BB_TC=0: the fp32 CUDA-core implicit GEMM (the tensor-core path's on-device reference)."""
+    monkeypatch.setenv("BB_TC", "0")
+    from tests.test_dqn_gpu import _run
+    _run("cnn", 32, "Mse", False, per=False, clip=False, steps=2, lr=1e-4)
+    _run("mlp", 64, "SmoothL1", True, per=False, clip=False, steps=2)
