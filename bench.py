@@ -310,13 +310,16 @@ def roofline_for(label, ms, step_ms, pk):
     phase, layer, kernel = label.split(":")
     name = layer.split(".")[0]
     macs = FWD_MACS.get(name)
-    if macs is not None and kernel.startswith("gemm"):
+    if macs is not None and ("gemm" in kernel or kernel.startswith("tc_")):
         flop = 2.0 * B * macs  # forward, wgrad and dgrad of a layer each contract the same MACs
         tf = flop / (ms * 1e-3) / 1e12
+        on_tc = kernel.startswith("tc_")
         return {"kernel": label, "bound": "tensor", "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": tf / pk["tf_sust"], "traffic": None, "ms_per_launch": ms, "share_of_step": ms / step_ms,
                 "algorithmic_flop": flop, "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside the step)",
-                "note": "fp32 CUDA-core implicit GEMM (parity path); peak is the dense bf16 tensor figure"}
+                "note": ("tcgen05 kind::tf32, 3 MMA passes per product (3xTF32 for fp32 parity): algorithmic FLOPs are "
+                         "counted once, so the tensor pipe does 3x this; peak is the dense bf16 figure (TF32 peak is half)")
+                if on_tc else "fp32 CUDA-core implicit GEMM; peak is the dense bf16 tensor figure"}
     return {"kernel": label, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
             "traffic": None, "ms_per_launch": ms, "share_of_step": ms / step_ms, "peak_source": pk["src"]}
 

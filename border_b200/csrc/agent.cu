@@ -54,7 +54,7 @@ void Agent::init_base(int dev) {
     ctx.sms = num_sms(dev);
     ctx.stream = device_stream(dev);
     ctx.ws_floats = 8u << 20;  // 32 MB split-K / reduction workspace
-    ctx.ws = dev_alloc<float>(ctx.ws_floats);
+    ctx.ws = dev_alloc_zero<float>(ctx.ws_floats, ctx.stream);  // the tail holds colsum's block counters (must start at 0)
     BB_CUDA(cudaMallocHost(&h_scratch, 4096 * sizeof(float)));
     d_scratch = dev_alloc<float>(1 << 20);
 }

@@ -46,6 +46,9 @@ struct GemmArgs {
     // tcgen05 path: where the generic->async proxy fence runs (0 = in every producer thread after
     // its st.shared, 1 = in the MMA-issuing thread after it has acquired the full barrier)
     int fence_mode;
+    // tcgen05 path only: store C transposed (element (m, n) at C[n*ldc + m]); used by the conv weight
+    // gradient, which is computed as dW^T = im2col^T dY so that the long K*K*C axis fills the 128 MMA rows
+    int trans_out;
 };
 
 constexpr int kBK = 16;

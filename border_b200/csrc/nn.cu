@@ -73,6 +73,7 @@ static void launch_cfg(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t
         case G_NN: gemm_kernel<BM, BN, TM, TN, true, false, false, false><<<grid, NT, 0, s>>>(a); break;
         case G_WGRAD: gemm_kernel<BM, BN, TM, TN, false, false, false, false><<<grid, NT, 0, s>>>(a); break;
         case G_WGRAD_U8: gemm_kernel<BM, BN, TM, TN, false, false, false, true><<<grid, NT, 0, s>>>(a); break;
+        case G_WGRAD_AU8: throw Error("G_WGRAD_AU8 exists on the tcgen05 path only");
     }
     BB_LAUNCHED();
 }
@@ -87,7 +88,8 @@ static int env_int(const char* name, int dflt) {
 void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
     if (a.M <= 0 || a.N <= 0) return;
     const int use_tc = env_int("BB_TC", 1);  // read per call so tests can flip it (0 = fp32 CUDA-core tiles)
-    if (use_tc && a.M >= 64 && tc_gemm(c, mode, a)) return;  // tcgen05 path (tc_gemm.cu); tiny M stays on CUDA cores
+    // tcgen05 path (tc_gemm.cu); tiny problems (policy forward, the 6-wide output layer) stay on CUDA cores
+    if (use_tc && a.M >= 64 && (long)a.M * a.N * a.K >= (1L << 22) && a.N >= 16 && tc_gemm(c, mode, a)) return;
     gemm_simt(c, mode, a);
 }
 
@@ -110,7 +112,8 @@ void gemm_simt(const Ctx& c, GemmMode mode, GemmArgs a) {
     if (tiles < want && kt >= 8) {
         split = (int)std::min<long>((want + tiles - 1) / tiles, kt / 4);
         size_t per = (size_t)a.M * a.N;
-        if (per * split > c.ws_floats) split = (int)(c.ws_floats / per);
+        const size_t usable = c.ws_floats - 1024;  // the last 1024 words hold colsum's block counters
+        if (per * split > usable) split = (int)(usable / per);
         if (split < 1) split = 1;
     }
     int kps = ((kt + split - 1) / split) * kBK;
@@ -181,27 +184,56 @@ __global__ void colsum_partial_kernel(const float* __restrict__ Y, float* __rest
         part[(size_t)blockIdx.y * N + n] = t;
     }
 }
-// one warp per column: lanes stride over the R partials, then a fixed-order shuffle tree
-__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int N, int R) {
-    int n = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-    int lane = threadIdx.x & 31;
-    if (n >= N) return;
-    float t = 0.f;
-    for (int r = lane; r < R; r += 32) t += part[(size_t)r * N + n];
+// Column sums in ONE launch: block (chunk, r) sums its row slice of 32 columns; the last block of a
+// chunk to finish (counter in the workspace tail) adds the R partials in index order (deterministic).
+__global__ void colsum_fused_kernel(const float* __restrict__ Y, float* __restrict__ part, unsigned int* __restrict__ counters,
+                                    float* __restrict__ out, int M, int N, int rows_per_block, int R) {
+    __shared__ float s[8][33];
+    __shared__ bool s_last;
+    int n = blockIdx.x * 32 + threadIdx.x;
+    int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float acc = 0.f;
+    if (n < N)
+        for (int m = r0 + threadIdx.y; m < r1; m += 8) acc += Y[(size_t)m * N + n];
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) out[n] = t;
+        for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x];
+        part[(size_t)blockIdx.y * N + n] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_last = (atomicAdd(&counters[blockIdx.x], 1u) == (unsigned)R - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // 8 row-groups x 32 columns: thread (x, y) sums partials y, y+8, ... of column n, then the 8 groups in order
+    float t = 0.f;
+    if (n < N)
+        for (int r = threadIdx.y; r < R; r += 8) t += part[(size_t)r * N + n];
+    s[threadIdx.y][threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v += s[i][threadIdx.x];
+        out[n] = v;
+    }
+    if (threadIdx.x == 0 && threadIdx.y == 0) counters[blockIdx.x] = 0;
 }
 
 void colsum(const Ctx& c, const float* dY, float* db, int M, int N) {
     int chunks = (N + 31) / 32;
     int R = std::max(1, std::min(std::min(256, (M + 31) / 32), (2 * c.sms + chunks - 1) / chunks));
-    while ((size_t)R * N > c.ws_floats && R > 1) R /= 2;
+    const size_t counter_floats = 1024;  // tail of the workspace holds the per-chunk counters (zeroed at creation)
+    while ((size_t)R * N > c.ws_floats - counter_floats && R > 1) R /= 2;
     int rpb = (M + R - 1) / R;
     R = (M + rpb - 1) / rpb;
-    colsum_partial_kernel<<<dim3(chunks, R), dim3(32, 8), 0, c.stream>>>(dY, c.ws, M, N, rpb);
-    BB_LAUNCHED();
-    colsum_final_kernel<<<(N + 7) / 8, 256, 0, c.stream>>>(c.ws, db, N, R);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(c.ws + c.ws_floats - counter_floats);
+    BB_CHECK(chunks <= (int)counter_floats, "colsum: too many column chunks");
+    colsum_fused_kernel<<<dim3(chunks, R), dim3(32, 8), 0, c.stream>>>(dY, c.ws, counters, db, M, N, rpb, R);
     BB_LAUNCHED();
     c.mark("colsum");
 }
@@ -245,6 +277,20 @@ void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, co
 
 void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW, float* db) {
     // dW[OC][K] = sum_m dY[m][OC]^T im2col(X)[m][K]
+    // (float inputs only: for the u8 conv1 frames the transposed 4-byte gathers are slower than the
+    // CUDA-core kernel -- 115 us vs 67 us at B=256)
+    if (!g.u8_chw && env_int("BB_TC", 1) && env_int("BB_TC_WGRAD_T", 1)) {
+        // tensor-core form: dW^T[K][OC] = im2col(X)^T dY, stored transposed.  The long K = KH*KW*C axis
+        // fills the 128 MMA rows (OC is only 32 / 64), A is the transposed gather (m-part from koff,
+        // k-part from rowbase), B = dY rows.
+        GemmArgs t = zero_args();
+        t.A = X; t.a_rowbase = g.koff; t.a_koff = g.rowbase; t.B = dY; t.ldb = g.OC; t.C = dW; t.ldc = g.K();
+        t.M = g.K(); t.N = g.OC; t.K = g.M(); t.trans_out = 1;
+        if (tc_gemm(c, g.u8_chw ? G_WGRAD_AU8 : G_WGRAD, t)) {
+            if (db) colsum(c, dY, db, g.M(), g.OC);
+            return;
+        }
+    }
     GemmArgs a = zero_args();
     a.A = dY; a.lda = g.OC; a.B = X; a.b_rowbase = g.rowbase; a.b_noff = g.koff; a.C = dW; a.ldc = g.K();
     a.M = g.OC; a.N = g.K(); a.K = g.M();

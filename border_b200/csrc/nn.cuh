@@ -37,7 +37,7 @@ struct Ctx {
 
 // ---- GEMM dispatch ---------------------------------------------------------------------------
 struct GemmArgs;
-enum GemmMode { G_FWD = 0, G_FWD_U8, G_NN, G_WGRAD, G_WGRAD_U8 };
+enum GemmMode { G_FWD = 0, G_FWD_U8, G_NN, G_WGRAD, G_WGRAD_U8, G_WGRAD_AU8 /* tcgen05 only: u8 m-contiguous A */ };
 void gemm(const Ctx& c, GemmMode mode, GemmArgs a);          // nn.cu: picks tcgen05 or CUDA-core tiles
 void gemm_simt(const Ctx& c, GemmMode mode, GemmArgs a);     // nn.cu: fp32 CUDA-core tiles only
 bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a);      // tc_gemm.cu: false => not handled

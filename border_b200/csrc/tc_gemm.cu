@@ -28,6 +28,7 @@ static void tc_launch(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t 
         case G_NN: BB_TC_LAUNCH(true, false, false, false); break;
         case G_WGRAD: BB_TC_LAUNCH(false, false, false, false); break;
         case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true); break;
+        case G_WGRAD_AU8: BB_TC_LAUNCH(false, false, true, false); break;
     }
 #undef BB_TC_LAUNCH
     BB_LAUNCHED();
@@ -52,6 +53,7 @@ static void tc_launch_persist(GemmMode mode, const GemmArgs& a, int tm, int tn, 
         case G_NN: BB_TC_LAUNCH(true, false, false, false); break;
         case G_WGRAD: BB_TC_LAUNCH(false, false, false, false); break;
         case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true); break;
+        case G_WGRAD_AU8: BB_TC_LAUNCH(false, false, true, false); break;
     }
 #undef BB_TC_LAUNCH
     BB_LAUNCHED();
@@ -76,6 +78,7 @@ static void tc_launch_tmem(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStre
         case G_NN: BB_TC_LAUNCH(true, false, false, false); break;
         case G_WGRAD: BB_TC_LAUNCH(false, false, false, false); break;
         case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true); break;
+        case G_WGRAD_AU8: BB_TC_LAUNCH(false, false, true, false); break;
     }
 #undef BB_TC_LAUNCH
     BB_LAUNCHED();
@@ -97,10 +100,11 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     int kt = (a.K + tc::BK - 1) / tc::BK;
     int split = 1;
     long want = (long)c.sms * fill_pct / 100;
-    if (tiles < want && kt >= 8) {
+    if (tiles * 2 <= want && kt >= 8) {  // a split costs a reduce launch: only when under half the SMs would work
         split = (int)std::min<long>((want + tiles - 1) / tiles, kt / 4);
         size_t per = (size_t)a.M * a.N;
-        if (per * split > c.ws_floats) split = (int)(c.ws_floats / per);
+        const size_t usable = c.ws_floats - 1024;  // the last 1024 words hold colsum's block counters
+        if (per * split > usable) split = (int)(usable / per);
         if (split < 1) split = 1;
     }
     int kps = ((kt + split - 1) / split) * tc::BK;
@@ -112,10 +116,11 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     static const int debug = getenv("BB_TC_DEBUG") ? atoi(getenv("BB_TC_DEBUG")) : 0;  // 1: no global loads, 2: no MMA
     a.fence_mode = fence_mode | (debug << 4);
     dim3 grid(tn, tm, split);
-    if (cfg2 == 4) {  // A operand in tensor memory (tc_gemm3.cuh)
+    const bool v1_only = a.trans_out || mode == G_WGRAD_AU8;  // transposed store / u8 m-contiguous A live in tc_gemm.cuh
+    if (cfg2 == 4 && !v1_only) {  // A operand in tensor memory (tc_gemm3.cuh)
         if (BN == 32) tc_launch_tmem<32>(mode, a, grid, c.stream);
         else tc_launch_tmem<64>(mode, a, grid, c.stream);
-    } else if (cfg2 == 3) {  // persistent, flat-pipelined kernel (tc_gemm2.cuh)
+    } else if (cfg2 == 3 && !v1_only) {  // persistent, flat-pipelined kernel (tc_gemm2.cuh)
         int total = tm * tn * split;
         int ctas = std::min(total, c.sms);
         if (BN == 32) tc_launch_persist<32, 4, 3>(mode, a, tm, tn, total, ctas, c.stream);
@@ -136,12 +141,13 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     c.mark(cfg2 == 4 ? (BN == 32 ? "tc_tmem128x32" : "tc_tmem128x64") : cfg2 == 3 ? (BN == 32 ? "tc_persist128x32" : "tc_persist128x64") : (BN == 32 ? "tc_gemm128x32" : (BN == 64 ? "tc_gemm128x64" : "tc_gemm128x128")));
     if (split > 1) {
         size_t total = (size_t)a.M * a.N;
+        const int rows = a.trans_out ? a.N : a.M, cols = a.trans_out ? a.M : a.N;  // layout of the partials = layout of C
         if (split >= 16) {
             int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
-            splitk_reduce8_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+            splitk_reduce8_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask);
         } else {
             int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
-            splitk_reduce_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+            splitk_reduce_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask);
         }
         BB_LAUNCHED();
         c.mark("splitk_reduce");
@@ -169,7 +175,7 @@ extern "C" int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, in
     Ctx c;
     c.device = device; c.sms = num_sms(device); c.stream = device_stream(device);
     c.ws_floats = 8u << 20;
-    c.ws = dev_alloc<float>(c.ws_floats);
+    c.ws = dev_alloc_zero<float>(c.ws_floats, c.stream);
     size_t na = (size_t)M * K, nb = (size_t)N * K, nc = (size_t)M * N;
     float *dA = dev_alloc<float>(na), *dB = dev_alloc<float>(nb), *dC = dev_alloc_zero<float>(nc, c.stream), *dbias = nullptr;
     BB_CUDA(cudaMemcpyAsync(dA, A, na * 4, cudaMemcpyHostToDevice, c.stream));
@@ -209,7 +215,7 @@ extern "C" int32_t bb_bench_gemm(int32_t device, int32_t mode, int32_t use_tc, i
     Ctx c;
     c.device = device; c.sms = num_sms(device); c.stream = device_stream(device);
     c.ws_floats = 8u << 20;
-    c.ws = dev_alloc<float>(c.ws_floats);
+    c.ws = dev_alloc_zero<float>(c.ws_floats, c.stream);
     size_t na = (size_t)M * K, nb = (size_t)N * K, nc = (size_t)M * N;
     float *dA = dev_alloc<float>(na), *dB = dev_alloc<float>(nb), *dC = dev_alloc_zero<float>(nc, c.stream);
     fill_uniform(c, dA, na, 1.0f, 1);

@@ -173,6 +173,16 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                 b_base[i] = (r < BN && n < g.N) ? (long)n * g.ldb : -1;
             }
         }
+        // m-contiguous A: address = koff-part(k) + m-part(m); dense is k*lda + m, a gather (the transposed
+        // im2col matrix of a conv weight gradient) takes the m-part from a_rowbase[m], the k-part from a_koff[k]
+        long a_moff[A_LD];
+        if (!A_KSRC) {
+#pragma unroll
+            for (int i = 0; i < A_LD; ++i) {
+                int m = m0 + (warp + 8 * i) * 4;
+                a_moff[i] = m < g.M ? (g.a_rowbase ? (long)g.a_rowbase[m] : (long)m) : 0;
+            }
+        }
         // The only per-stage table entries are a_koff[k] (k-contiguous gather A) and b_rowbase[k]
         // (n-contiguous gather B); they are fetched two stages ahead of the data loads that depend on
         // them, and the data loads run two stages ahead of the shared-memory stores (3 register sets).
@@ -193,6 +203,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
             if (A_KSRC) {
                 int k = k0 + (tid & 7) * 4;
                 if (k < k_end) oa = g.a_koff ? (long)__ldg(g.a_koff + k) : (long)k;
+            } else {
+                int k = k0 + lane;
+                if (k < k_end) oa = g.a_koff ? (long)__ldg(g.a_koff + k) : (long)k * g.lda;
             }
             if (!B_KSRC) {
                 int k = k0 + lane;
@@ -234,13 +247,19 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                     int k = k0 + lane;
                     int m = m0 + (warp + 8 * i) * 4;
                     if (k < k_end && m < g.M) {
-                        long off = (long)k * g.lda + m;
-                        if (a_vec && m + 3 < g.M) v = __ldg(reinterpret_cast<const float4*>(Af + off));
-                        else {
+                        long off = tabA + a_moff[i];
+                        if (A_U8) {
+                            v = u8x4_to_float4(__ldg(reinterpret_cast<const uint32_t*>(Au + off)));
+                            if (m + 1 >= g.M) v.y = 0.f;
+                            if (m + 2 >= g.M) v.z = 0.f;
+                            if (m + 3 >= g.M) v.w = 0.f;
+                        } else if (a_vec && m + 3 < g.M && ((off & 3) == 0)) {
+                            v = __ldg(reinterpret_cast<const float4*>(Af + off));
+                        } else {
                             v.x = __ldg(Af + off);
-                            if (m + 1 < g.M) v.y = __ldg(Af + off + 1);
-                            if (m + 2 < g.M) v.z = __ldg(Af + off + 2);
-                            if (m + 3 < g.M) v.w = __ldg(Af + off + 3);
+                            if (m + 1 < g.M) v.y = __ldg(Af + off + (g.a_rowbase ? g.a_rowbase[m + 1] - g.a_rowbase[m] : 1));
+                            if (m + 2 < g.M) v.z = __ldg(Af + off + (g.a_rowbase ? g.a_rowbase[m + 2] - g.a_rowbase[m] : 2));
+                            if (m + 3 < g.M) v.w = __ldg(Af + off + (g.a_rowbase ? g.a_rowbase[m + 3] - g.a_rowbase[m] : 3));
                         }
                     }
                 }
@@ -357,7 +376,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const bool direct = g.split_k <= 1;
         float* out = direct ? g.C : g.workspace + (size_t)blockIdx.z * g.M * g.N;
-        const int ldo = direct ? g.ldc : g.N;
+        const int ldo = direct ? g.ldc : (g.trans_out ? g.M : g.N);
         const int q = warp & 3;                     // TMEM lane quarter this warp may read
         const int m = m0 + q * 32 + lane;
         constexpr int HALF = BN / 2 < 16 ? 16 : BN / 2;   // columns per warp-pair member
@@ -396,6 +415,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                                 if (g.relu) v[j] = fmaxf(v[j], 0.f);
                                 if (g.mask) v[j] = g.mask[(size_t)m * g.ldc + n + j] > 0.f ? v[j] : 0.f;
                             }
+                        }
+                        if (g.trans_out) {  // C^T: consecutive lanes (rows m) write consecutive addresses
+                            for (int j = 0; j < 4; ++j)
+                                if (n + j < g.N) out[(size_t)(n + j) * ldo + m] = v[j];
+                            continue;
                         }
                         float* dst = out + (size_t)m * ldo + n;
                         if (n + 3 < g.N && ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0))

@@ -39,15 +39,17 @@ def _torch_batch(b):
     return out
 
 
-def _check_params(agent, oracle, lr, model="qnet", ref=None, tol_lr=2e-2):
+def _check_params(agent, oracle, lr, model="qnet", ref=None, tol_lr=2e-2, n_steps=1):
     got = agent.named_parameters(model)
     ref = ref if ref is not None else oracle.qnet
     for k, v in ref.items():
         d = np.abs(got[k] - v.detach().numpy())
         # Adam's step is lr * g/(|g|+eps): elements whose gradient is ~eps (1e-8) amplify rounding
         # noise, so bound every element by a few steps and all but a sliver tightly.
+        # Nothing re-synchronises the two trajectories between steps, so the sliver grows with the
+        # number of optimizer steps taken (each adds its own near-zero-gradient elements).
         assert d.max() <= 4.2 * lr, (k, d.max())
-        assert (d > tol_lr * lr + 1e-7).mean() <= 2e-3, (k, (d > tol_lr * lr).mean(), d.max())
+        assert (d > tol_lr * lr + 1e-7).mean() <= 2e-3 * n_steps, (k, (d > tol_lr * lr).mean(), d.max())
 
 
 def _run(kind, B, critic_loss, double_dqn, per, clip, steps=3, lr=1e-3, soft_update_interval=2, tau=0.5):
@@ -86,8 +88,8 @@ def _run(kind, B, critic_loss, double_dqn, per, clip, steps=3, lr=1e-3, soft_upd
         assert abs(rec["loss"] - loss_o) <= LOSS_RTOL * abs(loss_o) + 1e-7, (step, rec["loss"], loss_o)
         assert abs(rec["pred_mean"] - float(oracle.last["pred"].mean())) < 1e-4
         assert abs(rec["tgt_mean"] - float(oracle.last["tgt"].mean())) < 1e-4
-        _check_params(agent, oracle, lr)
-        _check_params(agent, oracle, lr, "qnet_tgt", oracle.qnet_tgt)
+        _check_params(agent, oracle, lr, n_steps=step + 1)
+        _check_params(agent, oracle, lr, "qnet_tgt", oracle.qnet_tgt, n_steps=step + 1)
         if per:  # priorities inherit the network tolerance (SURVEY hard parts): compare loosely
             t_dev = dev.dump_sum_tree()[0]
             t_orc = orc.sum_tree()[0]
