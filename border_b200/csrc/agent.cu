@@ -5,6 +5,7 @@
 #include <fstream>
 #include <mutex>
 #include <sstream>
+#include <stdlib.h>
 #include "agent.cuh"
 
 namespace bb {
@@ -57,8 +58,26 @@ void Agent::init_base(int dev) {
     ctx.ws = dev_alloc_zero<float>(ctx.ws_floats, ctx.stream);  // the tail holds colsum's block counters (must start at 0)
     BB_CUDA(cudaMallocHost(&h_scratch, 4096 * sizeof(float)));
     d_scratch = dev_alloc<float>(1 << 20);
+    BB_CUDA(cudaEventCreateWithFlags(&ctx.ev, cudaEventDisableTiming));
+    static const bool serial = getenv("BB_SERIAL") && atoi(getenv("BB_SERIAL")) != 0;
+    for (int i = 0; i < 2; ++i) {
+        Ctx& s = side_ctx[i];
+        s.device = dev; s.sms = ctx.sms;
+        BB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        s.ws_floats = ctx.ws_floats;
+        s.ws = dev_alloc_zero<float>(s.ws_floats, ctx.stream);
+        BB_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+        if (!serial) ctx.side[i] = &s;
+    }
+    BB_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 Agent::~Agent() {
+    for (int i = 0; i < 2; ++i) {
+        if (side_ctx[i].stream) { cudaStreamSynchronize(side_ctx[i].stream); cudaStreamDestroy(side_ctx[i].stream); }
+        cudaFree(side_ctx[i].ws);
+        if (side_ctx[i].ev) cudaEventDestroy(side_ctx[i].ev);
+    }
+    if (ctx.ev) cudaEventDestroy(ctx.ev);
     cudaFree(ctx.ws);
     cudaFree(d_scratch);
     cudaFree(my_flags);

@@ -71,6 +71,7 @@ struct Model {
 struct Agent {
     int device = 0;
     Ctx ctx;
+    Ctx side_ctx[2];  // side streams + workspaces for the concurrent branches of a step (Ctx::side)
     bool train = false;
     uint64_t n_opts = 0;
     std::vector<Model*> models;  // registered VarStores by name

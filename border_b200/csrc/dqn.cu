@@ -171,18 +171,23 @@ struct Dqn : Agent {
         if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
         ctx.phase = "replay"; ctx.layer = "batch";
         ctx.mark("sample_gather");
-        ctx.phase = "fwd_online";
         const long ld_in = net.in_elems;
+        // the target branch (dqn/base.rs:93-103) is independent of Q(obs): it runs on a side stream
+        const bool conc = ctx.concurrent();
+        const Ctx& tctx = conc ? *ctx.side[0] : ctx;
+        if (conc) ctx.fork_to(tctx);
+        ctx.phase = "fwd_online";
         const float* q = net.forward(ctx, qnet.p, bv.obs, ld_in, B, ws_online);         // :71-74
         const float* q_next = nullptr;
         ctx.phase = "fwd_target";
         if (cfg.double_dqn) {                                                              // :93-99
             // online net on next_obs: borrow the target workspace first, keep its Q in d_scratch
-            const float* qn = net.forward(ctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt);
-            BB_CUDA(cudaMemcpyAsync(d_scratch, qn, (size_t)B * net.out_dim * 4, cudaMemcpyDeviceToDevice, ctx.stream));
+            const float* qn = net.forward(tctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt);
+            BB_CUDA(cudaMemcpyAsync(d_scratch, qn, (size_t)B * net.out_dim * 4, cudaMemcpyDeviceToDevice, tctx.stream));
             q_next = d_scratch;
         }
-        const float* qt = net.forward(ctx, qnet_tgt.p, bv.next_obs, ld_in, B, ws_tgt);   // :100-103
+        const float* qt = net.forward(tctx, qnet_tgt.p, bv.next_obs, ld_in, B, ws_tgt);  // :100-103
+        if (conc) ctx.join_from(tctx);
         DqnLossParams lp;
         lp.q = q; lp.q_tgt = qt; lp.q_next = q_next; lp.act = (const long long*)bv.act;
         lp.act_stride = (int)rb.cfg.act_elems; lp.reward = bv.reward; lp.term = bv.is_terminated;

@@ -20,6 +20,15 @@ void Ctx::mark(const char* kernel) const {
     prof->marks.emplace_back(phase + ":" + layer + ":" + kernel, e);
 }
 
+void Ctx::fork_to(const Ctx& s) const {
+    BB_CUDA(cudaEventRecord(ev, stream));
+    BB_CUDA(cudaStreamWaitEvent(s.stream, ev, 0));
+}
+void Ctx::join_from(const Ctx& s) const {
+    BB_CUDA(cudaEventRecord(s.ev, s.stream));
+    BB_CUDA(cudaStreamWaitEvent(stream, s.ev, 0));
+}
+
 // ------------------------------------------------------------------------------- split-K reduce
 
 // Few splits of a large tile: one thread per output element, coalesced across elements.
@@ -659,6 +668,8 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
         relu_mask_kernel<<<(int)std::min<size_t>((n + 255) / 256, (size_t)c.sms * 8), 256, 0, c.stream>>>(w.dact[L - 1], w.act[L - 1], n);
         BB_LAUNCHED();
     }
+    const bool conc = c.concurrent() && g;
+    int n_side = 0;
     for (int i = L - 1; i >= 0; --i) {
         const Layer& l = layers[i];
         const void* x = i ? (const void*)w.act[i - 1] : input;
@@ -667,24 +678,32 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
         long lddx = i ? (long)layers[i - 1].out_elems_per_sample : ld_din;
         // the mask folds the previous layer's ReLU backward into this layer's data-grad epilogue
         const float* mask = (i && layers[i - 1].relu) ? w.act[i - 1] : nullptr;
+        // weight gradient: off the critical path (it only feeds the optimizer) unless nothing follows it
+        const Ctx* wc = &c;
+        if (conc && dx) {
+            wc = c.side[n_side++ & 1];
+            c.fork_to(*wc);  // dact[i] is complete on c.stream here
+        }
         if (l.type == 1) {
             ConvGeom cg = l.geom;
             cg.B = B; cg.rowbase = w.rowbase[i];
             if (g) {
                 c.layer = layer_name(i) + ".wgrad";
-                conv_bwd_weight(c, cg, w.dact[i], x, g + l.w_off, g + l.b_off);
+                conv_bwd_weight(*wc, cg, w.dact[i], x, g + l.w_off, g + l.b_off);
             }
             c.layer = layer_name(i) + ".dgrad";
             if (dx) conv_bwd_data(c, cg, w.dact[i], p + l.w_off, w.col, dx, mask);
         } else {
             if (g) {
                 c.layer = layer_name(i) + ".wgrad";
-                linear_bwd_weight(c, w.dact[i], (const float*)x, ldx, g + l.w_off, g + l.b_off, B, l.out_dim, l.in_dim);
+                linear_bwd_weight(*wc, w.dact[i], (const float*)x, ldx, g + l.w_off, g + l.b_off, B, l.out_dim, l.in_dim);
             }
             c.layer = layer_name(i) + ".dgrad";
             if (dx) linear_bwd_data(c, w.dact[i], p + l.w_off, dx, lddx, B, l.out_dim, l.in_dim, mask);
         }
     }
+    if (n_side > 0) c.join_from(*c.side[0]);
+    if (n_side > 1) c.join_from(*c.side[1]);
 }
 
 // ------------------------------------------------------------------------------- layout conversion

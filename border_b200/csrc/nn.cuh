@@ -33,6 +33,13 @@ struct Ctx {
     Profiler* prof = nullptr;
     mutable std::string phase, layer;
     void mark(const char* kernel) const;  // no-op unless prof is set
+    // Independent branches of the step (target forward, weight gradients) run on side contexts:
+    // own stream + own split-K workspace, ordered against this stream with events.  Null = serial.
+    const Ctx* side[2] = {nullptr, nullptr};
+    cudaEvent_t ev = nullptr;          // scratch event of this context
+    bool concurrent() const { return side[0] && !prof; }
+    void fork_to(const Ctx& s) const;   // s waits for everything enqueued on this stream so far
+    void join_from(const Ctx& s) const; // this stream waits for everything enqueued on s so far
 };
 
 // ---- GEMM dispatch ---------------------------------------------------------------------------
@@ -139,6 +146,8 @@ class Net {
     // backward from d(output) in w.dact.back(); accumulates nothing: grads are overwritten.
     // g == nullptr skips the weight gradients (data gradient only).
     // d_input (may be null) receives the gradient wrt a float input [B][in].
+    // With c.concurrent() the weight gradients of all layers but the first run on the side contexts
+    // while the data-gradient chain continues on c.stream; everything is joined before returning.
     void backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
                   float* d_input, long ld_din) const;
     void free_tables();

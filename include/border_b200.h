@@ -66,6 +66,9 @@ int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, in
 int32_t bb_bench_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, int32_t N, int32_t K,
                       int32_t iters, float* ms_out);
 
+/* Debug hook: clock64 stamps [2 roles][64 k-slices][4 points] of the last traced tcgen05 launch. */
+int32_t bb_debug_tc_trace(int64_t* out);
+
 /* ------------------------------------------------------------------------------------------
  * Replay buffer: SimpleReplayBuffer<O, A> (border-core/src/generic_replay_buffer/base.rs:86-426)
  * with TensorBatch storage (border-tch-agent/src/tensor_batch.rs:44-120), as a ring of SoA
