@@ -278,6 +278,7 @@ void linear_bwd_weight(const Ctx& c, const float* dY, const float* X, long ldx, 
 // ------------------------------------------------------------------------------- conv
 
 void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu) {
+    if (g.u8_chw && env_int("BB_TC", 1) && conv1_fwd_tc(c, g, X, W, b, Y, relu)) return;
     GemmArgs a = zero_args();
     a.A = X; a.a_rowbase = g.rowbase; a.a_koff = g.koff; a.B = W; a.ldb = g.K(); a.C = Y; a.ldc = g.OC;
     a.M = g.M(); a.N = g.OC; a.K = g.K(); a.bias = b; a.relu = relu;

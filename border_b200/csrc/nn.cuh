@@ -70,6 +70,8 @@ struct ConvGeom {
     int M() const { return B * OH * OW; }
     int K() const { return C * KH * KW; }
 };
+// conv1_tc.cu: dedicated tcgen05 kernel for the AtariCnn first layer; false => geometry not handled
+bool conv1_fwd_tc(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu);
 void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu);
 void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW, float* db);
 // dX[B][H][W][C] = col2im(dY W) * (mask > 0); `col` is [M][K] scratch

@@ -25,7 +25,7 @@
 
 namespace bb {
 
-__device__ int g_tc_error = 0;
+static __device__ int g_tc_error = 0;  // per translation unit (tc_gemm.cu reads its own copy)
 
 namespace tc {
 

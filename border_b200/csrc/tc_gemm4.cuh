@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_async_kernel(GemmA
     const int nks = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
     const uint32_t tiles = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
     const uint32_t raw = tiles + STAGES * STAGE_BYTES;
+    const bool trace0 = (g.fence_mode & 256) && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    if (trace0) g_tc_trace[1][56][0] = clock64();
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_async_kernel(GemmA
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    if (trace0) g_tc_trace[1][57][0] = clock64();
 
     if (warp < 8) {
         // ================================================================ producers
@@ -344,8 +347,10 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_async_kernel(GemmA
         }
 
         // ================================================================ epilogue
+        if (trace0) g_tc_trace[1][58][0] = clock64();
         if (nks > 0 && alive) alive = mbar_wait(smem_u32(&accum_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (trace0) g_tc_trace[1][59][0] = clock64();
         const bool direct = g.split_k <= 1;
         float* out = direct ? g.C : g.workspace + (size_t)blockIdx.z * g.M * g.N;
         const int ldo = direct ? g.ldc : (g.trans_out ? g.M : g.N);
@@ -434,11 +439,13 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_async_kernel(GemmA
         if (nks > 0) mma_commit(smem_u32(&accum_bar));
     }
 
+    if (trace0) g_tc_trace[1][60][0] = clock64();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+    if (trace0) g_tc_trace[1][61][0] = clock64();
 }
 
 }  // namespace bb

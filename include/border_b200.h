@@ -66,6 +66,10 @@ int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, in
 int32_t bb_bench_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, int32_t N, int32_t K,
                       int32_t iters, float* ms_out);
 
+/* Timing hook: mean milliseconds of `iters` back-to-back launches of the AtariCnn first-layer forward
+ * (cnn/base.rs:26-28) on a synthetic u8 batch [B][C][84][84]. */
+int32_t bb_bench_conv1(int32_t device, int32_t B, int32_t C, int32_t iters, float* ms_out);
+
 /* Debug hook: clock64 stamps [2 roles][64 k-slices][4 points] of the last traced tcgen05 launch. */
 int32_t bb_debug_tc_trace(int64_t* out);
 
