@@ -235,6 +235,242 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv1_fwd_kernel(Args g) {
 }
 }  // namespace c1
 
+
+// ---------------------------------------------------------------------------------------------
+// Weight gradient of the same layer:  dW[oc][k] = (1/255) sum_m dY[m][oc] x[m][k],  m = (b, oh, ow),
+// k = (c, kh, kw).  Computed transposed, D[k][oc] = sum_m A(k, m) B(m, oc), so that the 64C patch
+// positions fill the 128 MMA rows (two M-tiles for C = 4) and the contraction runs over pixels:
+//
+//   * A(k, m) is the u8 pixel X[b][c][4 oh + kh][4 ow + kw]: exact in TF32, no lo part.  Thread =
+//     patch position k = TMEM lane; one stage = two output rows (oh, oh + 1) of one sample = 40
+//     pixels = 5 MMA k-steps.  The thread reads its two input rows (20 words each, the 8 kw lanes
+//     of a row share addresses), picks byte kw of every word (PRMT + FADD) and stores 40 columns
+//     to tensor memory.
+//   * B(m, oc) = dY rows, split hi / lo by warps 8-11 into K-major SWIZZLE_128B tiles (transposing
+//     stores, conflict-free with lanes along m).  D += A B_hi + A B_lo: two passes.
+//   * CTAs are persistent: each takes a contiguous range of stages (split-K over the batch),
+//     accumulates in TMEM for its whole lifetime and writes one partial dW^T; a deterministic
+//     reduce (nn.cu splitk_reduce8_kernel) adds the partials.
+//
+//   warps 0-3 / 4-7  A producers of M-tile 0 / 1 (lane quarter w % 4), epilogue at the end
+//   warps 8-11       B producers
+//   warp 12          TMEM owner + MMA issuer
+// TMEM: [0,32) [32,64) accumulators of the two M-tiles, then S stages x 96 columns (40 + pad per tile).
+namespace c1w {
+using namespace tc;
+constexpr int NTHREADS = 13 * 32, S = 4, OC = 32, TMEM_COLS = 512, A_COL0 = 64, A_STAGE = 96, A_TILE1 = 48;
+constexpr uint32_t B_STAGE = 2 * 2 * 4096;   // hi (2 slices) + lo (2 slices)
+
+struct Args {
+    const uint8_t* X;   // [B][C][H][W] u8
+    const float* dY;    // [B*OH*OW][32]
+    float* part;        // [ctas][32][K] partial dW (already scaled by 1/255)
+    int n_stages;       // B * OH / 2
+    int C, HW, W, OHW /* OH*OW */, OW, OH2 /* OH/2 */;
+    int dbg;
+};
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3])
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv1_wgrad_kernel(Args g) {
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ uint64_t full_bar[S], empty_bar[S], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tiles = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const int n_mt = g.C / 2;                      // M-tiles of 128 patch positions
+    // this CTA's stage range
+    const int s_begin = (int)((long)g.n_stages * blockIdx.x / gridDim.x);
+    const int s_end = (int)((long)g.n_stages * (blockIdx.x + 1) / gridDim.x);
+    const int ns = s_end - s_begin;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&full_bar[s]), (uint32_t)(4 * n_mt + 4)); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        mbar_init(smem_u32(&done_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 8) {
+        // ================================================================ A producers (+ epilogue)
+        const int mt = warp >> 2, q = warp & 3;
+        const int r = warp * 32 + lane;            // patch position k = (c, kh, kw)
+        const bool active = mt < n_mt;
+        const int c = r >> 6, kh = (r >> 3) & 7, kw = r & 7;
+        const uint32_t sel = 0x7540u | (uint32_t)(kw & 3);
+        const size_t plane = (size_t)c * g.HW + (size_t)kh * g.W + (size_t)(kw >> 2) * 4;
+        bool alive = true;
+        auto load = [&](int st, uint32_t* w) {
+            const int b = st / g.OH2, oh0 = (st % g.OH2) * 2;
+            const uint8_t* p0 = g.X + (size_t)b * g.C * g.HW + plane + (size_t)(oh0 * 4) * g.W;
+            const uint32_t* r0 = reinterpret_cast<const uint32_t*>(p0);
+            const uint32_t* r1 = reinterpret_cast<const uint32_t*>(p0 + 4 * g.W);
+#pragma unroll
+            for (int j = 0; j < 20; ++j) { w[j] = __ldg(r0 + j); w[20 + j] = __ldg(r1 + j); }
+        };
+        if (active) {
+            uint32_t w[40], wn[40];
+            if (ns > 0 && !(g.dbg & 2)) load(s_begin, w);
+            for (int i = 0; i < ns; ++i) {
+                if (i + 1 < ns && !(g.dbg & 2)) load(s_begin + i + 1, wn);
+                const uint32_t s = (uint32_t)i % S, ph = ((uint32_t)i / S) & 1u;
+                if (alive && !c1::wait_bar(smem_u32(&empty_bar[s]), ph ^ 1u)) alive = false;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * A_STAGE + (uint32_t)mt * A_TILE1;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t f[20];
+#pragma unroll
+                    for (int j = 0; j < 20; ++j) {
+                        uint32_t v = __byte_perm(w[h * 20 + j], 0x4B000000u, sel);
+                        f[j] = __float_as_uint(__uint_as_float(v) - 8388608.0f);
+                    }
+                    if (!(g.dbg & 4)) {
+                        tc3::tmem_st16(ta + h * 20, f);
+                        tmem_st4(ta + h * 20 + 16, f + 16);
+                    }
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+#pragma unroll
+                for (int j = 0; j < 40; ++j) w[j] = wn[j];
+            }
+            // ------------------------------------------------------------ epilogue: D[k][oc] -> part[oc][k] / 255
+            if (ns > 0 && alive) alive = c1::wait_bar(smem_u32(&done_bar), 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t d[32];
+            if (ns > 0 && alive) {
+                c1::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mt * 32u, d);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) d[j] = 0u;
+            }
+            const int K = g.C * 64;
+            float* out = g.part + (size_t)blockIdx.x * OC * K + r;
+            const float sc = 1.0f / 255.0f;
+#pragma unroll
+            for (int oc = 0; oc < OC; ++oc) out[(size_t)oc * K] = __uint_as_float(d[oc]) * sc;
+        }
+    } else if (warp < 12) {
+        // ================================================================ B producers: dY rows -> hi / lo, transposed
+        const int t = tid - 256;
+        bool alive = true;
+        for (int i = 0; i < ns; ++i) {
+            const int st = s_begin + i;
+            const int b = st / g.OH2, oh0 = (st % g.OH2) * 2;
+            const float* src = g.dY + ((size_t)b * g.OHW + (size_t)oh0 * g.OW) * OC;
+            float4 v[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int idx = t + 128 * u;       // mm = idx % 40 (pixel), oc4 = idx / 40
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < 320) v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(idx % 40) * OC + (idx / 40) * 4));
+            }
+            const uint32_t s = (uint32_t)i % S, ph = ((uint32_t)i / S) & 1u;
+            if (alive && !c1::wait_bar(smem_u32(&empty_bar[s]), ph ^ 1u)) alive = false;
+            const uint32_t bhi = tiles + s * B_STAGE, blo = bhi + 2 * 4096;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int idx = t + 128 * u;
+                if (idx < 320) {
+                    const int mm = idx % 40, oc4 = idx / 40;
+                    const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t oc = (uint32_t)(oc4 * 4 + j), kk = (uint32_t)(mm & 31);
+                        const uint32_t off = (uint32_t)(mm >> 5) * 4096u + sw128(oc, kk >> 2) + (kk & 3u) * 4u;
+                        split_store1(bhi + off, blo + off, vv[j]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+        }
+    } else if (lane == 0) {
+        // ================================================================ MMA issuer
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(OC >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        bool alive = true;
+        for (int i = 0; i < ns && alive; ++i) {
+            const uint32_t s = (uint32_t)i % S, ph = ((uint32_t)i / S) & 1u;
+            if (!c1::wait_bar(smem_u32(&full_bar[s]), ph)) { alive = false; break; }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t bhi = tiles + s * B_STAGE, blo = bhi + 2 * 4096;
+            for (int mt = 0; mt < n_mt; ++mt) {
+                const uint32_t d = tmem_base + (uint32_t)mt * 32u;
+                const uint32_t a0 = tmem_base + A_COL0 + s * A_STAGE + (uint32_t)mt * A_TILE1;
+#pragma unroll
+                for (int k8 = 0; k8 < 5; ++k8) {
+                    if (g.dbg & 1) continue;
+                    const uint32_t sl = (uint32_t)(k8 >> 2) * 4096u;
+                    const uint64_t adv = (uint64_t)((k8 & 3) * 2);
+                    tc3::mma_tf32_ts(d, a0 + k8 * 8, make_desc(bhi + sl) + adv, idesc, (i | k8) ? 1u : 0u);
+                    tc3::mma_tf32_ts(d, a0 + k8 * 8, make_desc(blo + sl) + adv, idesc, 1u);
+                }
+            }
+            mma_commit(smem_u32(&empty_bar[s]));
+        }
+        if (ns > 0 && alive) mma_commit(smem_u32(&done_bar));
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 12) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+}  // namespace c1w
+
+__global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
+                                      int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask);
+
+// dW[32][64C] of the AtariCnn first layer; false => geometry not handled (generic path).
+bool conv1_wgrad_tc(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW) {
+    static const int on = getenv("BB_CONV1_TC") ? atoi(getenv("BB_CONV1_TC")) : 1;
+    if (!on || !g.u8_chw || g.KH != 8 || g.KW != 8 || g.S != 4 || g.OC != 32 || (g.C != 2 && g.C != 4) || (g.W & 3) || (g.OH & 1) ||
+        g.OW != 20 || g.M() < 1024)
+        return false;
+    c1w::Args a;
+    a.X = (const uint8_t*)X; a.dY = dY; a.part = c.ws; a.n_stages = g.B * g.OH / 2; a.C = g.C; a.HW = g.H * g.W; a.W = g.W;
+    a.OHW = g.OH * g.OW; a.OW = g.OW; a.OH2 = g.OH / 2;
+    static const int dbg = getenv("BB_CONV1_DEBUG") ? atoi(getenv("BB_CONV1_DEBUG")) : 0;
+    a.dbg = dbg;
+    const int K = g.K();
+    const int ctas = std::min(a.n_stages, c.sms);
+    if ((size_t)ctas * 32 * K > c.ws_floats - 1024) return false;
+    const size_t smem = (size_t)c1w::S * c1w::B_STAGE + 1024;
+    static bool configured = false;
+    if (!configured) {
+        BB_CUDA(cudaFuncSetAttribute(c1w::conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    c1w::conv1_wgrad_kernel<<<ctas, c1w::NTHREADS, smem, c.stream>>>(a);
+    BB_LAUNCHED();
+    c.mark("tc_conv1_wgrad");
+    const size_t total = (size_t)32 * K;
+    const int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
+    splitk_reduce8_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, dW, 32, K, K, ctas, nullptr, 0, nullptr);
+    BB_LAUNCHED();
+    c.mark("splitk_reduce");
+    return true;
+}
+
 // Returns false when the geometry is not the AtariCnn first layer (the caller falls back to the
 // generic implicit GEMM).
 bool conv1_fwd_tc(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu) {

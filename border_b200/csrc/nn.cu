@@ -287,6 +287,10 @@ void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, co
 
 void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW, float* db) {
     // dW[OC][K] = sum_m dY[m][OC]^T im2col(X)[m][K]
+    if (g.u8_chw && env_int("BB_TC", 1) && conv1_wgrad_tc(c, g, dY, X, dW)) {  // dedicated kernel (conv1_tc.cu)
+        if (db) colsum(c, dY, db, g.M(), g.OC);
+        return;
+    }
     // (float inputs only: for the u8 conv1 frames the transposed 4-byte gathers are slower than the
     // CUDA-core kernel -- 115 us vs 67 us at B=256)
     if (!g.u8_chw && env_int("BB_TC", 1) && env_int("BB_TC_WGRAD_T", 1)) {

@@ -72,6 +72,7 @@ struct ConvGeom {
 };
 // conv1_tc.cu: dedicated tcgen05 kernel for the AtariCnn first layer; false => geometry not handled
 bool conv1_fwd_tc(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu);
+bool conv1_wgrad_tc(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW);
 void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu);
 void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW, float* db);
 // dX[B][H][W][C] = col2im(dY W) * (mask > 0); `col` is [M][K] scratch
