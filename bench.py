@@ -169,7 +169,10 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = local
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default stream: the legacy default stream cannot be captured into a CUDA graph
+    torch_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(torch_stream)
+    stream = torch_stream.cuda_stream
     pk = peaks()
 
     cap = args.capacity
@@ -224,20 +227,38 @@ def run_b200(args):
     launches = int(round(launches_total * args.steps / float(args.steps + args.warmup)))
     value = world * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers: Trainer iteration = push one host
-    # transition (H2D inside) + opt_with_record (loss D2H inside)
+    # ---- end to end through the C ABI with host buffers: the Trainer's inner loop in C++ (libborder_host.so,
+    # the stand-in for the Rust host): push one host transition (H2D inside) + opt with record (loss D2H inside),
+    # synchronous every step exactly like Agent::opt_with_record
+    from border_b200 import host_loops as hl
     rng = np.random.default_rng(rank)
-    h_obs = rng.integers(0, 256, (1,) + OBS_SHAPE, dtype=np.uint8)
-    h_next = rng.integers(0, 256, (1,) + OBS_SHAPE, dtype=np.uint8)
-    tr = GenericTransitionBatch(h_obs, np.zeros((1, 1), np.int64), h_next, np.ones(1, np.float32),
-                                np.zeros(1, np.int8), np.zeros(1, np.int8))
+    n_slots = 16
+    h_obs = rng.integers(0, 256, (n_slots,) + OBS_SHAPE, dtype=np.uint8)
+    h_next = rng.integers(0, 256, (n_slots,) + OBS_SHAPE, dtype=np.uint8)
+    h_act = rng.integers(0, N_ACT, (n_slots, 1)).astype(np.int64)
+    h_rew = np.ones(n_slots, np.float32)
+    h_term = np.zeros(n_slots, np.int8)
+    h_trunc = np.zeros(n_slots, np.int8)
+    tr = GenericTransitionBatch(h_obs[:1], h_act[:1], h_next[:1], h_rew[:1], h_term[:1], h_trunc[:1])
 
-    def e2e_step():
-        rb.push(tr)
-        agent.opt_with_record(rb)
+    def e2e_run(k):
+        return hl.e2e_steps(agent, rb, h_obs, h_act, h_next, h_rew, h_term, h_trunc, k)
 
     e2e_steps = max(10, args.steps // 2)
-    ms_e2e = timed(e2e_step, e2e_steps, max(3, args.warmup // 2))
+    e2e_run(max(3, args.warmup // 2))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t_host0 = time.perf_counter()
+    e2e_run(e2e_steps)
+    t_host1 = time.perf_counter()
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), 1e3 * (t_host1 - t_host0))  # the loop is synchronous: device span == host span
+    if world > 1:
+        t = torch.tensor([ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
     e2e_value = world * e2e_steps / (ms_e2e * 1e-3)
     h2d = 2 * ROW + 8 + 4 + 1 + 1 + 2  # packed staging block of one transition (padded to 16 B)
     h2d = (h2d + 15) // 16 * 16
@@ -245,7 +266,7 @@ def run_b200(args):
     # ---- env-steps/sec: Sampler::sample_and_push with a zero-cost synthetic env
     # (Policy::sample on a host obs + push), the reference's `samples_per_sec`
     def env_step():
-        agent.sample(h_obs)
+        agent.sample(h_obs[:1])
         rb.push(tr)
 
     env_n = max(50, args.steps)
@@ -292,7 +313,8 @@ def run_b200(args):
                           "target fwd, loss, bwd, Adam) per GPU"},
                "clocks": clk,
                "e2e": {"value": e2e_value, "unit": "grad-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
-                       "what": "bb_replay_push(1 host transition) + bb_agent_opt(record): loss read back every step"},
+                       "what": "C++ host loop over the C ABI (bbh_e2e_steps): bb_replay_push(1 host transition) + bb_agent_opt(record), "
+                       "loss read back every step"},
                "gpu_launches": launches,
                "env_steps_per_sec": env_sps,
                "roofline": roof, "roofline_replay": roof_replay,

@@ -8,6 +8,8 @@
 // backward -> fused Adam -> (PER) priority update, all enqueued on one stream with no host
 // round trip; the loss scalar is copied back only for opt_with_record.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include "agent.cuh"
 
 namespace bb {
@@ -115,6 +117,12 @@ struct Dqn : Agent {
     FastRand fr;
     float* d_td = nullptr;
     float* d_out = nullptr;
+    // CUDA graph of one update (sample+gather .. backward): replayed when nothing about the launch changes
+    cudaGraphExec_t gexec = nullptr;
+    const void* g_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t eager_updates = 0;
+    bool graph_broken = false;
+    uint64_t graph_kernels = 0;  // kernels inside the captured update (for bb_kernel_launch_count)
     uint8_t* d_obs_in = nullptr;  // policy input staging
     uint8_t* h_obs_in = nullptr;
     float* h_q = nullptr;
@@ -143,6 +151,7 @@ struct Dqn : Agent {
         ws_online.release(); ws_tgt.release(); ws_act.release();
         qnet.release(); qnet_tgt.release();
         net.free_tables();
+        if (gexec) cudaGraphExecDestroy(gexec);
         cudaFree(d_td); cudaFree(d_out); cudaFree(d_obs_in);
         if (h_obs_in) cudaFreeHost(h_obs_in);
         if (h_q) cudaFreeHost(h_q);
@@ -158,16 +167,12 @@ struct Dqn : Agent {
         ws_batch = B;
     }
 
-    void update_critic(Replay& rb, bb_record* rec) {
-        const int B = (int)cfg.batch_size;
-        BB_CHECK(B >= 1 && B <= 65536, "batch_size out of range");
-        ensure_ws(B);
-        BB_CHECK(rb.obs_row_bytes == (uint32_t)net.in_elems * (net.u8_input ? 1u : 4u),
-                 "replay obs rows do not match the Q network input");
-        BB_CHECK(rb.cfg.act_kind == BB_I64, "DQN needs i64 action rows");
+    // Everything of one update up to (not including) the optimizer: replay sample+gather, the two
+    // forwards, loss / TD kernel, backward.  Every kernel argument here is launch-invariant for a fixed
+    // (replay, batch size, stream), so the sequence can be captured once and replayed as a CUDA graph.
+    void enqueue_update(Replay& rb, int B, bool launch_sample, bb_batch_view& bv) {
         if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
-        bb_batch_view bv;
-        rb.sample(B, &bv);  // buffer.batch(self.batch_size), dqn/base.rs:62
+        rb.sample(B, &bv, launch_sample);  // buffer.batch(self.batch_size), dqn/base.rs:62
         if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
         ctx.phase = "replay"; ctx.layer = "batch";
         ctx.mark("sample_gather");
@@ -203,6 +208,65 @@ struct Dqn : Agent {
         ctx.phase = "backward";
         // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
         net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0);
+    }
+
+    void update_critic(Replay& rb, bb_record* rec) {
+        const int B = (int)cfg.batch_size;
+        BB_CHECK(B >= 1 && B <= 65536, "batch_size out of range");
+        ensure_ws(B);
+        BB_CHECK(rb.obs_row_bytes == (uint32_t)net.in_elems * (net.u8_input ? 1u : 4u),
+                 "replay obs rows do not match the Q network input");
+        BB_CHECK(rb.cfg.act_kind == BB_I64, "DQN needs i64 action rows");
+        bb_batch_view bv;
+        const char* genv = getenv("BB_GRAPH");  // read per call so tests can flip it
+        const bool graphs_on = !(genv && atoi(genv) == 0);
+        // a graph needs a capturable stream shared with the replay, launch-invariant kernels (uniform replay)
+        // and warm kernels/workspaces (the first updates run eagerly)
+        const bool want_graph = graphs_on && !graph_broken && !ctx.prof && !rb.per && ctx.stream != nullptr &&
+                                ctx.stream != cudaStreamLegacy && ctx.stream != cudaStreamPerThread &&
+                                rb.stream == ctx.stream && eager_updates >= 3 && rb.batch_cap >= (size_t)B;
+        bool done = false;
+        if (want_graph) {
+            const void* key[4] = {&rb, (const void*)(uintptr_t)B, (const void*)ctx.stream, (const void*)rb.b_obs};
+            if (gexec && memcmp(key, g_key, sizeof(key)) == 0) {
+                rb.sample(B, &bv, false);
+                BB_CUDA(cudaGraphLaunch(gexec, ctx.stream));
+                g_launch_count.fetch_add(graph_kernels, std::memory_order_relaxed);
+                done = true;
+            } else {
+                if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+                const uint64_t rng0 = rb.rng_pos;
+                const size_t lb0 = rb.last_batch;
+                const uint64_t n0 = g_launch_count.load();
+                cudaGraph_t graph = nullptr;
+                bool ok = cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    try {
+                        enqueue_update(rb, B, true, bv);
+                    } catch (...) {
+                        ok = false;
+                    }
+                    if (cudaStreamEndCapture(ctx.stream, &graph) != cudaSuccess || !graph) ok = false;
+                }
+                if (ok && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) { ok = false; gexec = nullptr; }
+                if (graph) cudaGraphDestroy(graph);
+                if (ok) {
+                    graph_kernels = g_launch_count.load() - n0;
+                    memcpy(g_key, key, sizeof(key));
+                    BB_CUDA(cudaGraphLaunch(gexec, ctx.stream));  // the capture enqueued nothing: run this update now
+                    done = true;
+                } else {
+                    cudaGetLastError();  // clear the sticky capture error, fall back to eager launches for good
+                    graph_broken = true;
+                    rb.rng_pos = rng0; rb.last_batch = lb0;
+                    g_launch_count.store(n0);
+                }
+            }
+        }
+        if (!done) {
+            enqueue_update(rb, B, true, bv);
+            eager_updates += 1;
+        }
         qnet.step += 1;
         ctx.phase = "optimizer";
         grad_sync_begin();

@@ -368,11 +368,45 @@ struct PeerPtrs { const float* p[8]; };
 //   p = p - lr/(1-b1^t) * m/denom.     AdamW: p *= (1 - lr*wd) first; Adam: g += wd*p.
 // With world > 1 the gradient is the mean over the ranks' buffers read through peer pointers
 // (NVLink P2P loads): all-reduce and optimizer step in one kernel, no parameter broadcast needed.
+__device__ __forceinline__ void adam_elem(float& pi, float gi, float& mi, float& vi, float b1, float b2, float one_m_b1,
+                                          float one_m_b2, float eps, float bc2_sqrt, float neg_step, float wd, float decay,
+                                          int adamw) {
+    if (adamw) pi = pi * decay;
+    else if (wd != 0.f) gi = gi + wd * pi;
+    mi = mi * b1 + one_m_b1 * gi;
+    vi = vi * b2 + one_m_b2 * gi * gi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi + neg_step * (mi / denom);
+}
+
+// n4 = n / 4 float4 groups (every tensor of the flat vector is 16 B aligned and padded), tail scalars after.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float b1, float b2, float one_m_b1, float one_m_b2,
                             float eps, float bc2_sqrt, float neg_step, float wd, float decay, int adamw,
                             PeerPtrs peers, int world) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n4 = n >> 2;
+    const float inv_world = 1.0f;
+    (void)inv_world;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 gi;
+        if (world > 1) {
+            gi = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < world; ++r) {
+                float4 t = reinterpret_cast<const float4*>(peers.p[r])[i];
+                gi.x += t.x; gi.y += t.y; gi.z += t.z; gi.w += t.w;
+            }
+            gi.x = gi.x / (float)world; gi.y = gi.y / (float)world; gi.z = gi.z / (float)world; gi.w = gi.w / (float)world;
+        } else {
+            gi = reinterpret_cast<const float4*>(g)[i];
+        }
+        float4 pi = reinterpret_cast<float4*>(p)[i], mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+        adam_elem(pi.x, gi.x, mi.x, vi.x, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
+        adam_elem(pi.y, gi.y, mi.y, vi.y, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
+        adam_elem(pi.z, gi.z, mi.z, vi.z, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
+        adam_elem(pi.w, gi.w, mi.w, vi.w, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
+        reinterpret_cast<float4*>(m)[i] = mi; reinterpret_cast<float4*>(v)[i] = vi; reinterpret_cast<float4*>(p)[i] = pi;
+    }
+    for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float gi;
         if (world > 1) {
             gi = 0.f;
@@ -381,13 +415,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         } else {
             gi = g[i];
         }
-        float pi = p[i];
-        if (adamw) pi = pi * decay;
-        else if (wd != 0.f) gi = gi + wd * pi;
-        float mi = m[i] * b1 + one_m_b1 * gi;
-        float vi = v[i] * b2 + one_m_b2 * gi * gi;
-        float denom = sqrtf(vi) / bc2_sqrt + eps;
-        pi = pi + neg_step * (mi / denom);
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_elem(pi, gi, mi, vi, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
         m[i] = mi; v[i] = vi; p[i] = pi;
     }
 }
@@ -399,7 +428,9 @@ void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_
     double step_size = h.lr / bc1;
     PeerPtrs pp;
     for (int r = 0; r < 8; ++r) pp.p[r] = (peer_grads && r < world) ? peer_grads[r] : nullptr;
-    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)c.sms * 8);
+    BB_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+               reinterpret_cast<uintptr_t>(v)) & 15) == 0, "adam_step: buffers must be 16 B aligned");
+    int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)c.sms * 8);
     adam_kernel<<<blocks, 256, 0, c.stream>>>(p, g, m, v, n, (float)h.beta1, (float)h.beta2, (float)(1.0 - h.beta1),
                                               (float)(1.0 - h.beta2), (float)h.eps, (float)sqrt(bc2),
                                               (float)(-step_size), (float)h.wd, (float)(1.0 - h.lr * h.wd),
@@ -685,16 +716,22 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
         const float* mask = (i && layers[i - 1].relu) ? w.act[i - 1] : nullptr;
         // weight gradient: off the critical path (it only feeds the optimizer) unless nothing follows it
         const Ctx* wc = &c;
+        const Ctx* bc = nullptr;   // where the bias gradient (column sums) runs; null = with the weight gradient
         if (conc && dx) {
             wc = c.side[n_side++ & 1];
             c.fork_to(*wc);  // dact[i] is complete on c.stream here
+        } else if (conc && l.type == 1) {
+            // last layer of the chain: the weight gradient stays on c.stream, its bias gradient goes aside
+            bc = c.side[n_side++ & 1];
+            c.fork_to(*bc);
         }
         if (l.type == 1) {
             ConvGeom cg = l.geom;
             cg.B = B; cg.rowbase = w.rowbase[i];
             if (g) {
                 c.layer = layer_name(i) + ".wgrad";
-                conv_bwd_weight(*wc, cg, w.dact[i], x, g + l.w_off, g + l.b_off);
+                if (bc) colsum(*bc, w.dact[i], g + l.b_off, cg.M(), cg.OC);
+                conv_bwd_weight(*wc, cg, w.dact[i], x, g + l.w_off, bc ? nullptr : g + l.b_off);
             }
             c.layer = layer_name(i) + ".dgrad";
             if (dx) conv_bwd_data(c, cg, w.dact[i], p + l.w_off, w.col, dx, mask);

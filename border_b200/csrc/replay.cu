@@ -683,7 +683,7 @@ void Replay::push(const void* o, const void* a, const void* no, const float* r, 
     if (per) n_samples = std::min<uint64_t>(n_samples + n, cfg.capacity);
 }
 
-void Replay::sample(size_t B, bb_batch_view* out) {
+void Replay::sample(size_t B, bb_batch_view* out, bool launch) {
     DeviceGuard g(device);
     BB_CHECK(B >= 1 && B <= 65535, "batch size out of range");
     BB_CHECK(size > 0, "cannot sample from an empty replay buffer");
@@ -697,8 +697,10 @@ void Replay::sample(size_t B, bb_batch_view* out) {
     sp.per = per; sp.normalize = cfg.normalize; sp.tree = tree; sp.min_tree = min_tree;
     sp.beta_0 = cfg.beta_0; sp.beta_final = cfg.beta_final; sp.n_opts_final = cfg.n_opts_final;
     sp.fr_seed = cfg.fastrand_seed; sp.inject_u = inject_u; sp.powf_fused = powf_fused;
-    replay_sample_gather_kernel<<<dim3(n_chunks, (unsigned)B), 256, 0, stream>>>(sp, (uint32_t)B);
-    BB_LAUNCHED();
+    if (launch) {
+        replay_sample_gather_kernel<<<dim3(n_chunks, (unsigned)B), 256, 0, stream>>>(sp, (uint32_t)B);
+        BB_LAUNCHED();
+    }
     if (!per) rng_pos += B;
     else if (inject_pending >= B) inject_pending = 0;
     else { fr_draws += B; inject_pending = 0; }

@@ -72,7 +72,9 @@ struct Replay {
     void ensure_batch(size_t B);
     void push(const void* o, const void* a, const void* no, const float* r, const int8_t* t, const int8_t* tr,
               size_t n, bool on_device);
-    void sample(size_t B, bb_batch_view* out);
+    // launch = false only advances the host mirror and fills `out` (the launch itself is replayed by a
+    // CUDA graph that captured an identical call: every kernel argument of sample() is launch-invariant)
+    void sample(size_t B, bb_batch_view* out, bool launch = true);
     void update_priority_dev(const unsigned long long* ixs, const float* td, size_t n);
     void update_priority_host(const uint64_t* ixs, const float* td, size_t n);
     void fill_synthetic(uint64_t n_rows, uint32_t n_actions, uint64_t seed);

@@ -137,4 +137,23 @@ int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg
     BBH_END
 }
 
+int32_t bbh_e2e_steps(bb_agent* agent, bb_replay* replay, const void* obs, const void* act, const void* next_obs,
+                      const float* reward, const int8_t* is_terminated, const int8_t* is_truncated,
+                      uint64_t obs_row_bytes, uint64_t act_row_bytes, uint64_t n_slots, uint64_t n_steps,
+                      float* last_loss) {
+    BBH_BEGIN
+    if (!agent || !replay || !obs || !act || !next_obs || !reward || !is_terminated || !is_truncated || !n_slots)
+        throw Error("null argument");
+    bb_record rec;
+    memset(&rec, 0, sizeof(rec));
+    for (uint64_t i = 0; i < n_steps; ++i) {
+        const uint64_t j = i % n_slots;
+        check(bb_replay_push(replay, (const uint8_t*)obs + j * obs_row_bytes, (const uint8_t*)act + j * act_row_bytes,
+                             (const uint8_t*)next_obs + j * obs_row_bytes, reward + j, is_terminated + j, is_truncated + j, 1, 0));
+        check(bb_agent_opt(agent, replay, &rec));
+    }
+    if (last_loss) *last_loss = rec.loss;
+    BBH_END
+}
+
 }  // extern "C"

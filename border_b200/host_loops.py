@@ -46,6 +46,8 @@ def host_lib():
         l.bbh_train_async.restype = C.c_int32
         l.bbh_train_async.argtypes = [C.c_int32, C.c_void_p, C.POINTER(L.bb_replay_cfg), C.POINTER(bbh_env_cfg),
                                       C.POINTER(bbh_trainer_cfg), C.POINTER(bbh_train_stat)]
+        l.bbh_e2e_steps.restype = C.c_int32
+        l.bbh_e2e_steps.argtypes = [C.c_void_p] * 8 + [C.c_uint64] * 4 + [C.POINTER(C.c_float)]
         _hl = l
     return _hl
 
@@ -81,3 +83,16 @@ def train_async(algo, agent_cfg, replay_cfg, env_cfg, tcfg):
     _check(host_lib().bbh_train_async(ALGO[algo], C.cast(C.pointer(agent_cfg), C.c_void_p), C.byref(replay_cfg),
                                       C.byref(env_cfg), C.byref(tcfg), C.byref(st)))
     return _stat(st)
+
+
+def e2e_steps(agent, buffer, obs, act, next_obs, reward, is_terminated, is_truncated, n_steps):
+    """n_steps x [ExperienceBufferBase::push(one host transition); Agent::opt_with_record] over the C ABI, in C++
+    (the Trainer inner loop, border-core/src/trainer.rs:206-228).  Arrays hold n_slots transitions, pushed round-robin."""
+    import numpy as np
+    n = len(reward)
+    arrs = [np.ascontiguousarray(a) for a in (obs, act, next_obs, reward, is_terminated, is_truncated)]
+    assert arrs[3].dtype == np.float32 and arrs[4].dtype == np.int8 and arrs[5].dtype == np.int8
+    loss = C.c_float()
+    _check(host_lib().bbh_e2e_steps(agent.handle, buffer.handle, *[a.ctypes.data for a in arrs],
+                                    arrs[0].nbytes // n, arrs[1].nbytes // n, n, n_steps, C.byref(loss)))
+    return loss.value

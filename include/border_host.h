@@ -50,6 +50,16 @@ int32_t bbh_train(int32_t algo, const void* agent_cfg, const bb_replay_cfg* repl
 int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg,
                         const bbh_env_cfg* env_cfg, const bbh_trainer_cfg* trainer_cfg, bbh_train_stat* out);
 
+/* Measurement aid: `n_steps` iterations of the Trainer's inner loop on EXISTING handles, all through
+ * the C ABI with host buffers: bb_replay_push(one host transition) + bb_agent_opt(record) -- the
+ * loss is read back to the host every step (trainer.rs:206-228 with opt_interval 1).  The n_slots
+ * host transitions (obs/next_obs rows of obs_row_bytes, act rows of act_row_bytes) are pushed
+ * round-robin.  Returns the last loss. */
+int32_t bbh_e2e_steps(bb_agent* agent, bb_replay* replay, const void* obs, const void* act, const void* next_obs,
+                      const float* reward, const int8_t* is_terminated, const int8_t* is_truncated,
+                      uint64_t obs_row_bytes, uint64_t act_row_bytes, uint64_t n_slots, uint64_t n_steps,
+                      float* last_loss);
+
 #ifdef __cplusplus
 }
 #endif

@@ -183,3 +183,26 @@ def test_dqn_policy_sample_and_sync_model(tmp_path):
     agent.eval()
     acts = [int(agent.sample(obs[:1])[0, 0]) for _ in range(50)]
     assert acts.count(int(q[0].argmax())) >= 45
+
+
+def test_graph_replay_of_the_update_is_bit_identical_to_eager_launches(monkeypatch):
+    """After three eager updates Dqn captures sample+gather .. backward into a CUDA graph and replays it; the
+    parameters after 10 updates must equal the eager run bit for bit (same kernels, same order)."""
+    import numpy as np
+    from border_b200 import (AtariCnnConfig, Dqn, DqnConfig, DqnModelConfig, OptimizerConfig, SimpleReplayBuffer,
+                             SimpleReplayBufferConfig)
+    outs = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("BB_GRAPH", graph)
+        rb = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=4096, seed=7))
+        rb.allocate((4, 84, 84), np.uint8, (1,), np.int64)
+        rb.fill_synthetic(4096, 6, 99)
+        agent = Dqn.build(DqnConfig(model_config=DqnModelConfig(q_config=AtariCnnConfig(4, 6), opt_config=OptimizerConfig(lr=1e-4)),
+                                    soft_update_interval=4, tau=1.0, batch_size=64, train=True, device=0, init_seed=3))
+        losses = [agent.opt_with_record(rb)["loss"] for _ in range(10)]
+        outs.append((losses, agent.named_parameters("qnet"), agent.named_parameters("qnet_tgt"), rb.state()))
+    assert outs[0][0] == outs[1][0]
+    for k in outs[0][1]:
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
+        assert np.array_equal(outs[0][2][k], outs[1][2][k]), k
+    assert outs[0][3] == outs[1][3]
