@@ -165,7 +165,10 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (no version banner)
+        # keep stdout to the one JSON line: NCCL prints its version banner (and anything NCCL_DEBUG asks for) there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = local
@@ -284,16 +287,26 @@ def run_b200(args):
         for k, v in run:
             agg[k] = agg.get(k, 0.0) + v / len(prof_runs)
     step_ms_prof = sum(agg.values())
-    top = max(agg.items(), key=lambda kv: kv[1])
+    # dominant kernel = the costliest contraction (at N>1 the profiled Adam also absorbs the ranks' skew in its
+    # peer barrier, which is waiting, not work)
+    gemms = {k: v for k, v in agg.items() if "gemm" in k or ":tc_" in k}
+    top = max((gemms or agg).items(), key=lambda kv: kv[1])
     roof = roofline_for(top[0], top[1], step_ms_prof, pk)
     # the replay kernel on its own, back to back (north-star HBM target)
     ms_g = timed(lambda: rb.batch_device(B), 2000, 20)
     us_gather = 1e3 * ms_g / 2000
     gather_gbs = 2 * GATHER_READ_BYTES / (us_gather * 1e-6) / 1e9
     roof_replay = {"kernel": "replay_sample_gather_kernel", "bound": "hbm", "achieved": gather_gbs, "peak": pk["hbm"],
-                   "unit": "GB/s", "frac": gather_gbs / pk["hbm"], "traffic": None, "us_per_launch": us_gather,
+                   "unit": "GB/s", "frac": gather_gbs / pk["hbm"], "traffic": 14627840 + 256, "us_per_launch": us_gather,
                    "algorithmic_bytes": 2 * GATHER_READ_BYTES, "note": "read + materialised write of one B=256 batch; "
                    "frac of 8 TB/s nominal = %.3f" % (gather_gbs / 8000.0), "peak_source": pk["src"]}
+
+    extra = None
+    if world == 1 and not args.no_extra:
+        try:
+            extra = other_workloads(dev, stream, timed, pk)
+        except Exception as e:  # the headline line must still print
+            extra = {"error": repr(e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -320,11 +333,107 @@ def run_b200(args):
                "roofline": roof, "roofline_replay": roof_replay,
                "step_flop": STEP_FLOP, "step_tflops": STEP_FLOP / (ms / args.steps * 1e-3) / 1e12,
                "kernel_breakdown_ms": {k: round(v, 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:12]}}
+        if extra:
+            out["other_workloads"] = extra
         if cpu:
             out["cpu_baseline"] = cpu
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_workloads(dev, stream, timed, pk):
+    """SURVEY.md 8(d)'s remaining measurement rows, device-resident, N=1 only (reported beside the headline,
+    never as it): the gather in its bandwidth-bound regime (B scaled to 65,535 rows), the prioritized replay
+    calls, the SAC (BASELINE configs[2]) and IQN (configs[3]) update steps."""
+    import ctypes as C
+    import numpy as np
+    from border_b200 import (AtariCnnConfig, EpsilonGreedy, Iqn, IqnConfig, MlpConfig, OptimizerConfig, PerConfig, Sac,
+                             SacConfig, SimpleReplayBuffer, SimpleReplayBufferConfig)
+    from border_b200 import _lib as L
+    lib = L.lib()
+    out = {}
+
+    def launches_of(fn):
+        n = C.c_uint64()
+        lib.bb_kernel_launch_count(None, 1)
+        fn()
+        lib.bb_kernel_launch_count(C.byref(n), 0)
+        return int(n.value)
+
+    # ---- replay sample+gather, bandwidth-bound regime: one launch moves 65,535 rows (3.7 GB read + 3.7 GB written)
+    cap = 1 << 18
+    rb = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=cap, seed=42), device=dev)
+    rb.allocate(OBS_SHAPE, np.uint8, (1,), np.int64)
+    rb.fill_synthetic(cap, N_ACT, 1234)
+    rb.set_stream(stream)
+    big_b = 65535  # the kernel's grid.y limit
+    ms = timed(lambda: rb.batch_device(big_b), 20, 3) / 20
+    nbytes = 2 * big_b * (2 * ROW + 14)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    out["replay_gather_b65535"] = {"kernel": "replay_sample_gather_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
+                                   "unit": "GB/s", "frac": gbs / pk["hbm"], "frac_of_8TBs_nominal": gbs / 8000.0,
+                                   "ms_per_launch": ms, "algorithmic_bytes": nbytes, "rows": big_b,
+                                   "note": "same kernel as the B=256 call, batch scaled so that bandwidth (not launch "
+                                           "latency) bounds it; read + materialised write", "peak_source": pk["src"]}
+    rb.close()
+
+    # ---- prioritized replay (configs[3]): sample (sum-tree descent + IS weights) and update_priority, B=256
+    per = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=cap, seed=42, per_config=PerConfig(
+        alpha=0.6, beta_0=0.4, beta_final=1.0, n_opts_final=500000, normalize="All")), device=dev)
+    per.allocate(OBS_SHAPE, np.uint8, (1,), np.int64)
+    per.fill_synthetic(cap, 4, 4321)
+    per.set_stream(stream)
+    us_s = 1e3 * timed(lambda: per.batch_device(B), 500, 10) / 500
+    ix = np.random.default_rng(0).integers(0, cap, B).astype(np.uint64)
+    td = np.random.default_rng(1).random(B).astype(np.float32)
+    us_u = 1e3 * timed(lambda: per.update_priority(ix, td), 200, 10) / 200
+    out["per_replay_b256"] = {"capacity": cap, "sample_gather_us": us_s, "update_priority_us_incl_h2d": us_u,
+                              "note": "PER alpha 0.6, beta 0.4->1, WeightNormalizer::All; update_priority takes host ixs/td "
+                                      "as the trait does"}
+
+    # ---- IQN Atari (configs[3]): B=256, N=N'=64, AtariCnn.skip_linear features 3136, merge Mlp(3136->512->4)
+    icfg = IqnConfig(f_config=AtariCnnConfig(n_stack=4, out_dim=0, skip_linear=True), m_config=MlpConfig(3136, [512], 4),
+                     opt_config=OptimizerConfig(lr=1e-4), feature_dim=3136, embed_dim=64, soft_update_interval=10000,
+                     batch_size=B, discount_factor=0.99, tau=1.0, train=True, sample_percents_pred="Uniform64",
+                     sample_percents_tgt="Uniform64", explorer=EpsilonGreedy(), device=dev)
+    iqn = Iqn.build(icfg)
+    iqn.set_stream(stream)
+    n_l = launches_of(lambda: iqn.opt(per))
+    ms = timed(lambda: iqn.opt(per), 30, 5) / 30
+    iqn_flop = 2.0 * 4 * 123.5e6 * B  # SURVEY.md 8(d): ~253 GFLOP/step
+    out["iqn_atari_b256_n64"] = {"ms_per_step": ms, "grad_steps_per_sec": 1e3 / ms, "gpu_launches_per_step": n_l,
+                                 "algorithmic_tflops": iqn_flop / (ms * 1e-3) / 1e12, "algorithmic_flop": iqn_flop,
+                                 "frac_of_bf16_peak": iqn_flop / (ms * 1e-3) / 1e12 / pk["tf_sust"],
+                                 "replay": "prioritized (sampling + IS weights; the reference's IQN never updates priorities)"}
+    iqn.close()
+    per.close()
+
+    # ---- SAC Ant-like (configs[2]): obs 17, act 8, MLP[256,256], B=512, n_critics 1 (reference default) and 2
+    scap = 1 << 20
+    srb = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=scap, seed=42), device=dev)
+    srb.allocate((17,), np.float32, (8,), np.float32)
+    srb.fill_synthetic(scap, 0, 99)
+    srb.set_stream(stream)
+    for nc in (1, 2):
+        scfg = SacConfig(pi_config=MlpConfig(17, [256, 256], 8), q_config=MlpConfig(25, [256, 256], 1), batch_size=512,
+                         train=True, n_critics=nc, device=dev)
+        sac = Sac.build(scfg)
+        sac.set_stream(stream)
+        n_l = launches_of(lambda: sac.opt(srb))
+        ms = timed(lambda: sac.opt(srb), 200, 20) / 200
+        out["sac_ant_b512_critics%d" % nc] = {"us_per_step": 1e3 * ms, "grad_steps_per_sec": 1e3 / ms,
+                                               "gpu_launches_per_step": n_l, "bound": "latency (0.75 / 1.19 GFLOP per step)"}
+        sac.close()
+    srb.close()
+    return out
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture of the same
+# step (profiles/r01_tc_gemm_ncu_full.txt, profiles/r01_misc_ncu_full.txt; cold-cache replays)
+NCU_TRAFFIC = {"c2.fwd": 13397760, "c3.fwd": 5583104, "l1.fwd": 9708032, "l1.wgrad": 3817472, "l1.dgrad": 10241792,
+               "c3.wgrad": 8654080, "c3.dgrad": 4136704 + 707840, "c2.wgrad": 18582528, "c2.dgrad": 6237184 + 987648,
+               "c1.wgrad": 20360704, "c1.fwd": 7693056}
 
 
 def roofline_for(label, ms, step_ms, pk):
@@ -337,7 +446,7 @@ def roofline_for(label, ms, step_ms, pk):
         tf = flop / (ms * 1e-3) / 1e12
         on_tc = kernel.startswith("tc_")
         return {"kernel": label, "bound": "tensor", "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": tf / pk["tf_sust"], "traffic": None, "ms_per_launch": ms, "share_of_step": ms / step_ms,
+                "frac": tf / pk["tf_sust"], "traffic": NCU_TRAFFIC.get(layer), "ms_per_launch": ms, "share_of_step": ms / step_ms,
                 "algorithmic_flop": flop, "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside the step)",
                 "note": ("tcgen05 kind::tf32, 3 MMA passes per product (3xTF32 for fp32 parity): algorithmic FLOPs are "
                          "counted once, so the tensor pipe does 3x this; peak is the dense bf16 figure (TF32 peak is half)")
@@ -356,6 +465,7 @@ def main():
     ap.add_argument("--sync", default="allreduce", choices=["allreduce", "replicas"])
     ap.add_argument("--cpu-steps", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the SAC / IQN / PER / large-batch gather side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
