@@ -344,21 +344,39 @@ __global__ void per_push_priority_kernel(PerParams p) {
 
 __device__ __forceinline__ int node_depth(unsigned long long node) { return 63 - __clzll(node + 1); }
 
+constexpr uint32_t kRunStart = 0x8000u, kOrgMask = 0x7fffu;
+
 // SumTree::update for a batch, in batch order (sum_tree.rs:93-107 applied by base.rs:421-423 or
-// by SumTree::add from set_priority).  One CTA; thread u owns update u.
+// by SumTree::add from set_priority).  One CTA; thread u owns update u (n <= 1024).
 //   mode 0: ix = ixs[u], priority = td[u]                        (update_priority)
 //   mode 1: ix = (head + j0 + u) % capacity, priority = push_p   (set_priority; also n_samples++)
-// f32 `tree[parent] += change` is order dependent, so for every heap depth the updates that hit
-// the same node are applied by the first of them, sequentially, in batch order; different nodes
-// (and different depths) are independent and run in parallel.
+// f32 `tree[parent] += change` is order dependent: the value a node ends with is the left fold of
+// the changes of the updates below it, in batch order.  Every update gets the path key
+// (leaf + 1) << (dmax - depth(leaf)); the updates below a node of depth d are those sharing the
+// key's top d+1 bits.  Starting from batch order, one STABLE partition per depth (by the next key
+// bit, inside every run of equal prefix: a block-wide scan) keeps every run in batch order, so
+//   * the final runs are the duplicates of one leaf, in batch order: change = p - previous value;
+//   * at every depth the first element of a run folds its run's changes into tree[node].
+// O(n log cap) work instead of the all-pairs duplicate scans (1.16 ms -> tens of us at n = 256); the
+// folds of different nodes and depths are independent and run in parallel.
 __global__ void __launch_bounds__(1024) per_update_kernel(PerParams p, const unsigned long long* __restrict__ ixs,
                                                           const float* __restrict__ td, uint32_t n, int mode,
                                                           uint32_t j0, int bump_n_opts) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned long long* s_node = reinterpret_cast<unsigned long long*>(smem_raw);  // [n]
-    float* s_p = reinterpret_cast<float*>(s_node + n);                              // [n]
-    float* s_change = s_p + n;                                                      // [n]
-    const uint32_t u = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int dmax = node_depth(2 * p.capacity - 2);
+    unsigned long long* s_key0 = reinterpret_cast<unsigned long long*>(smem_raw);  // [2][n] keys in the current order
+    unsigned long long* s_keyu = s_key0 + 2 * n;                                    // [n] by update
+    float* s_p = reinterpret_cast<float*>(s_keyu + n);                              // [n] by update
+    float* s_change = s_p + n;                                                      // [n] by update
+    uint16_t* s_org0 = reinterpret_cast<uint16_t*>(s_change + n);                   // [2][n] update at a position
+    uint16_t* s_rs0 = s_org0 + 2 * n;                                               // [2][n] run start of a position
+    uint16_t* s_re0 = s_rs0 + 2 * n;                                                // [2][n] run end (exclusive)
+    uint16_t* s_z = s_re0 + 2 * n;                                                  // [n + 1] exclusive scan of the zero bits
+    uint16_t* s_pos = s_z + n + 1;                                                  // [n] final position of an update
+    uint16_t* s_dl = s_pos + n;                                                     // [n] depth of the update's leaf
+    uint16_t* s_perm = s_dl + n;                                                    // [dmax + 1][n] order (+ run-start flag) per depth
+    __shared__ uint32_t s_wsum[32];
+    const uint32_t u = threadIdx.x, lane = u & 31u, warp = u >> 5;
     const bool act = u < n;
     unsigned long long ix = 0, leaf = 0;
     float pv = 0.f;
@@ -367,47 +385,82 @@ __global__ void __launch_bounds__(1024) per_update_kernel(PerParams p, const uns
         else { ix = (p.ctl->head + j0 + u) % p.capacity; pv = p.ctl->push_p; }
         pv = bbpow::powf_glibc(pv + p.eps, p.alpha, p.powf_fused);  // (p + eps).powf(alpha)
         leaf = ix + p.capacity - 1;
-        s_node[u] = leaf;
-        s_p[u] = pv;
+        const int dl = node_depth(leaf);
+        const unsigned long long key = (leaf + 1) << (dmax - dl);
+        s_keyu[u] = key; s_p[u] = pv; s_dl[u] = (uint16_t)dl;
+        s_key0[u] = key; s_org0[u] = (uint16_t)u; s_rs0[u] = 0; s_re0[u] = (uint16_t)n;
+        s_perm[u] = (uint16_t)(u | (u == 0 ? kRunStart : 0u));
+        if (dmax == 0) s_pos[u] = (uint16_t)u;
     }
     __syncthreads();
-    // leaf: change = p - tree[leaf], where tree[leaf] already reflects earlier duplicates
-    bool is_last = true;
+    int cur = 0;
+    for (int d = 1; d <= dmax; ++d) {
+        const int b = dmax - d;
+        unsigned long long k = 0;
+        bool z = false;
+        if (act) { k = s_key0[cur * n + u]; z = ((k >> b) & 1ull) == 0ull; }
+        const unsigned bal = __ballot_sync(0xffffffffu, z);
+        if (lane == 0) s_wsum[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t zex = __popc(bal & ((1u << lane) - 1u));
+        for (uint32_t w = 0; w < warp; ++w) zex += s_wsum[w];
+        if (act) s_z[u] = (uint16_t)zex;
+        if (u == n - 1) s_z[n] = (uint16_t)(zex + (z ? 1u : 0u));
+        __syncthreads();
+        if (act) {
+            const uint32_t s = s_rs0[cur * n + u], t = s_re0[cur * n + u];
+            const uint32_t zs = s_z[s], zb = zex - zs, zr = s_z[t] - zs;
+            uint32_t np, nrs, nre;
+            if (z) { np = s + zb; nrs = s; nre = s + zr; }
+            else { np = s + zr + (u - s - zb); nrs = s + zr; nre = t; }
+            const int nx = cur ^ 1;
+            const uint16_t o = s_org0[cur * n + u];
+            s_key0[nx * n + np] = k; s_org0[nx * n + np] = o;
+            s_rs0[nx * n + np] = (uint16_t)nrs; s_re0[nx * n + np] = (uint16_t)nre;
+            s_perm[(size_t)d * n + np] = (uint16_t)(o | (np == nrs ? kRunStart : 0u));
+            if (d == dmax) s_pos[o] = (uint16_t)np;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    // leaf: change = p - tree[leaf], where tree[leaf] already reflects earlier duplicates (the run's predecessor)
+    bool last_dup = false;
     if (act) {
-        float prev = 0.f;
-        bool found = false;
-        for (int v = (int)u - 1; v >= 0; --v)
-            if (s_node[v] == leaf) { prev = s_p[v]; found = true; break; }
-        if (!found) prev = p.tree[leaf];
+        const uint32_t pos = s_pos[u], s = s_rs0[cur * n + pos], t = s_re0[cur * n + pos];
+        const float prev = pos == s ? p.tree[leaf] : s_p[s_org0[cur * n + pos - 1]];
         s_change[u] = pv - prev;
-        for (uint32_t v = u + 1; v < n; ++v)
-            if (s_node[v] == leaf) { is_last = false; break; }
+        last_dup = pos == t - 1;
     }
-    __syncthreads();
-    if (act && is_last) {
+    __syncthreads();  // the run's first element has read tree[leaf] before its last one overwrites it
+    if (last_dup) {  // the last duplicate's value stays
         p.tree[leaf] = pv;
         p.min_tree[p.capacity + ix] = pv;  // min_tree.modify / max_tree.modify leaves
         p.max_tree[p.capacity + ix] = pv;
     }
-    // propagate: ancestors by heap depth
-    const int my_depth = act ? node_depth(leaf) : 0;
-    int max_depth = node_depth(2 * p.capacity - 2);
-    for (int d = max_depth - 1; d >= 0; --d) {
-        unsigned long long node = ~0ull;
-        if (act && my_depth > d) node = ((leaf + 1) >> (my_depth - d)) - 1;
-        __syncthreads();
-        if (act) s_node[u] = node;
-        __syncthreads();
-        if (node != ~0ull) {
-            bool leader = true;
-            for (uint32_t v = 0; v < u; ++v)
-                if (s_node[v] == node) { leader = false; break; }
-            if (leader) {
-                float acc = p.tree[node];
-                for (uint32_t v = u; v < n; ++v)
-                    if (s_node[v] == node) acc = acc + s_change[v];
-                p.tree[node] = acc;
+    // propagate: the first element of every run of every depth folds the run into its node.  Position 0 starts
+    // a run at every depth, so the (depth, position) pairs are skewed over the threads.
+    if (act) {
+        for (int d = 0; d < dmax; ++d) {
+            const uint32_t i = (u + n - (uint32_t)((d * 37) % (int)n)) % n;
+            const uint16_t* perm = s_perm + (size_t)d * n;
+            const uint32_t e = perm[i];
+            if (!(e & kRunStart)) continue;
+            const uint32_t u0 = e & kOrgMask;
+            if ((int)s_dl[u0] <= d) continue;  // the run IS a leaf of depth d: nothing above the leaf stage
+            const unsigned long long node = (s_keyu[u0] >> (dmax - d)) - 1ull;
+            float acc = p.tree[node];
+            uint32_t j = i;
+            float c = s_change[u0];
+            while (true) {
+                const uint32_t jn = j + 1;
+                const uint32_t en = jn < n ? perm[jn] : kRunStart;
+                const bool more = !(en & kRunStart);
+                const float cn = more ? s_change[en & kOrgMask] : 0.f;
+                acc = acc + c;
+                if (!more) break;
+                c = cn; j = jn;
             }
+            p.tree[node] = acc;
         }
     }
     // min/max trees: recompute the ancestors of every touched leaf by bit-length level (a node of
@@ -601,7 +654,13 @@ void Replay::launch_per_update(const unsigned long long* ixs, const float* td, s
         uint32_t m = (uint32_t)std::min<size_t>(1024, n - j0);
         bool last = j0 + m >= n;
         uint32_t threads = (m + 31) / 32 * 32;
-        size_t smem = (size_t)m * (8 + 4 + 4);
+        const int dmax = 63 - __builtin_clzll(2 * cfg.capacity - 1);  // depth of the last heap node
+        size_t smem = (size_t)m * (8 * 3 + 4 * 2) + 2 * ((size_t)m * (6 + 1 + 1 + 1 + (size_t)dmax + 1) + 1);
+        static bool configured = false;
+        if (!configured) {
+            BB_CUDA(cudaFuncSetAttribute(per_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            configured = true;
+        }
         per_update_kernel<<<1, threads, smem, stream>>>(pp, ixs ? ixs + j0 : nullptr, td ? td + j0 : nullptr, m, mode,
                                                         (uint32_t)j0, bump && last);
         BB_LAUNCHED();
