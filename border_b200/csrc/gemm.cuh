@@ -49,6 +49,12 @@ struct GemmArgs {
     // tcgen05 path only: store C transposed (element (m, n) at C[n*ldc + m]); used by the conv weight
     // gradient, which is computed as dW^T = im2col^T dY so that the long K*K*C axis fills the 128 MMA rows
     int trans_out;
+    // tcgen05 path only, direct (unsplit) stores: separable output map, element (m, n) at
+    // C[c_rowoff[m] + c_coloff[n]] (the mask is read through the same map); null => m*ldc / n.  Groups of
+    // 4 consecutive n (n % 4 == 0) must stay contiguous.  Used by the gather-form conv data gradient,
+    // whose GEMM rows / columns are (image, h/S, w/S) / (h%S, w%S, channel).
+    const int* c_rowoff;
+    const int* c_coloff;
 };
 
 constexpr int kBK = 16;

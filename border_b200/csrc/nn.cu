@@ -346,9 +346,60 @@ __global__ void col2im_nhwc_kernel(const float* __restrict__ col, float* __restr
     }
 }
 
+// Operand preparation of the gather-form data gradient, one launch:
+//   blocks [0, pad_blocks): interior of the zero-padded dY copy, dypad[b][oh + Jh-1][ow + Jw-1][:] = dY[b][oh][ow][:]
+//   the rest:               Wt[n][k] = W[brow[k] + bnoff[n]]  (weights re-laid so that the GEMM's B operand is k-contiguous)
+__global__ void dgrad_prep_kernel(const float4* __restrict__ dY, float4* __restrict__ pad, int B, int OH, int OW, int OC4,
+                                  int OHp, int OWp, int offh, int offw, int pad_blocks, const float* __restrict__ W,
+                                  float* __restrict__ Wt, const int* __restrict__ brow, const int* __restrict__ bnoff,
+                                  int N, int K) {
+    if ((int)blockIdx.x < pad_blocks) {
+        size_t total = (size_t)B * OH * OW * OC4;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)pad_blocks * blockDim.x) {
+            int c = (int)(i % OC4);
+            size_t t = i / OC4;
+            int ow = (int)(t % OW); t /= OW;
+            int oh = (int)(t % OH);
+            size_t b = t / OH;
+            pad[((b * OHp + oh + offh) * OWp + ow + offw) * OC4 + c] = dY[i];
+        }
+    } else {
+        const int wb = gridDim.x - pad_blocks;
+        const int total = N * K;
+        for (int i = (blockIdx.x - pad_blocks) * blockDim.x + threadIdx.x; i < total; i += wb * blockDim.x) {
+            int k = i % K, n = i / K;
+            Wt[i] = W[brow[k] + bnoff[n]];
+        }
+    }
+}
+
 void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float* W, float* col, float* dX,
                    const float* mask) {
     BB_CHECK(!g.u8_chw && g.C % 4 == 0, "conv_bwd_data expects an NHWC float input with C % 4 == 0");
+    // Opt-in (BB_DGRAD_GATHER=1): measured equal to the col2im path at B = 256 (c2 8+68 us vs 54+22 us, c3 8+50 us
+    // vs 36+18 us; the tcgen05 kernel is bound per 128x64x32 tile step, and the padded form runs 23-65 % more of
+    // them), so the proven path stays the default until the GEMM main loop is faster.
+    if (g.dypad && g.dg_rowbase && g.dg_wt && env_int("BB_TC", 1) && env_int("BB_DGRAD_GATHER", 0)) {
+        // dX[b][S hq + ph][S wq + pw][c] = sum_{jh,jw,oc} dYpad[b][hq + Jh-1-jh][wq + Jw-1-jw][oc] W[oc][S jh + ph][S jw + pw][c]:
+        // one tcgen05 GEMM, no [M][K] column buffer and no col2im pass (the buffer was 42 MB for c2 at B = 256)
+        const int Jh = g.KH / g.S, Jw = g.KW / g.S;
+        const int N = g.S * g.S * g.C, K = Jh * Jw * g.OC;
+        size_t total = (size_t)g.B * g.OH * g.OW * (g.OC / 4);
+        int pad_blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 6);
+        int w_blocks = std::min((N * K + 255) / 256, c.sms * 2);
+        dgrad_prep_kernel<<<pad_blocks + w_blocks, 256, 0, c.stream>>>(
+            reinterpret_cast<const float4*>(dY), reinterpret_cast<float4*>(g.dypad), g.B, g.OH, g.OW, g.OC / 4, g.dg_hp(),
+            g.dg_wp(), Jh - 1, Jw - 1, pad_blocks, W, g.dg_wt, g.dg_brow, g.dg_bnoff, N, K);
+        BB_LAUNCHED();
+        c.mark("dgrad_prep");
+        GemmArgs a = zero_args();
+        a.A = g.dypad; a.a_rowbase = g.dg_rowbase; a.a_koff = g.dg_koff;
+        a.B = g.dg_wt; a.ldb = K;
+        a.C = dX; a.ldc = N; a.c_rowoff = g.dg_crow; a.c_coloff = g.dg_ccol; a.mask = mask;
+        a.M = g.B * (g.H / g.S) * (g.W / g.S); a.N = N; a.K = K;
+        if (tc_gemm(c, G_FWD, a)) return;
+    }
+    BB_CHECK(col != nullptr, "conv_bwd_data: no column buffer for the col2im path");
     GemmArgs a = zero_args();
     a.A = dY; a.lda = g.OC; a.B = W; a.ldb = g.K(); a.C = col; a.ldc = g.K(); a.M = g.M(); a.N = g.K(); a.K = g.OC;
     gemm(c, G_NN, a);
@@ -485,8 +536,12 @@ void NetWorkspace::release() {
     for (auto p : act) cudaFree(p);
     for (auto p : dact) cudaFree(p);
     for (auto p : rowbase) cudaFree(p);
+    for (auto p : dg_rowbase) cudaFree(p);
+    for (auto p : dg_crow) cudaFree(p);
+    for (auto p : dypad) cudaFree(p);
+    for (auto p : dg_wt) cudaFree(p);
     cudaFree(col);
-    act.clear(); dact.clear(); rowbase.clear(); col = nullptr;
+    act.clear(); dact.clear(); rowbase.clear(); dg_rowbase.clear(); dg_crow.clear(); dypad.clear(); dg_wt.clear(); col = nullptr;
 }
 
 static void add_param(Net& n, const std::string& name, std::vector<int64_t> shape, int perm, int pc, int ph, int pw,
@@ -605,12 +660,40 @@ void Net::init_tables(int device) {
         BB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
         koff.push_back(d);
         g.koff = d;
+        if (&l != &layers[0] && g.dgrad_gather_ok()) {
+            // gather-form data gradient (see ConvGeom): k = (jh, jw, oc), n = (ph, pw, c)
+            const int S = g.S, Jh = g.KH / S, Jw = g.KW / S, OWp = g.dg_wp();
+            std::vector<int> ko((size_t)Jh * Jw * g.OC), br(ko.size()), bn((size_t)S * S * g.C), cc(bn.size());
+            for (int jh = 0; jh < Jh; ++jh)
+                for (int jw = 0; jw < Jw; ++jw)
+                    for (int oc = 0; oc < g.OC; ++oc) {
+                        size_t k = ((size_t)jh * Jw + jw) * g.OC + oc;
+                        ko[k] = ((Jh - 1 - jh) * OWp + (Jw - 1 - jw)) * g.OC + oc;   // oh + Jh-1 = h/S + (Jh-1-jh)
+                        br[k] = ((oc * g.KH + S * jh) * g.KW + S * jw) * g.C;       // W[oc][S jh + ph][S jw + pw][c]
+                    }
+            for (int ph = 0; ph < S; ++ph)
+                for (int pw = 0; pw < S; ++pw)
+                    for (int c = 0; c < g.C; ++c) {
+                        size_t n = ((size_t)ph * S + pw) * g.C + c;
+                        bn[n] = (ph * g.KW + pw) * g.C + c;
+                        cc[n] = (ph * g.W + pw) * g.C + c;
+                    }
+            auto up = [&](const std::vector<int>& v) {
+                int* dp = dev_alloc<int>(v.size());
+                BB_CUDA(cudaMemcpy(dp, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+                dg_tables.push_back(dp);
+                return dp;
+            };
+            g.dg_koff = up(ko); g.dg_brow = up(br); g.dg_bnoff = up(bn); g.dg_ccol = up(cc);
+        }
     }
 }
 
 void Net::free_tables() {
     for (auto p : koff) cudaFree(p);
+    for (auto p : dg_tables) cudaFree(p);
     koff.clear();
+    dg_tables.clear();
 }
 
 void Net::alloc_workspace(NetWorkspace& w, int max_batch, bool with_grad) const {
@@ -638,9 +721,34 @@ void Net::alloc_workspace(NetWorkspace& w, int max_batch, bool with_grad) const 
             int* d = dev_alloc<int>(M);
             BB_CUDA(cudaMemcpy(d, h.data(), M * sizeof(int), cudaMemcpyHostToDevice));
             w.rowbase.push_back(d);
+            int *dgr = nullptr, *dgc = nullptr;
+            float *pad = nullptr, *wt = nullptr;
+            if (with_grad && i > 0 && g.dg_koff) {  // gather-form data gradient: per-batch row tables + padded dY
+                const int Hq = g.H / g.S, Wq = g.W / g.S, OHp = g.dg_hp(), OWp = g.dg_wp();
+                size_t Mq = (size_t)max_batch * Hq * Wq;
+                BB_CHECK((size_t)max_batch * OHp * OWp * g.OC < (1ull << 31), "batch too large for int32 gather tables");
+                std::vector<int> rb(Mq), cr(Mq);
+                for (int b = 0; b < max_batch; ++b)
+                    for (int hq = 0; hq < Hq; ++hq)
+                        for (int wq = 0; wq < Wq; ++wq) {
+                            size_t m = ((size_t)b * Hq + hq) * Wq + wq;
+                            rb[m] = ((b * OHp + hq) * OWp + wq) * g.OC;
+                            cr[m] = ((b * g.H + g.S * hq) * g.W + g.S * wq) * g.C;
+                        }
+                dgr = dev_alloc<int>(Mq); dgc = dev_alloc<int>(Mq);
+                BB_CUDA(cudaMemcpy(dgr, rb.data(), Mq * sizeof(int), cudaMemcpyHostToDevice));
+                BB_CUDA(cudaMemcpy(dgc, cr.data(), Mq * sizeof(int), cudaMemcpyHostToDevice));
+                size_t pn = (size_t)max_batch * OHp * OWp * g.OC;
+                pad = dev_alloc<float>(pn);
+                BB_CUDA(cudaMemset(pad, 0, pn * sizeof(float)));
+                wt = dev_alloc<float>((size_t)g.K() * g.OC);
+            }
+            // the col2im path (CUDA-core fallback, BB_TC=0 / BB_DGRAD_GATHER=0) keeps its column buffer
             if (with_grad && i > 0) col = std::max(col, M * (size_t)g.K());
+            w.dg_rowbase.push_back(dgr); w.dg_crow.push_back(dgc); w.dypad.push_back(pad); w.dg_wt.push_back(wt);
         } else {
             w.rowbase.push_back(nullptr);
+            w.dg_rowbase.push_back(nullptr); w.dg_crow.push_back(nullptr); w.dypad.push_back(nullptr); w.dg_wt.push_back(nullptr);
         }
     }
     w.col_floats = col;
@@ -728,6 +836,7 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
         if (l.type == 1) {
             ConvGeom cg = l.geom;
             cg.B = B; cg.rowbase = w.rowbase[i];
+            cg.dg_rowbase = w.dg_rowbase[i]; cg.dg_crow = w.dg_crow[i]; cg.dypad = w.dypad[i]; cg.dg_wt = w.dg_wt[i];
             if (g) {
                 c.layer = layer_name(i) + ".wgrad";
                 if (bc) colsum(*bc, w.dact[i], g + l.b_off, cg.M(), cg.OC);

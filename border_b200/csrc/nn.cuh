@@ -67,8 +67,24 @@ struct ConvGeom {
     bool u8_chw;         // input is the u8 [B][C][H][W] frame stack (scaled by 1/255 on load)
     const int* rowbase;  // [B*OH*OW] device
     const int* koff;     // [K] device
+    // Gather-form data gradient (conv_bwd_data, tensor-core path): the transposed convolution as ONE GEMM
+    // over a zero-padded copy of dY.  Rows m = (image, h/S, w/S), columns n = (h%S, w%S, c), contraction
+    // k = (kh/S, kw/S, oc); every operand and the output are separable gathers.  Null => col2im path.
+    const int* dg_rowbase = nullptr;  // [B*(H/S)*(W/S)] per workspace: A row offsets into the padded dY
+    const int* dg_crow = nullptr;     // [B*(H/S)*(W/S)] per workspace: output row offsets into dX
+    const int* dg_koff = nullptr;     // [(KH/S)*(KW/S)*OC]
+    const int* dg_brow = nullptr;     // [(KH/S)*(KW/S)*OC] weight rows of the B operand
+    const int* dg_bnoff = nullptr;    // [S*S*C]
+    const int* dg_ccol = nullptr;     // [S*S*C]
+    float* dypad = nullptr;           // [B][H/S + KH/S - 1][W/S + KW/S - 1][OC] per workspace, borders stay zero
+    float* dg_wt = nullptr;           // [S*S*C][(KH/S)*(KW/S)*OC] per workspace: the weights re-laid k-contiguous per step
     int M() const { return B * OH * OW; }
     int K() const { return C * KH * KW; }
+    bool dgrad_gather_ok() const {
+        return !u8_chw && KH % S == 0 && KW % S == 0 && H % S == 0 && W % S == 0 && C % 4 == 0 && OC % 4 == 0;
+    }
+    int dg_hp() const { return H / S + KH / S - 1; }
+    int dg_wp() const { return W / S + KW / S - 1; }
 };
 // conv1_tc.cu: dedicated tcgen05 kernel for the AtariCnn first layer; false => geometry not handled
 bool conv1_fwd_tc(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu);
@@ -119,6 +135,8 @@ struct NetWorkspace {
     std::vector<float*> act;    // output of each layer [B][out]
     std::vector<float*> dact;   // grad wrt output of each layer
     std::vector<int*> rowbase;  // per conv layer
+    std::vector<int*> dg_rowbase, dg_crow;  // per layer (null unless the gather-form data gradient applies)
+    std::vector<float*> dypad, dg_wt;
     float* col = nullptr;
     size_t col_floats = 0;
     void release();
@@ -134,6 +152,7 @@ class Net {
     std::vector<Layer> layers;
     std::vector<ParamInfo> params;
     std::vector<int*> koff;  // per conv layer (device), shared by all workspaces
+    std::vector<int*> dg_tables;  // batch-independent tables of the gather-form data gradient (owned; see ConvGeom)
 
     // Custom stacks (SAC's Mlp2 actor, IQN sub-nets): append one linear layer; or two heads that
     // share an input, stored as ONE [2*out][in] layer whose halves keep their own VarStore names.

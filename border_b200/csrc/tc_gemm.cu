@@ -153,7 +153,8 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     int kt = (a.K + tc::BK - 1) / tc::BK;
     int split = 1;
     long want = (long)c.sms * fill_pct / 100;
-    if (tiles * 2 <= want && kt >= 8) {  // a split costs a reduce launch: only when under half the SMs would work
+    const bool mapped_out = a.c_rowoff != nullptr;  // the output map lives in the direct epilogue only
+    if (tiles * 2 <= want && kt >= 8 && !mapped_out) {  // a split costs a reduce launch: only when under half the SMs would work
         split = (int)std::min<long>((want + tiles - 1) / tiles, kt / 4);
         size_t per = (size_t)a.M * a.N;
         const size_t usable = c.ws_floats - 1024;  // the last 1024 words hold colsum's block counters
@@ -169,15 +170,15 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     static const int debug = getenv("BB_TC_DEBUG") ? atoi(getenv("BB_TC_DEBUG")) : 0;  // 1: no global loads, 2: no MMA
     a.fence_mode = fence_mode | (debug << 4);
     dim3 grid(tn, tm, split);
-    const bool v1_only = a.trans_out || mode == G_WGRAD_AU8;  // transposed store / u8 m-contiguous A live in tc_gemm.cuh
+    const bool v1_only = a.trans_out || mode == G_WGRAD_AU8 || mapped_out;  // transposed store / u8 m-contiguous A live in tc_gemm.cuh
     static const int avar = getenv("BB_TC_ASYNC") ? atoi(getenv("BB_TC_ASYNC")) : 0;
     bool ta_done = false;
-    if (cfg2 == 6) {  // A in tensor memory + cp.async staging (tc_gemm5.cuh)
+    if (cfg2 == 6 && !mapped_out) {  // A in tensor memory + cp.async staging (tc_gemm5.cuh)
         if (avar == 0) ta_done = BN == 32 ? tc_launch_ta<32, 3, 1, 2>(mode, a, grid, c.stream) : tc_launch_ta<64, 3, 1, 2>(mode, a, grid, c.stream);
         else ta_done = BN == 32 ? tc_launch_ta<32, 6, 2, 1>(mode, a, grid, c.stream) : tc_launch_ta<64, 6, 2, 1>(mode, a, grid, c.stream);
     }
     if (ta_done) {
-    } else if (cfg2 == 5) {  // cp.async operand pipeline (tc_gemm4.cuh)
+    } else if (cfg2 == 5 && !mapped_out) {  // cp.async operand pipeline (tc_gemm4.cuh)
         if (avar == 0) {
             if (BN == 32) tc_launch_async<32, 2, 4, 1>(mode, a, grid, c.stream);
             else tc_launch_async<64, 2, 4, 1>(mode, a, grid, c.stream);

@@ -379,6 +379,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
         const int ldo = direct ? g.ldc : (g.trans_out ? g.M : g.N);
         const int q = warp & 3;                     // TMEM lane quarter this warp may read
         const int m = m0 + q * 32 + lane;
+        const bool mapped = direct && g.c_rowoff != nullptr;
+        const size_t rowo = m < g.M ? (mapped ? (size_t)g.c_rowoff[m] : (size_t)m * ldo) : 0;
         constexpr int HALF = BN / 2 < 16 ? 16 : BN / 2;   // columns per warp-pair member
         const int c_begin = (warp >> 2) * HALF;
         if (c_begin < BN) {
@@ -407,13 +409,14 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                         const int n = n0 + col + j4;
                         if (n >= g.N) break;
                         float v[4];
+                        const size_t colo = (mapped && g.c_coloff) ? (size_t)g.c_coloff[n] : (size_t)n;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             v[j] = __uint_as_float(r[j4 + j]);
                             if (direct && n + j < g.N) {
                                 if (g.bias) v[j] += g.bias[n + j];
                                 if (g.relu) v[j] = fmaxf(v[j], 0.f);
-                                if (g.mask) v[j] = g.mask[(size_t)m * g.ldc + n + j] > 0.f ? v[j] : 0.f;
+                                if (g.mask) v[j] = g.mask[rowo + colo + j] > 0.f ? v[j] : 0.f;
                             }
                         }
                         if (g.trans_out) {  // C^T: consecutive lanes (rows m) write consecutive addresses
@@ -421,8 +424,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                                 if (n + j < g.N) out[(size_t)(n + j) * ldo + m] = v[j];
                             continue;
                         }
-                        float* dst = out + (size_t)m * ldo + n;
-                        if (n + 3 < g.N && ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0))
+                        float* dst = out + rowo + colo;
+                        if (n + 3 < g.N && (((rowo + colo) & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0))
                             *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                         else
                             for (int j = 0; j < 4; ++j)
