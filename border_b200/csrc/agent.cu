@@ -127,6 +127,23 @@ void Agent::grad_sync_begin() {
 void Agent::grad_sync_end() {
     if (world > 1) peer_barrier(this);
 }
+void Agent::synced_adam(Model& m) {
+    if (world <= 1) {
+        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1);
+        return;
+    }
+    const char* e = getenv("BB_GRAD_SYNC");
+    const bool sharded = e ? strcmp(e, "sharded") == 0 : world >= 4;
+    peer_barrier(this);  // every rank's gradient is complete
+    if (sharded) {
+        grad_reduce_scatter(ctx, peer_grad, m.n, rank, world);
+        peer_barrier(this);  // every slice of the mean has landed in this rank's buffer (and nobody still reads the old one)
+        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1);
+    } else {
+        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, peer_grad, world);
+        peer_barrier(this);  // everyone done reading before anyone overwrites
+    }
+}
 
 // ------------------------------------------------------------------------------- checkpoints
 

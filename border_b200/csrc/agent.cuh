@@ -88,6 +88,10 @@ struct Agent {
     const float* const* peer_grads() const { return world > 1 ? peer_grad : nullptr; }
     void grad_sync_begin();  // all ranks' gradients complete before anyone reads them
     void grad_sync_end();    // everyone done reading before anyone overwrites
+    // Optimizer step of a data-parallel replica.  world 1: plain Adam.  world 2-3: ONE kernel reads every rank's
+    // gradient and applies Adam (fused all-reduce + optimizer).  world >= 4: sharded mean (reduce-scatter +
+    // broadcast through peer stores) then local Adam.  BB_GRAD_SYNC=fused|sharded overrides the choice.
+    void synced_adam(Model& m);
 
     virtual ~Agent();
     void init_base(int dev);

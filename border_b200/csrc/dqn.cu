@@ -269,9 +269,7 @@ struct Dqn : Agent {
         }
         qnet.step += 1;
         ctx.phase = "optimizer";
-        grad_sync_begin();
-        adam_step(ctx, qnet.p, qnet.g, qnet.m, qnet.v, qnet.n, qnet.hyper, qnet.step, peer_grads(), world);
-        grad_sync_end();
+        synced_adam(qnet);
         if (bv.weight) {  // :142-143
             if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
             rb.update_priority_dev((const unsigned long long*)bv.ix_sample, d_td, B);

@@ -351,9 +351,7 @@ struct Iqn : Agent {
         f_net.backward(ctx, iqn.p + base_f, iqn.g + base_f, bv.obs, f_net.in_elems, B, ws_online.f, nullptr, 0);
         iqn.step += 1;
         ctx.phase = "optimizer";
-        grad_sync_begin();
-        adam_step(ctx, iqn.p, iqn.g, iqn.m, iqn.v, iqn.n, iqn.hyper, iqn.step, peer_grads(), world);
-        grad_sync_end();
+        synced_adam(iqn);
         inject_n[0] = inject_n[1] = 0;
         if (want_loss) {
             BB_CUDA(cudaMemcpyAsync(h_scratch, d_out, 4, cudaMemcpyDeviceToHost, ctx.stream));

@@ -102,6 +102,8 @@ struct AdamHyper {
 };
 void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
                uint64_t step /* 1-based */, const float* const* peer_grads = nullptr, int world = 1);
+// mean of all ranks' gradients, slice-owner computes and stores it into every rank's buffer (peer memory)
+void grad_reduce_scatter(const Ctx& c, const float* const* peer_grads, size_t n, int rank, int world);
 // dest = tau*src + (1-tau)*dest  (util.rs:43)
 void track(const Ctx& c, float* dest, const float* src, size_t n, double tau);
 void fill_uniform(const Ctx& c, float* p, size_t n, float bound, uint64_t seed);

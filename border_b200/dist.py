@@ -36,6 +36,10 @@ def connect_gradient_peers(agent, dist, torch):
     hs = b"".join(b[:HANDLE_BYTES] for b in blobs)
     fs = b"".join(b[HANDLE_BYTES:] for b in blobs)
     L.check(L.lib().bb_agent_ipc_connect(agent.handle, rank, world, hs, fs))
+    import os
+    mode = os.environ.get("BB_GRAD_SYNC") or ("sharded" if world >= 4 else "fused")
+    if mode == "sharded":
+        return "sharded mean over NVLink (each rank reduces 1/%d of the gradient through CUDA-IPC peer loads and stores it to every rank) + local Adam" % world
     return "fused P2P all-reduce + Adam over NVLink (CUDA IPC peer loads)"
 
 
