@@ -430,6 +430,34 @@ __device__ __forceinline__ void adam_elem(float& pi, float gi, float& mi, float&
     pi = pi + neg_step * (mi / denom);
 }
 
+// Mean over ranks as a pairwise tree in rank order, ((g0+g1)+(g2+g3))+..., then / world: the same value on every
+// rank, and for a power-of-two world of IDENTICAL gradients exactly the gradient itself (2g, 4g, 8g and the
+// division are exact), which is what lets tests/mgpu_check.py compare a data-parallel run with one GPU bit for bit.
+__device__ __forceinline__ float4 mean_over_ranks4(const PeerPtrs& peers, size_t i, int world) {
+    float4 t[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        t[r] = r < world ? reinterpret_cast<const float4*>(peers.p[r])[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 1; s < 8; s *= 2)
+#pragma unroll
+        for (int r = 0; r + s < 8; r += 2 * s)
+            if (r + s < world) { t[r].x += t[r + s].x; t[r].y += t[r + s].y; t[r].z += t[r + s].z; t[r].w += t[r + s].w; }
+    const float w = (float)world;
+    return make_float4(t[0].x / w, t[0].y / w, t[0].z / w, t[0].w / w);
+}
+__device__ __forceinline__ float mean_over_ranks1(const PeerPtrs& peers, size_t i, int world) {
+    float t[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t[r] = r < world ? peers.p[r][i] : 0.f;
+#pragma unroll
+    for (int s = 1; s < 8; s *= 2)
+#pragma unroll
+        for (int r = 0; r + s < 8; r += 2 * s)
+            if (r + s < world) t[r] += t[r + s];
+    return t[0] / (float)world;
+}
+
 // n4 = n / 4 float4 groups (every tensor of the flat vector is 16 B aligned and padded), tail scalars after.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float b1, float b2, float one_m_b1, float one_m_b2,
@@ -441,12 +469,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 gi;
         if (world > 1) {
-            gi = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < world; ++r) {
-                float4 t = reinterpret_cast<const float4*>(peers.p[r])[i];
-                gi.x += t.x; gi.y += t.y; gi.z += t.z; gi.w += t.w;
-            }
-            gi.x = gi.x / (float)world; gi.y = gi.y / (float)world; gi.z = gi.z / (float)world; gi.w = gi.w / (float)world;
+            gi = mean_over_ranks4(peers, i, world);
         } else {
             gi = reinterpret_cast<const float4*>(g)[i];
         }
@@ -460,9 +483,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float gi;
         if (world > 1) {
-            gi = 0.f;
-            for (int r = 0; r < world; ++r) gi += peers.p[r][i];
-            gi = gi / (float)world;
+            gi = mean_over_ranks1(peers, i, world);
         } else {
             gi = g[i];
         }
@@ -473,8 +494,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 // Sharded gradient exchange for world >= 4: rank r owns float4 groups [r*per, (r+1)*per).  It reads
-// that slice of EVERY rank's gradient through the peer pointers, forms the mean (sum in rank order from 0.f, then
-// / world -- the same arithmetic as the fused kernel above, so all ranks end bit-identical) and stores it back into
+// that slice of EVERY rank's gradient through the peer pointers, forms the mean (mean_over_ranks4: the same
+// arithmetic as the fused kernel, so all ranks end bit-identical) and stores it back into
 // that slice of every rank's buffer.  Per GPU that is 2*(world-1)/world of the vector over NVLink instead of the
 // (world-1) full vectors the all-read form moves (47 MB -> 11.8 MB at world = 8); a plain local Adam follows.
 __global__ void grad_reduce_scatter_kernel(PeerPtrs peers, size_t n, int rank, int world) {
@@ -482,19 +503,12 @@ __global__ void grad_reduce_scatter_kernel(PeerPtrs peers, size_t n, int rank, i
     const size_t per = (n4 + world - 1) / world;
     const size_t lo = (size_t)rank * per, hi = lo + per < n4 ? lo + per : n4;
     for (size_t i = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
-        float4 gi = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < world; ++r) {
-            float4 t = reinterpret_cast<const float4*>(peers.p[r])[i];
-            gi.x += t.x; gi.y += t.y; gi.z += t.z; gi.w += t.w;
-        }
-        gi.x = gi.x / (float)world; gi.y = gi.y / (float)world; gi.z = gi.z / (float)world; gi.w = gi.w / (float)world;
+        const float4 gi = mean_over_ranks4(peers, i, world);
         for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(const_cast<float*>(peers.p[r]))[i] = gi;
     }
     if (rank == 0)  // tail scalars (the flat vector is padded to float4 per tensor, so normally none)
         for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-            float gi = 0.f;
-            for (int r = 0; r < world; ++r) gi += peers.p[r][i];
-            gi = gi / (float)world;
+            const float gi = mean_over_ranks1(peers, i, world);
             for (int r = 0; r < world; ++r) const_cast<float*>(peers.p[r])[i] = gi;
         }
 }

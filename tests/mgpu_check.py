@@ -2,7 +2,7 @@
 
 Checks (SURVEY.md 8e parity definition; there is no reference twin):
   1. identical data on every rank  -> parameters after 3 steps equal the single-GPU run bit for bit
-     (mean of identical gradients, divided by world, = the gradient) up to fp32 (g+g)/2 == g exactly;
+     (the pairwise-tree mean of identical gradients is the gradient itself, exactly, for a power-of-two world);
   2. different data per rank       -> all ranks hold bit-identical parameters, and the applied
      gradient (first Adam moment / 0.1 after one step) is the mean of the ranks' own gradients.
 """
@@ -46,8 +46,12 @@ def main():
         agent.opt(rb)
         solo.opt(rb1)
     pa, ps = agent.named_parameters("qnet"), solo.named_parameters("qnet")
+    pow2 = world & (world - 1) == 0  # pairwise-tree mean of identical gradients is exact only then
     for k in pa:
-        assert np.array_equal(pa[k], ps[k]), ("identical-data run diverged from single GPU", k)
+        if pow2:
+            assert np.array_equal(pa[k], ps[k]), ("identical-data run diverged from single GPU", k)
+        else:
+            assert np.allclose(pa[k], ps[k], rtol=1e-5, atol=1e-7), ("identical-data run diverged from single GPU", k)
     # 2. different data per rank
     rb, agent = make(local, 1000 + rank, True)
     rb1, solo = make(local, 1000 + rank, False)
