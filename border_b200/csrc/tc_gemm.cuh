@@ -26,6 +26,8 @@
 namespace bb {
 
 static __device__ int g_tc_error = 0;  // per translation unit (tc_gemm.cu reads its own copy)
+// debug trace (BB_TC_DEBUG bit 16): clock64 stamps of CTA (0,0,0)'s producer thread 0 and MMA thread
+__device__ long long g_tc_trace[2][64][8];
 
 namespace tc {
 
@@ -128,6 +130,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
     const int k_end = min(g.K, k_begin + g.k_per_split);
     const int nks = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
     const uint32_t tiles = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
+    const bool trace_cta = (g.fence_mode & 256) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    const bool trace0 = trace_cta && tid == 0;
+    if (trace0) g_tc_trace[1][56][0] = clock64();
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -147,6 +152,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    if (trace0) g_tc_trace[1][57][0] = clock64();
 
     if (warp < 8) {
         // ================================================================ producers
@@ -306,7 +312,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
         auto store = [&](const float4* pa, const float4* pb, int ks) {
             const int s = ks % STAGES;
             const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
+            if (trace0 && ks < 56) g_tc_trace[0][ks][0] = clock64();
             if (alive && !mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u)) alive = false;
+            if (trace0 && ks < 56) g_tc_trace[0][ks][2] = clock64();
             const uint32_t a_hi = tiles + s * STAGE_BYTES, a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
 #pragma unroll
             for (int i = 0; i < A_LD; ++i) {
@@ -349,6 +357,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
             if ((g.fence_mode & 1) == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();  // orders the warp's st.shared before lane 0's release-arrive (256 arrives/stage were costly)
             if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+            if (trace0 && ks < 56) g_tc_trace[0][ks][3] = clock64();
         };
 
         // software pipeline: tables PF stages ahead, data PF-1 stages ahead, stores now
@@ -372,8 +381,10 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
         }
 
         // ================================================================ epilogue
+        if (trace0) g_tc_trace[1][58][0] = clock64();
         if (nks > 0 && alive) alive = mbar_wait(smem_u32(&accum_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (trace0) g_tc_trace[1][59][0] = clock64();
         const bool direct = g.split_k <= 1;
         float* out = direct ? g.C : g.workspace + (size_t)blockIdx.z * g.M * g.N;
         const int ldo = direct ? g.ldc : (g.trans_out ? g.M : g.N);
@@ -434,8 +445,10 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                 }
             }
         }
+        if (trace0) g_tc_trace[1][60][0] = clock64();
     } else if (lane == 0) {
         // ================================================================ MMA issuer (one thread)
+        const bool trace = trace_cta;
         // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), both K-major,
         // N >> 3 at bit 17, M >> 4 at bit 24
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -443,8 +456,10 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
         for (int ks = 0; ks < nks && alive; ++ks) {
             const int s = ks % STAGES;
             const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
+            if (trace && ks < 56) g_tc_trace[1][ks][0] = clock64();
             if (!mbar_wait(smem_u32(&full_bar[s]), ph)) { alive = false; break; }
-            if ((g.fence_mode & 1) == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (trace && ks < 56) g_tc_trace[1][ks][1] = clock64();
+            if ((g.fence_mode & 1) == 1 && !(g.fence_mode & 64)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = tiles + s * STAGE_BYTES, a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
             const uint64_t da_hi = make_desc(a_hi), da_lo = make_desc(a_lo), db_hi = make_desc(b_hi), db_lo = make_desc(b_lo);
@@ -453,10 +468,12 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                 const uint64_t adv = (uint64_t)(k4 * 2);  // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle atom
                 if (g.fence_mode & 32) continue;
                 mma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, (ks | k4) ? 1u : 0u);
+                if (g.fence_mode & 128) continue;  // debug: one pass only (timing floor, wrong numerics)
                 mma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
                 mma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
             }
             mma_commit(smem_u32(&empty_bar[s]));  // frees the stage once the MMAs above have read it
+            if (trace && ks < 56) g_tc_trace[1][ks][3] = clock64();
         }
         if (nks > 0) mma_commit(smem_u32(&accum_bar));
     }
@@ -466,6 +483,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
     if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+    if (trace0) g_tc_trace[1][61][0] = clock64();
 }
 
 }  // namespace bb

@@ -15,8 +15,6 @@
 
 namespace bb {
 
-// debug trace (BB_TC_DEBUG bit 16): clock64 stamps of CTA (0,0,0)'s producer thread 0 and MMA thread
-__device__ long long g_tc_trace[2][64][8];
 
 namespace tc4 {
 
