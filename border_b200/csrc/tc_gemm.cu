@@ -148,6 +148,13 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     // CTAs/SM; 3: persistent flat-pipelined kernel (tc_gemm2.cuh)
     static const int cfg2 = getenv("BB_TC_CFG") ? atoi(getenv("BB_TC_CFG")) : 2;
     int BN = a.N <= 32 ? 32 : ((a.N <= 64 || cfg2 >= 2) ? 64 : 128);
+    // Both operands of an untransposed weight gradient are stored transposed (scalar st.shared): the producer cost per
+    // k-slice is per ROW loaded, so the wider 128x128 tile (3 stages, 1 CTA/SM) wins there -- l1.wgrad 30.8 -> 24.6 us,
+    // 64x512x20736 71 -> 49 us on the box -- while it loses on the forward / dgrad shapes (l1.fwd 24.5 -> 35.9 us).
+    const bool wgrad_mode = mode == G_WGRAD || mode == G_WGRAD_U8 || mode == G_WGRAD_AU8;
+    // Only for long contractions (IQN's 512x3136x16384: 1561 -> 913 us): the 1-CTA/SM, 200 KB tile keeps other streams'
+    // CTAs off its SMs, which cost the DQN step 26 us when its small l1.wgrad (K = 256, side stream) took it.
+    if (cfg2 == 2 && wgrad_mode && !a.trans_out && a.N >= 128 && a.M >= 64 && a.K >= 4096) BN = 128;
     int tm = (a.M + tc::BM - 1) / tc::BM, tn = (a.N + BN - 1) / BN;
     long tiles = (long)tm * tn;
     int kt = (a.K + tc::BK - 1) / tc::BK;
