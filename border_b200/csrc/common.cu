@@ -14,10 +14,12 @@ std::atomic<uint64_t> g_launch_count{0};
 
 // ------------------------------------------------------------------------------- streams
 
+// One non-blocking stream per (host thread, device): handles created on one thread (a learner's agent + replay)
+// share it, which is what lets the update be captured into a CUDA graph; handles created on other threads (the
+// actors of the async trainer build their own agents, actor/base.rs:127-136) get their own, so their calls never
+// land on a stream another thread is capturing.
 cudaStream_t device_stream(int device) {
-    static std::mutex mu;
-    static std::map<int, cudaStream_t> streams;
-    std::lock_guard<std::mutex> lk(mu);
+    static thread_local std::map<int, cudaStream_t> streams;
     auto it = streams.find(device);
     if (it != streams.end()) return it->second;
     DeviceGuard g(device);

@@ -85,7 +85,7 @@ T* dev_alloc_zero(size_t n, cudaStream_t s = 0) {
     return p;
 }
 
-cudaStream_t device_stream(int device);  // one shared non-blocking stream per device
+cudaStream_t device_stream(int device);  // one non-blocking stream per (host thread, device)
 void stream_wait(cudaStream_t waiter, cudaStream_t signaler);
 
 inline int num_sms(int device) {

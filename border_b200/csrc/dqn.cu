@@ -123,6 +123,10 @@ struct Dqn : Agent {
     uint64_t eager_updates = 0;
     bool graph_broken = false;
     uint64_t graph_kernels = 0;  // kernels inside the captured update (for bb_kernel_launch_count)
+    // record path: the loss statistics leave the device right after the loss kernel (side branch of the update) and
+    // opt_with_record waits for THAT event only, so the host enqueues the next step while backward + Adam still run
+    cudaEvent_t ev_rec = nullptr;
+    float* h_rec = nullptr;  // pinned, 8 floats
     uint8_t* d_obs_in = nullptr;  // policy input staging
     uint8_t* h_obs_in = nullptr;
     float* h_q = nullptr;
@@ -143,6 +147,8 @@ struct Dqn : Agent {
         d_td = dev_alloc<float>(65536);
         d_out = dev_alloc_zero<float>(8, ctx.stream);
         net.alloc_workspace(ws_act, 1, false);
+        BB_CUDA(cudaEventCreateWithFlags(&ev_rec, cudaEventDisableTiming));
+        BB_CUDA(cudaMallocHost(&h_rec, 8 * sizeof(float)));
         BB_CUDA(cudaStreamSynchronize(ctx.stream));
     }
     ~Dqn() override {
@@ -152,6 +158,8 @@ struct Dqn : Agent {
         qnet.release(); qnet_tgt.release();
         net.free_tables();
         if (gexec) cudaGraphExecDestroy(gexec);
+        if (ev_rec) cudaEventDestroy(ev_rec);
+        if (h_rec) cudaFreeHost(h_rec);
         cudaFree(d_td); cudaFree(d_out); cudaFree(d_obs_in);
         if (h_obs_in) cudaFreeHost(h_obs_in);
         if (h_q) cudaFreeHost(h_q);
@@ -170,7 +178,7 @@ struct Dqn : Agent {
     // Everything of one update up to (not including) the optimizer: replay sample+gather, the two
     // forwards, loss / TD kernel, backward.  Every kernel argument here is launch-invariant for a fixed
     // (replay, batch size, stream), so the sequence can be captured once and replayed as a CUDA graph.
-    void enqueue_update(Replay& rb, int B, bool launch_sample, bb_batch_view& bv) {
+    void enqueue_update(Replay& rb, int B, bool launch_sample, bb_batch_view& bv, bool capturing) {
         if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
         rb.sample(B, &bv, launch_sample);  // buffer.batch(self.batch_size), dqn/base.rs:62
         if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
@@ -205,9 +213,16 @@ struct Dqn : Agent {
         BB_LAUNCHED();
         ctx.phase = "loss"; ctx.layer = "td";
         ctx.mark("dqn_loss");
+        // loss / means -> pinned host memory, off the critical path; inside a capture the event becomes an
+        // event-record node the host can wait on (cudaEventRecordExternal)
+        const Ctx& rctx = conc ? *ctx.side[1] : ctx;
+        if (conc) ctx.fork_to(rctx);
+        BB_CUDA(cudaMemcpyAsync(h_rec, d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, rctx.stream));
+        BB_CUDA(cudaEventRecordWithFlags(ev_rec, rctx.stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
         ctx.phase = "backward";
         // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
         net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0);
+        if (conc) ctx.join_from(rctx);  // (backward joins the side streams it used; this one may not be among them)
     }
 
     void update_critic(Replay& rb, bb_record* rec) {
@@ -242,7 +257,7 @@ struct Dqn : Agent {
                 bool ok = cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
                 if (ok) {
                     try {
-                        enqueue_update(rb, B, true, bv);
+                        enqueue_update(rb, B, true, bv, true);
                     } catch (...) {
                         ok = false;
                     }
@@ -264,7 +279,7 @@ struct Dqn : Agent {
             }
         }
         if (!done) {
-            enqueue_update(rb, B, true, bv);
+            enqueue_update(rb, B, true, bv, false);
             eager_updates += 1;
         }
         qnet.step += 1;
@@ -278,12 +293,11 @@ struct Dqn : Agent {
             ctx.mark("update_priority");
         }
         if (rec) {
-            BB_CUDA(cudaMemcpyAsync(h_scratch, d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx.stream));
-            BB_CUDA(cudaStreamSynchronize(ctx.stream));
-            rec->loss = h_scratch[0];
+            BB_CUDA(cudaEventSynchronize(ev_rec));  // the loss of THIS update is on the host; backward / Adam may still run
+            rec->loss = h_rec[0];
             if (cfg.record_verbose_level >= 2) {
-                rec->pred_mean = h_scratch[1]; rec->tgt_mean = h_scratch[2]; rec->reward_mean = h_scratch[3];
-                rec->tgt_minus_pred_mean = h_scratch[4];
+                rec->pred_mean = h_rec[1]; rec->tgt_mean = h_rec[2]; rec->reward_mean = h_rec[3];
+                rec->tgt_minus_pred_mean = h_rec[4];
             }
         }
     }

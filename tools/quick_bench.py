@@ -12,7 +12,7 @@ rb.allocate((4, 84, 84), np.uint8, (1,), np.int64)
 t0 = time.time(); rb.fill_synthetic(cap, 6, 1234); torch.cuda.synchronize(); print("fill s", time.time() - t0)
 agent = Dqn.build(DqnConfig(model_config=DqnModelConfig(q_config=AtariCnnConfig(4, 6), opt_config=OptimizerConfig(lr=1e-4)),
                             soft_update_interval=10000, tau=1.0, batch_size=B, train=True, device=0))
-ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
+ts = torch.cuda.Stream(priority=int(os.environ.get("BB_PRIO", "0"))); torch.cuda.set_stream(ts)
 s = ts.cuda_stream
 rb.set_stream(s); agent.set_stream(s)
 def timeit(fn, n, w=5):
