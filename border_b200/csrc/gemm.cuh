@@ -55,6 +55,9 @@ struct GemmArgs {
     // whose GEMM rows / columns are (image, h/S, w/S) / (h%S, w%S, channel).
     const int* c_rowoff;
     const int* c_coloff;
+    // tcgen05 path only: every gather-table entry in use is a multiple of 4 elements (conv tables with C % 4 == 0), so
+    // whole-tile problems may take the branch-free producer loads (tc_gemm_kernel<..., FAST>)
+    int tables_vec4;
 };
 
 constexpr int kBK = 16;

@@ -282,6 +282,7 @@ void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, co
     GemmArgs a = zero_args();
     a.A = X; a.a_rowbase = g.rowbase; a.a_koff = g.koff; a.B = W; a.ldb = g.K(); a.C = Y; a.ldc = g.OC;
     a.M = g.M(); a.N = g.OC; a.K = g.K(); a.bias = b; a.relu = relu;
+    a.tables_vec4 = !g.u8_chw && g.C % 4 == 0;
     gemm(c, g.u8_chw ? G_FWD_U8 : G_FWD, a);
 }
 
@@ -300,6 +301,7 @@ void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const voi
         GemmArgs t = zero_args();
         t.A = X; t.a_rowbase = g.koff; t.a_koff = g.rowbase; t.B = dY; t.ldb = g.OC; t.C = dW; t.ldc = g.K();
         t.M = g.K(); t.N = g.OC; t.K = g.M(); t.trans_out = 1;
+        t.tables_vec4 = g.C % 4 == 0;
         if (tc_gemm(c, g.u8_chw ? G_WGRAD_AU8 : G_WGRAD, t)) {
             if (db) colsum(c, dY, db, g.M(), g.OC);
             return;
@@ -397,6 +399,7 @@ void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float
         a.B = g.dg_wt; a.ldb = K;
         a.C = dX; a.ldc = N; a.c_rowoff = g.dg_crow; a.c_coloff = g.dg_ccol; a.mask = mask;
         a.M = g.B * (g.H / g.S) * (g.W / g.S); a.N = N; a.K = K;
+        a.tables_vec4 = 1;  // OC % 4 == 0 and C % 4 == 0 (dgrad_gather_ok)
         if (tc_gemm(c, G_FWD, a)) return;
     }
     BB_CHECK(col != nullptr, "conv_bwd_data: no column buffer for the col2im path");

@@ -12,11 +12,11 @@
 namespace bb {
 
 template <int BN, int STAGES, int PF, int MINB>
-static void tc_launch(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
+static void tc_launch(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s, bool fast = false) {
     constexpr size_t smem = (size_t)STAGES * (2 * tc::BM * 128 + 2 * BN * 128) + 1024;
-#define BB_TC_LAUNCH(AK, BK_, AU, BU)                                                                           \
+#define BB_TC_LAUNCH(AK, BK_, AU, BU, FAST_)                                                                    \
     do {                                                                                                        \
-        auto kern = tc_gemm_kernel<BN, STAGES, PF, MINB, AK, BK_, AU, BU>;                                      \
+        auto kern = tc_gemm_kernel<BN, STAGES, PF, MINB, AK, BK_, AU, BU, FAST_>;                               \
         static bool configured = false;                                                                         \
         if (!configured) {                                                                                      \
             BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
@@ -25,12 +25,12 @@ static void tc_launch(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t 
         kern<<<grid, tc::NTHREADS, smem, s>>>(a);                                                               \
     } while (0)
     switch (mode) {
-        case G_FWD: BB_TC_LAUNCH(true, true, false, false); break;
-        case G_FWD_U8: BB_TC_LAUNCH(true, true, true, false); break;
-        case G_NN: BB_TC_LAUNCH(true, false, false, false); break;
-        case G_WGRAD: BB_TC_LAUNCH(false, false, false, false); break;
-        case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true); break;
-        case G_WGRAD_AU8: BB_TC_LAUNCH(false, false, true, false); break;
+        case G_FWD: if (fast) BB_TC_LAUNCH(true, true, false, false, true); else BB_TC_LAUNCH(true, true, false, false, false); break;
+        case G_FWD_U8: BB_TC_LAUNCH(true, true, true, false, false); break;
+        case G_NN: if (fast) BB_TC_LAUNCH(true, false, false, false, true); else BB_TC_LAUNCH(true, false, false, false, false); break;
+        case G_WGRAD: if (fast) BB_TC_LAUNCH(false, false, false, false, true); else BB_TC_LAUNCH(false, false, false, false, false); break;
+        case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true, false); break;
+        case G_WGRAD_AU8: BB_TC_LAUNCH(false, false, true, false, false); break;
     }
 #undef BB_TC_LAUNCH
     BB_LAUNCHED();
@@ -205,10 +205,16 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
         if (BN == 32) tc_launch_persist<32, 4, 3>(mode, a, tm, tn, total, ctas, c.stream);
         else tc_launch_persist<64, 4, 3>(mode, a, tm, tn, total, ctas, c.stream);
     } else if (cfg2 >= 1) {
+        // branch-free producer loads when every tile and k-slice is whole and every 4-group is 16-byte aligned
+        static const int fast_env = getenv("BB_TC_FAST") ? atoi(getenv("BB_TC_FAST")) : 1;
+        const bool a_tab = a.a_rowbase || a.a_koff, b_tab = a.b_rowbase || a.b_noff;
+        const bool fast = fast_env && (mode == G_FWD || mode == G_NN || mode == G_WGRAD) && a.M % tc::BM == 0 &&
+                          a.N % BN == 0 && a.K % tc::BK == 0 && ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) == 0 &&
+                          (a_tab ? a.tables_vec4 != 0 : (a.lda & 3) == 0) && (b_tab ? a.tables_vec4 != 0 : (a.ldb & 3) == 0);
         switch (BN) {
-            case 32: tc_launch<32, 2, 2, 2>(mode, a, grid, c.stream); break;
-            case 64: tc_launch<64, 2, 2, 2>(mode, a, grid, c.stream); break;
-            default: tc_launch<128, 3, 3, 1>(mode, a, grid, c.stream); break;
+            case 32: tc_launch<32, 2, 2, 2>(mode, a, grid, c.stream, fast); break;
+            case 64: tc_launch<64, 2, 2, 2>(mode, a, grid, c.stream, fast); break;
+            default: tc_launch<128, 3, 3, 1>(mode, a, grid, c.stream, fast); break;
         }
     } else {
         switch (BN) {

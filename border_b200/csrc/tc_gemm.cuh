@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "gemm.cuh"
 
 namespace bb {
@@ -112,7 +113,10 @@ __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 1
 // STAGES shared-memory stages, PF register sets of prefetched operand data per producer thread,
 // MINB co-resident CTAs per SM (two small CTAs overlap one's prologue/epilogue with the other's
 // main loop).
-template <int BN, int STAGES, int PF, int MINB, bool A_KSRC, bool B_KSRC, bool A_U8, bool B_U8>
+// FAST: the host guarantees whole tiles (M % 128 == 0, N % BN == 0, K % 32 == 0), float operands and 16-byte
+// aligned groups (dense leading dimensions or gather tables that are multiples of 4), so the producers' loads
+// carry no bounds / alignment branches -- the loop is paced by the producer warps' instruction count.
+template <int BN, int STAGES, int PF, int MINB, bool A_KSRC, bool B_KSRC, bool A_U8, bool B_U8, bool FAST = false>
 __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g) {
     using namespace tc;
     constexpr uint32_t A_TILE = BM * 128, B_TILE = BN * 128;       // bytes per hi (or lo) tile
@@ -206,6 +210,12 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
         auto load_tab = [&](long& oa, long& ob, int ks) {
             const int k0 = k_begin + ks * BK;
             oa = 0; ob = 0;
+            if (FAST) {
+                const int ka = k0 + (A_KSRC ? (tid & 7) * 4 : lane);
+                oa = g.a_koff ? (long)__ldg(g.a_koff + ka) : (A_KSRC ? (long)ka : (long)ka * g.lda);
+                if (!B_KSRC) ob = g.b_rowbase ? (long)__ldg(g.b_rowbase + k0 + lane) : (long)(k0 + lane) * g.ldb;
+                return;
+            }
             if (A_KSRC) {
                 int k = k0 + (tid & 7) * 4;
                 if (k < k_end) oa = g.a_koff ? (long)__ldg(g.a_koff + k) : (long)k;
@@ -219,137 +229,166 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
             }
         };
 
-        auto load = [&](float4* pa, float4* pb, int ks, long tabA, long tabB) {
-            if (g.fence_mode & 16) {
-#pragma unroll
-                for (int i = 0; i < A_LD; ++i) pa[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-                for (int i = 0; i < B_LD; ++i) pb[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-                return;
+        // one 16-byte group of the A tile (group i of this thread) of k-slice ks
+        auto load_a = [&](int i, int ks, long tabA) -> float4 {
+            if (!FAST && (g.fence_mode & 16)) return make_float4(1.f, 1.f, 1.f, 1.f);
+            if (FAST && !A_U8) {
+                if (A_KSRC) return __ldg(reinterpret_cast<const float4*>(Af + a_base[i] + tabA));
+                return __ldg(reinterpret_cast<const float4*>(Af + tabA + a_moff[i]));
             }
             const int k0 = k_begin + ks * BK;
-#pragma unroll
-            for (int i = 0; i < A_LD; ++i) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (A_KSRC) {
-                    int k = k0 + (tid & 7) * 4;
-                    if (a_base[i] >= 0 && k < k_end) {
-                        long off = a_base[i] + tabA;
-                        if (A_U8) {
-                            v = u8x4_to_float4(__ldg(reinterpret_cast<const uint32_t*>(Au + off)));
-                            if (k + 1 >= k_end) v.y = 0.f;
-                            if (k + 2 >= k_end) v.z = 0.f;
-                            if (k + 3 >= k_end) v.w = 0.f;
-                        } else if (a_vec && k + 3 < k_end && ((off & 3) == 0)) {
-                            v = __ldg(reinterpret_cast<const float4*>(Af + off));
-                        } else {
-                            v.x = __ldg(Af + off);
-                            if (k + 1 < k_end) v.y = __ldg(Af + off + (g.a_koff ? g.a_koff[k + 1] - g.a_koff[k] : 1));
-                            if (k + 2 < k_end) v.z = __ldg(Af + off + (g.a_koff ? g.a_koff[k + 2] - g.a_koff[k] : 2));
-                            if (k + 3 < k_end) v.w = __ldg(Af + off + (g.a_koff ? g.a_koff[k + 3] - g.a_koff[k] : 3));
-                        }
-                    }
-                } else {  // 4 consecutive m at one k: lanes run along k (conflict-free transposing stores)
-                    int k = k0 + lane;
-                    int m = m0 + (warp + 8 * i) * 4;
-                    if (k < k_end && m < g.M) {
-                        long off = tabA + a_moff[i];
-                        if (A_U8) {
-                            v = u8x4_to_float4(__ldg(reinterpret_cast<const uint32_t*>(Au + off)));
-                            if (m + 1 >= g.M) v.y = 0.f;
-                            if (m + 2 >= g.M) v.z = 0.f;
-                            if (m + 3 >= g.M) v.w = 0.f;
-                        } else if (a_vec && m + 3 < g.M && ((off & 3) == 0)) {
-                            v = __ldg(reinterpret_cast<const float4*>(Af + off));
-                        } else {
-                            v.x = __ldg(Af + off);
-                            if (m + 1 < g.M) v.y = __ldg(Af + off + (g.a_rowbase ? g.a_rowbase[m + 1] - g.a_rowbase[m] : 1));
-                            if (m + 2 < g.M) v.z = __ldg(Af + off + (g.a_rowbase ? g.a_rowbase[m + 2] - g.a_rowbase[m] : 2));
-                            if (m + 3 < g.M) v.w = __ldg(Af + off + (g.a_rowbase ? g.a_rowbase[m + 3] - g.a_rowbase[m] : 3));
-                        }
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (A_KSRC) {
+                int k = k0 + (tid & 7) * 4;
+                if (a_base[i] >= 0 && k < k_end) {
+                    long off = a_base[i] + tabA;
+                    if (A_U8) {
+                        v = u8x4_to_float4(__ldg(reinterpret_cast<const uint32_t*>(Au + off)));
+                        if (k + 1 >= k_end) v.y = 0.f;
+                        if (k + 2 >= k_end) v.z = 0.f;
+                        if (k + 3 >= k_end) v.w = 0.f;
+                    } else if (a_vec && k + 3 < k_end && ((off & 3) == 0)) {
+                        v = __ldg(reinterpret_cast<const float4*>(Af + off));
+                    } else {
+                        v.x = __ldg(Af + off);
+                        if (k + 1 < k_end) v.y = __ldg(Af + off + (g.a_koff ? g.a_koff[k + 1] - g.a_koff[k] : 1));
+                        if (k + 2 < k_end) v.z = __ldg(Af + off + (g.a_koff ? g.a_koff[k + 2] - g.a_koff[k] : 2));
+                        if (k + 3 < k_end) v.w = __ldg(Af + off + (g.a_koff ? g.a_koff[k + 3] - g.a_koff[k] : 3));
                     }
                 }
-                pa[i] = v;
+            } else {  // 4 consecutive m at one k: lanes run along k (conflict-free transposing stores)
+                int k = k0 + lane;
+                int m = m0 + (warp + 8 * i) * 4;
+                if (k < k_end && m < g.M) {
+                    long off = tabA + a_moff[i];
+                    if (A_U8) {
+                        v = u8x4_to_float4(__ldg(reinterpret_cast<const uint32_t*>(Au + off)));
+                        if (m + 1 >= g.M) v.y = 0.f;
+                        if (m + 2 >= g.M) v.z = 0.f;
+                        if (m + 3 >= g.M) v.w = 0.f;
+                    } else if (a_vec && m + 3 < g.M && ((off & 3) == 0)) {
+                        v = __ldg(reinterpret_cast<const float4*>(Af + off));
+                    } else {
+                        v.x = __ldg(Af + off);
+                        if (m + 1 < g.M) v.y = __ldg(Af + off + (g.a_rowbase ? g.a_rowbase[m + 1] - g.a_rowbase[m] : 1));
+                        if (m + 2 < g.M) v.z = __ldg(Af + off + (g.a_rowbase ? g.a_rowbase[m + 2] - g.a_rowbase[m] : 2));
+                        if (m + 3 < g.M) v.w = __ldg(Af + off + (g.a_rowbase ? g.a_rowbase[m + 3] - g.a_rowbase[m] : 3));
+                    }
+                }
             }
-#pragma unroll
-            for (int i = 0; i < B_LD; ++i) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (B_KSRC) {
-                    int k = k0 + (tid & 7) * 4;
-                    if (b_base[i] >= 0 && k < k_end) {
-                        long off = b_base[i] + k;
-                        if (b_vec && k + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(Bf + off));
-                        else {
-                            v.x = __ldg(Bf + off);
-                            if (k + 1 < k_end) v.y = __ldg(Bf + off + 1);
-                            if (k + 2 < k_end) v.z = __ldg(Bf + off + 2);
-                            if (k + 3 < k_end) v.w = __ldg(Bf + off + 3);
-                        }
-                    }
-                } else {
-                    int k = k0 + lane;
-                    int n4 = warp + 8 * i;          // group of 4 consecutive n
-                    int n = n0 + n4 * 4;
-                    if (n4 * 4 < BN && k < k_end && n < g.N) {
-                        long off = tabB + b_noff_r[i];
-                        if (B_U8) {
-                            v = u8x4_to_float4(__ldg(reinterpret_cast<const uint32_t*>(Bu + off)));
-                        } else if (b_vec && n + 3 < g.N && ((off & 3) == 0)) {
-                            v = __ldg(reinterpret_cast<const float4*>(Bf + off));
-                        } else {
-                            v.x = __ldg(Bf + off);
-                            if (n + 1 < g.N) v.y = __ldg(Bf + off + (g.b_noff ? g.b_noff[n + 1] - g.b_noff[n] : 1));
-                            if (n + 2 < g.N) v.z = __ldg(Bf + off + (g.b_noff ? g.b_noff[n + 2] - g.b_noff[n] : 2));
-                            if (n + 3 < g.N) v.w = __ldg(Bf + off + (g.b_noff ? g.b_noff[n + 3] - g.b_noff[n] : 3));
-                        }
+            return v;
+        };
+        auto load_b = [&](int i, int ks, long tabB) -> float4 {
+            if (!FAST && (g.fence_mode & 16)) return make_float4(1.f, 1.f, 1.f, 1.f);
+            if (FAST && !B_U8) {
+                if (B_KSRC) return __ldg(reinterpret_cast<const float4*>(Bf + b_base[i] + (k_begin + ks * BK + (tid & 7) * 4)));
+                return __ldg(reinterpret_cast<const float4*>(Bf + tabB + b_noff_r[i]));
+            }
+            const int k0 = k_begin + ks * BK;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (B_KSRC) {
+                int k = k0 + (tid & 7) * 4;
+                if (b_base[i] >= 0 && k < k_end) {
+                    long off = b_base[i] + k;
+                    if (b_vec && k + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(Bf + off));
+                    else {
+                        v.x = __ldg(Bf + off);
+                        if (k + 1 < k_end) v.y = __ldg(Bf + off + 1);
+                        if (k + 2 < k_end) v.z = __ldg(Bf + off + 2);
+                        if (k + 3 < k_end) v.w = __ldg(Bf + off + 3);
                     }
                 }
-                pb[i] = v;
+            } else {
+                int k = k0 + lane;
+                int n4 = warp + 8 * i;          // group of 4 consecutive n
+                int n = n0 + n4 * 4;
+                if (n4 * 4 < BN && k < k_end && n < g.N) {
+                    long off = tabB + b_noff_r[i];
+                    if (B_U8) {
+                        v = u8x4_to_float4(__ldg(reinterpret_cast<const uint32_t*>(Bu + off)));
+                    } else if (b_vec && n + 3 < g.N && ((off & 3) == 0)) {
+                        v = __ldg(reinterpret_cast<const float4*>(Bf + off));
+                    } else {
+                        v.x = __ldg(Bf + off);
+                        if (n + 1 < g.N) v.y = __ldg(Bf + off + (g.b_noff ? g.b_noff[n + 1] - g.b_noff[n] : 1));
+                        if (n + 2 < g.N) v.z = __ldg(Bf + off + (g.b_noff ? g.b_noff[n + 2] - g.b_noff[n] : 2));
+                        if (n + 3 < g.N) v.w = __ldg(Bf + off + (g.b_noff ? g.b_noff[n + 3] - g.b_noff[n] : 3));
+                    }
+                }
+            }
+            return v;
+        };
+        // the matching split + swizzled stores of one group
+        auto store_a = [&](int i, const float4& v4, uint32_t a_hi, uint32_t a_lo) {
+            if (A_KSRC) {
+                uint32_t off = sw128((uint32_t)(tid >> 3) + 32u * i, (uint32_t)(tid & 7));
+                split_store(a_hi + off, a_lo + off, v4);
+            } else {
+                uint32_t r = (uint32_t)(warp + 8 * i) * 4u;
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t off = sw128(r + j, (uint32_t)lane >> 2) + ((uint32_t)lane & 3u) * 4u;
+                    split_store1(a_hi + off, a_lo + off, v[j]);
+                }
             }
         };
-
-        bool alive = true;
-        auto store = [&](const float4* pa, const float4* pb, int ks) {
-            const int s = ks % STAGES;
-            const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
-            if (trace0 && ks < 56) g_tc_trace[0][ks][0] = clock64();
-            if (alive && !mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u)) alive = false;
-            if (trace0 && ks < 56) g_tc_trace[0][ks][2] = clock64();
-            const uint32_t a_hi = tiles + s * STAGE_BYTES, a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
-#pragma unroll
-            for (int i = 0; i < A_LD; ++i) {
-                if (A_KSRC) {
-                    uint32_t off = sw128((uint32_t)(tid >> 3) + 32u * i, (uint32_t)(tid & 7));
-                    split_store(a_hi + off, a_lo + off, pa[i]);
-                } else {
-                    uint32_t r = (uint32_t)(warp + 8 * i) * 4u;
-                    const float v[4] = {pa[i].x, pa[i].y, pa[i].z, pa[i].w};
+        auto store_b = [&](int i, const float4& v4, uint32_t b_hi, uint32_t b_lo) {
+            if (B_KSRC) {
+                uint32_t r = (uint32_t)(tid >> 3) + 32u * i;
+                if (r < (uint32_t)BN) {
+                    uint32_t off = sw128(r, (uint32_t)(tid & 7));
+                    split_store(b_hi + off, b_lo + off, v4);
+                }
+            } else {
+                uint32_t r = (uint32_t)(warp + 8 * i) * 4u;
+                if (r < (uint32_t)BN) {
+                    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint32_t off = sw128(r + j, (uint32_t)lane >> 2) + ((uint32_t)lane & 3u) * 4u;
-                        split_store1(a_hi + off, a_lo + off, v[j]);
+                        split_store1(b_hi + off, b_lo + off, v[j]);
                     }
                 }
             }
+        };
+
+        // Software pipeline with PF register sets and the loads issued PF k-slices ahead: every 16-byte group of
+        // k-slice k is split + stored and its register is IMMEDIATELY reloaded with the same group of k-slice k+PF
+        // (the trace showed the producers, not the MMAs, pacing the loop: with the reload deferred to the next
+        // iteration only one slice of loads was in flight).  Gather-table entries run one slice further ahead.
+        bool alive = true;
+        long nta = 0, ntb = 0;   // table entries of the next k-slice to be loaded
+#pragma unroll
+        for (int j = 0; j < PF; ++j)
+            if (j < nks) load_tab(ta[j], tb[j], j);
+#pragma unroll
+        for (int j = 0; j < PF; ++j)
+            if (j < nks) {
+#pragma unroll
+                for (int i = 0; i < A_LD; ++i) ra[j][i] = load_a(i, j, ta[j]);
+#pragma unroll
+                for (int i = 0; i < B_LD; ++i) rb[j][i] = load_b(i, j, tb[j]);
+            }
+        if (PF < nks) load_tab(nta, ntb, PF);
+        // one k-slice: wait for the stage, split + store every group, reload it (MORE) with the slice PF ahead
+        auto slice = [&](auto more_tag, float4* pa, float4* pb, int k) {
+            constexpr bool MORE = decltype(more_tag)::value;
+            const int s = k % STAGES;
+            const uint32_t ph = (uint32_t)(k / STAGES) & 1u;
+            if (!FAST && trace0 && k < 56) g_tc_trace[0][k][0] = clock64();
+            if (alive && !mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u)) alive = false;
+            if (!FAST && trace0 && k < 56) g_tc_trace[0][k][2] = clock64();
+            const uint32_t a_hi = tiles + s * STAGE_BYTES, a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+            for (int i = 0; i < A_LD; ++i) {
+                store_a(i, pa[i], a_hi, a_lo);
+                if (MORE) pa[i] = load_a(i, k + PF, nta);
+            }
 #pragma unroll
             for (int i = 0; i < B_LD; ++i) {
-                if (B_KSRC) {
-                    uint32_t r = (uint32_t)(tid >> 3) + 32u * i;
-                    if (r < (uint32_t)BN) {
-                        uint32_t off = sw128(r, (uint32_t)(tid & 7));
-                        split_store(b_hi + off, b_lo + off, pb[i]);
-                    }
-                } else {
-                    uint32_t r = (uint32_t)(warp + 8 * i) * 4u;
-                    if (r < (uint32_t)BN) {
-                        const float v[4] = {pb[i].x, pb[i].y, pb[i].z, pb[i].w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t off = sw128(r + j, (uint32_t)lane >> 2) + ((uint32_t)lane & 3u) * 4u;
-                            split_store1(b_hi + off, b_lo + off, v[j]);
-                        }
-                    }
-                }
+                store_b(i, pb[i], b_hi, b_lo);
+                if (MORE) pb[i] = load_b(i, k + PF, ntb);
             }
             // generic stores -> async proxy (UMMA).  A fence waits for ALL of the thread's outstanding
             // memory operations, including the prefetched global loads, so the writer-side fence
@@ -357,25 +396,16 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
             if ((g.fence_mode & 1) == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();  // orders the warp's st.shared before lane 0's release-arrive (256 arrives/stage were costly)
             if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
-            if (trace0 && ks < 56) g_tc_trace[0][ks][3] = clock64();
+            if (!FAST && trace0 && k < 56) g_tc_trace[0][k][3] = clock64();
+            if (MORE && k + PF + 1 < nks) load_tab(nta, ntb, k + PF + 1);
         };
-
-        // software pipeline: tables PF stages ahead, data PF-1 stages ahead, stores now
-#pragma unroll
-        for (int j = 0; j < PF; ++j)
-            if (j < nks) load_tab(ta[j], tb[j], j);
-#pragma unroll
-        for (int j = 0; j < PF - 1; ++j)
-            if (j < nks) load(ra[j], rb[j], j, ta[j], tb[j]);
         for (int ks = 0; ks < nks; ks += PF) {
 #pragma unroll
             for (int u = 0; u < PF; ++u) {
                 const int k = ks + u;
                 if (k < nks) {
-                    if (k + PF - 1 < nks)
-                        load(ra[(u + PF - 1) % PF], rb[(u + PF - 1) % PF], k + PF - 1, ta[(u + PF - 1) % PF], tb[(u + PF - 1) % PF]);
-                    if (k + PF < nks) load_tab(ta[u], tb[u], k + PF);
-                    store(ra[u], rb[u], k);
+                    if (k + PF < nks) slice(std::true_type{}, ra[u], rb[u], k);
+                    else slice(std::false_type{}, ra[u], rb[u], k);
                 }
             }
         }
