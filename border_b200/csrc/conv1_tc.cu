@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv1_fwd_kernel(Args g) {
     const int K = g.C * 64, nslice = K / 32;
     const uint32_t tiles = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // hi slices, then lo slices (4 KB each)
     const uint32_t lo0 = tiles + (uint32_t)nslice * 4096u;
+    pdl_sync();
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&full_bar[s]), 4); mbar_init(smem_u32(&empty_bar[s]), 1); }
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1_wgrad_kernel(Args g) {
     const int s_begin = (int)((long)g.n_stages * blockIdx.x / gridDim.x);
     const int s_end = (int)((long)g.n_stages * (blockIdx.x + 1) / gridDim.x);
     const int ns = s_end - s_begin;
+    pdl_sync();
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&full_bar[s]), (uint32_t)(4 * n_mt + 4)); mbar_init(smem_u32(&empty_bar[s]), 1); }
@@ -460,12 +462,12 @@ bool conv1_wgrad_tc(const Ctx& c, const ConvGeom& g, const float* dY, const void
         BB_CUDA(cudaFuncSetAttribute(c1w::conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    c1w::conv1_wgrad_kernel<<<ctas, c1w::NTHREADS, smem, c.stream>>>(a);
+    launch_pdl(c1w::conv1_wgrad_kernel, dim3(ctas), dim3(c1w::NTHREADS), smem, c.stream, a);
     BB_LAUNCHED();
     c.mark("tc_conv1_wgrad");
     const size_t total = (size_t)32 * K;
     const int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
-    splitk_reduce8_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, dW, 32, K, K, ctas, nullptr, 0, nullptr);
+    launch_pdl(splitk_reduce8_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, dW, 32, K, K, ctas, nullptr, 0, nullptr);
     BB_LAUNCHED();
     c.mark("splitk_reduce");
     return true;
@@ -489,7 +491,7 @@ bool conv1_fwd_tc(const Ctx& c, const ConvGeom& g, const void* X, const float* W
         configured = true;
     }
     const int ctas = std::min(a.n_tiles, 2 * c.sms);
-    c1::conv1_fwd_kernel<<<ctas, c1::NTHREADS, smem, c.stream>>>(a);
+    launch_pdl(c1::conv1_fwd_kernel, dim3(ctas), dim3(c1::NTHREADS), smem, c.stream, a);
     BB_LAUNCHED();
     c.mark("tc_conv1_fwd");
     return true;

@@ -45,6 +45,7 @@ __device__ __forceinline__ float block_sum(float v, float* s) {
 
 // dqn/base.rs:71-152 after the two forwards: gather, target, loss, and the loss gradient.
 __global__ void __launch_bounds__(1024) dqn_loss_kernel(DqnLossParams p) {
+    pdl_sync();
     __shared__ float s[1024];
     float l_sum = 0.f, pred_sum = 0.f, tgt_sum = 0.f, r_sum = 0.f;
     const float invB = 1.0f / (float)p.B;
@@ -209,7 +210,7 @@ struct Dqn : Agent {
         lp.clip = cfg.clip_td_err_some; lp.clip_min = (float)cfg.clip_td_err_min; lp.clip_max = (float)cfg.clip_td_err_max;
         lp.double_dqn = cfg.double_dqn;
         int threads = std::min(1024, (B + 31) / 32 * 32);
-        dqn_loss_kernel<<<1, threads, 0, ctx.stream>>>(lp);
+        launch_pdl(dqn_loss_kernel, dim3(1), dim3(threads), 0, ctx.stream, lp);
         BB_LAUNCHED();
         ctx.phase = "loss"; ctx.layer = "td";
         ctx.mark("dqn_loss");

@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "common.cuh"
 
 namespace bb {
 
@@ -66,6 +67,7 @@ template <int BM, int BN, int TM, int TN, bool A_KMAJOR, bool B_KMAJOR, bool A_U
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmArgs g) {
     constexpr int NT = (BM / TM) * (BN / TN);  // threads per CTA
     static_assert(NT % 32 == 0 && NT <= 1024, "whole warps");
+    pdl_sync();
     static_assert(TM % 4 == 0 && TN % 4 == 0, "float4 register tiles");
     constexpr int BK = kBK;
     constexpr int PAD = 4;

@@ -35,6 +35,7 @@ void Ctx::join_from(const Ctx& s) const {
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                      int splits, const float* __restrict__ bias, int relu,
                                      const float* __restrict__ mask) {
+    pdl_sync();
     size_t total = (size_t)M * N;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         int m = (int)(i / N), n = (int)(i % N);
@@ -52,6 +53,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
 __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                       int splits, const float* __restrict__ bias, int relu,
                                       const float* __restrict__ mask) {
+    pdl_sync();
     size_t total = (size_t)M * N;
     const int g = threadIdx.x & 7;
     for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3; i < ((total + 31) & ~(size_t)31);
@@ -77,11 +79,11 @@ template <int BM, int BN, int TM, int TN>
 static void launch_cfg(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
     constexpr int NT = (BM / TM) * (BN / TN);
     switch (mode) {
-        case G_FWD: gemm_kernel<BM, BN, TM, TN, true, true, false, false><<<grid, NT, 0, s>>>(a); break;
-        case G_FWD_U8: gemm_kernel<BM, BN, TM, TN, true, true, true, false><<<grid, NT, 0, s>>>(a); break;
-        case G_NN: gemm_kernel<BM, BN, TM, TN, true, false, false, false><<<grid, NT, 0, s>>>(a); break;
-        case G_WGRAD: gemm_kernel<BM, BN, TM, TN, false, false, false, false><<<grid, NT, 0, s>>>(a); break;
-        case G_WGRAD_U8: gemm_kernel<BM, BN, TM, TN, false, false, false, true><<<grid, NT, 0, s>>>(a); break;
+        case G_FWD: launch_pdl(gemm_kernel<BM, BN, TM, TN, true, true, false, false>, grid, dim3(NT), 0, s, a); break;
+        case G_FWD_U8: launch_pdl(gemm_kernel<BM, BN, TM, TN, true, true, true, false>, grid, dim3(NT), 0, s, a); break;
+        case G_NN: launch_pdl(gemm_kernel<BM, BN, TM, TN, true, false, false, false>, grid, dim3(NT), 0, s, a); break;
+        case G_WGRAD: launch_pdl(gemm_kernel<BM, BN, TM, TN, false, false, false, false>, grid, dim3(NT), 0, s, a); break;
+        case G_WGRAD_U8: launch_pdl(gemm_kernel<BM, BN, TM, TN, false, false, false, true>, grid, dim3(NT), 0, s, a); break;
         case G_WGRAD_AU8: throw Error("G_WGRAD_AU8 exists on the tcgen05 path only");
     }
     BB_LAUNCHED();
@@ -157,10 +159,10 @@ void gemm_simt(const Ctx& c, GemmMode mode, GemmArgs a) {
         size_t total = (size_t)a.M * a.N;
         if (split >= 16) {
             int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
-            splitk_reduce8_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+            launch_pdl(splitk_reduce8_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
         } else {
             int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
-            splitk_reduce_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+            launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
         }
         BB_LAUNCHED();
         c.mark("splitk_reduce");
@@ -197,6 +199,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ Y, float* __rest
 // chunk to finish (counter in the workspace tail) adds the R partials in index order (deterministic).
 __global__ void colsum_fused_kernel(const float* __restrict__ Y, float* __restrict__ part, unsigned int* __restrict__ counters,
                                     float* __restrict__ out, int M, int N, int rows_per_block, int R) {
+    pdl_sync();
     __shared__ float s[8][33];
     __shared__ bool s_last;
     int n = blockIdx.x * 32 + threadIdx.x;
@@ -242,7 +245,7 @@ void colsum(const Ctx& c, const float* dY, float* db, int M, int N) {
     R = (M + rpb - 1) / rpb;
     unsigned int* counters = reinterpret_cast<unsigned int*>(c.ws + c.ws_floats - counter_floats);
     BB_CHECK(chunks <= (int)counter_floats, "colsum: too many column chunks");
-    colsum_fused_kernel<<<dim3(chunks, R), dim3(32, 8), 0, c.stream>>>(dY, c.ws, counters, db, M, N, rpb, R);
+    launch_pdl(colsum_fused_kernel, dim3(chunks, R), dim3(32, 8), 0, c.stream, dY, c.ws, counters, db, M, N, rpb, R);
     BB_LAUNCHED();
     c.mark("colsum");
 }
@@ -317,6 +320,7 @@ void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const voi
 // dX[b][h][w][c] = sum over the kernel taps that touch (h, w) of col[(b,oh,ow)][(kh,kw,c)]
 __global__ void col2im_nhwc_kernel(const float* __restrict__ col, float* __restrict__ dX, const float* __restrict__ mask,
                                    int B, int C, int H, int W, int KH, int KW, int S, int OH, int OW) {
+    pdl_sync();
     const int C4 = C / 4;
     size_t total = (size_t)B * H * W * C4;
     const int K = KH * KW * C;
@@ -408,7 +412,7 @@ void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float
     gemm(c, G_NN, a);
     size_t total = (size_t)g.B * g.H * g.W * (g.C / 4);
     int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 16);
-    col2im_nhwc_kernel<<<blocks, 256, 0, c.stream>>>(col, dX, mask, g.B, g.C, g.H, g.W, g.KH, g.KW, g.S, g.OH, g.OW);
+    launch_pdl(col2im_nhwc_kernel, dim3(blocks), dim3(256), 0, c.stream, col, dX, mask, g.B, g.C, g.H, g.W, g.KH, g.KW, g.S, g.OH, g.OW);
     BB_LAUNCHED();
     c.mark("col2im");
 }

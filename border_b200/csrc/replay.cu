@@ -200,6 +200,7 @@ struct SampleParams {
 __global__ void __launch_bounds__(256) replay_sample_gather_kernel(SampleParams p, uint32_t batch) {
     __shared__ unsigned long long s_ix;
     __shared__ bool s_last;
+    pdl_sync();
     const uint32_t b = blockIdx.y, c = blockIdx.x;
     if (threadIdx.x == 0) {
         unsigned long long ix;
@@ -757,7 +758,7 @@ void Replay::sample(size_t B, bb_batch_view* out, bool launch) {
     sp.beta_0 = cfg.beta_0; sp.beta_final = cfg.beta_final; sp.n_opts_final = cfg.n_opts_final;
     sp.fr_seed = cfg.fastrand_seed; sp.inject_u = inject_u; sp.powf_fused = powf_fused;
     if (launch) {
-        replay_sample_gather_kernel<<<dim3(n_chunks, (unsigned)B), 256, 0, stream>>>(sp, (uint32_t)B);
+        launch_pdl_if(pdl_replay_enabled(), replay_sample_gather_kernel, dim3(n_chunks, (unsigned)B), dim3(256), 0, stream, sp, (uint32_t)B);
         BB_LAUNCHED();
     }
     if (!per) rng_pos += B;

@@ -22,7 +22,7 @@ static void tc_launch(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t 
             BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
             configured = true;                                                                                  \
         }                                                                                                       \
-        kern<<<grid, tc::NTHREADS, smem, s>>>(a);                                                               \
+        launch_pdl(kern, grid, dim3(tc::NTHREADS), smem, s, a);                                                 \
     } while (0)
     switch (mode) {
         case G_FWD: if (fast) BB_TC_LAUNCH(true, true, false, false, true); else BB_TC_LAUNCH(true, true, false, false, false); break;
@@ -229,10 +229,10 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
         const int rows = a.trans_out ? a.N : a.M, cols = a.trans_out ? a.M : a.N;  // layout of the partials = layout of C
         if (split >= 16) {
             int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
-            splitk_reduce8_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask);
+            launch_pdl(splitk_reduce8_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask);
         } else {
             int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
-            splitk_reduce_kernel<<<blocks, 256, 0, c.stream>>>(c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask);
+            launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask);
         }
         BB_LAUNCHED();
         c.mark("splitk_reduce");

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    pdl_sync();  // barriers / tensor memory are set up while the previous kernel of the stream drains
     if (trace0) g_tc_trace[1][57][0] = clock64();
 
     if (warp < 8) {
