@@ -413,9 +413,6 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
 
         // ================================================================ epilogue
         if (trace0) g_tc_trace[1][58][0] = clock64();
-        if (nks > 0 && alive) alive = mbar_wait(smem_u32(&accum_bar), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (trace0) g_tc_trace[1][59][0] = clock64();
         const bool direct = g.split_k <= 1;
         float* out = direct ? g.C : g.workspace + (size_t)blockIdx.z * g.M * g.N;
         const int ldo = direct ? g.ldc : (g.trans_out ? g.M : g.N);
@@ -425,6 +422,63 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
         const size_t rowo = m < g.M ? (mapped ? (size_t)g.c_rowoff[m] : (size_t)m * ldo) : 0;
         constexpr int HALF = BN / 2 < 16 ? 16 : BN / 2;   // columns per warp-pair member
         const int c_begin = (warp >> 2) * HALF;
+        // FAST, whole-tile problems with 16-byte aligned rows: the bias / ReLU-mask groups of this thread's columns are
+        // fetched as float4 BEFORE the accumulator is waited for (they do not depend on it), and stored as float4.
+        constexpr bool EPI_VEC = FAST && BN <= 64;
+        bool epi_vec = false;
+        if (EPI_VEC)
+            epi_vec = !g.trans_out && (ldo & 3) == 0 && (!mapped || g.tables_vec4) &&
+                      ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(g.bias) | reinterpret_cast<uintptr_t>(g.mask)) & 15) == 0;
+        if (EPI_VEC && epi_vec) {
+            constexpr int G = HALF / 4;
+            const bool use_bias = direct && g.bias != nullptr, use_mask = direct && g.mask != nullptr;
+            float4 b4[G], k4[G];
+            size_t colo[G];
+#pragma unroll
+            for (int gi = 0; gi < G; ++gi) {
+                const int n = n0 + c_begin + 4 * gi;
+                colo[gi] = (mapped && g.c_coloff) ? (size_t)g.c_coloff[n] : (size_t)n;
+                b4[gi] = use_bias ? __ldg(reinterpret_cast<const float4*>(g.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                k4[gi] = use_mask ? __ldg(reinterpret_cast<const float4*>(g.mask + rowo + colo[gi])) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+            if (nks > 0 && alive) alive = mbar_wait(smem_u32(&accum_bar), 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (trace0) g_tc_trace[1][59][0] = clock64();
+#pragma unroll
+            for (int c0 = 0; c0 < HALF; c0 += 16) {
+                uint32_t r[16];
+                if (nks > 0 && alive) {
+                    uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+                        "%14, %15}, [%16];\n"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = 0u;
+                }
+#pragma unroll
+                for (int j4 = 0; j4 < 16; j4 += 4) {
+                    const int gi = (c0 + j4) / 4;
+                    float4 v = make_float4(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]),
+                                           __uint_as_float(r[j4 + 3]));
+                    if (direct) {
+                        v.x += b4[gi].x; v.y += b4[gi].y; v.z += b4[gi].z; v.w += b4[gi].w;
+                        if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        v.x = k4[gi].x > 0.f ? v.x : 0.f; v.y = k4[gi].y > 0.f ? v.y : 0.f;
+                        v.z = k4[gi].z > 0.f ? v.z : 0.f; v.w = k4[gi].w > 0.f ? v.w : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(out + rowo + colo[gi]) = v;
+                }
+            }
+        } else {
+        if (nks > 0 && alive) alive = mbar_wait(smem_u32(&accum_bar), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (trace0) g_tc_trace[1][59][0] = clock64();
         if (c_begin < BN) {
 #pragma unroll
             for (int c0 = 0; c0 < HALF; c0 += 16) {
@@ -475,6 +529,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                     }
                 }
             }
+        }
         }
         if (trace0) g_tc_trace[1][60][0] = clock64();
     } else if (lane == 0) {
