@@ -103,6 +103,26 @@ __device__ __forceinline__ float4 u8x4_to_float4(uint32_t w) {
                        (float)(w >> 24) * s);
 }
 
+// 16 accumulator columns at taddr plus the 16 columns `second` further on, summed (the two accumulator halves of
+// the stacked 3xTF32 scheme)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+        "%14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, uint32_t second, uint32_t* r) {
+    uint32_t r2[16];
+    tmem_ld16(taddr, r);
+    tmem_ld16(taddr + second, r2);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+}
+
 // swizzled byte offset of 16-byte chunk c (0..7) of row r inside a [rows][128 B] K-major tile
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
@@ -123,7 +143,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
     constexpr int A_LD = BM * 8 / NPROD;                             // float4 per producer thread per stage (4)
     constexpr int B_LD = (BN * 8 + NPROD - 1) / NPROD;               // 1, 2 or 4
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    // accumulator: columns [0, BN) = hi*hi + lo*hi, columns [BN, 2 BN) = hi*lo (see the MMA issuer); summed in the epilogue
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
     __shared__ uint32_t tmem_base_s;
@@ -448,15 +469,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
             for (int c0 = 0; c0 < HALF; c0 += 16) {
                 uint32_t r[16];
                 if (nks > 0 && alive) {
-                    uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin + c0);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-                        "%14, %15}, [%16];\n"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                        : "r"(taddr)
-                        : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    tmem_ld16_sum(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin + c0), (uint32_t)BN, r);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) r[j] = 0u;
@@ -486,15 +499,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                 if (col >= BN) break;
                 uint32_t r[16];
                 if (nks > 0 && alive) {
-                    uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-                        "%14, %15}, [%16];\n"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                        : "r"(taddr)
-                        : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    tmem_ld16_sum(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, (uint32_t)BN, r);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) r[j] = 0u;
@@ -538,6 +543,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
         // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), both K-major,
         // N >> 3 at bit 17, M >> 4 at bit 24
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // "stacked" 3xTF32: the hi and lo tiles of B are adjacent in shared memory, so ONE descriptor spans [B_hi; B_lo]
+        // as 2 BN rows.  A_hi x [B_hi; B_lo] (N = 2 BN) yields hi*hi in columns [0, BN) and hi*lo in [BN, 2 BN);
+        // A_lo x B_hi (N = BN) accumulates lo*hi into [0, BN).  8 MMAs per k-slice instead of 12, A_hi read once
+        // instead of twice (56 KB instead of 72 KB of shared-memory operand reads per 128x64x32 slice).
+        const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         bool alive = true;
         for (int ks = 0; ks < nks && alive; ++ks) {
             const int s = ks % STAGES;
@@ -547,16 +557,15 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
             if (trace && ks < 56) g_tc_trace[1][ks][1] = clock64();
             if ((g.fence_mode & 1) == 1 && !(g.fence_mode & 64)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = tiles + s * STAGE_BYTES, a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
-            const uint64_t da_hi = make_desc(a_hi), da_lo = make_desc(a_lo), db_hi = make_desc(b_hi), db_lo = make_desc(b_lo);
+            const uint32_t a_hi = tiles + s * STAGE_BYTES, a_lo = a_hi + A_TILE, b_hi = a_lo + A_TILE;  // b_lo = b_hi + B_TILE follows
+            const uint64_t da_hi = make_desc(a_hi), da_lo = make_desc(a_lo), db_hi = make_desc(b_hi);
 #pragma unroll
             for (int k4 = 0; k4 < BK / 8; ++k4) {
                 const uint64_t adv = (uint64_t)(k4 * 2);  // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle atom
                 if (g.fence_mode & 32) continue;
-                mma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, (ks | k4) ? 1u : 0u);
-                if (g.fence_mode & 128) continue;  // debug: one pass only (timing floor, wrong numerics)
+                mma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc2, (ks | k4) ? 1u : 0u);
+                if (g.fence_mode & 128) continue;  // debug: skip the lo*hi pass (timing floor, wrong numerics)
                 mma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
-                mma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
             }
             mma_commit(smem_u32(&empty_bar[s]));  // frees the stage once the MMAs above have read it
             if (trace && ks < 56) g_tc_trace[1][ks][3] = clock64();
