@@ -382,10 +382,9 @@ __global__ void dgrad_prep_kernel(const float4* __restrict__ dY, float4* __restr
 void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float* W, float* col, float* dX,
                    const float* mask) {
     BB_CHECK(!g.u8_chw && g.C % 4 == 0, "conv_bwd_data expects an NHWC float input with C % 4 == 0");
-    // Opt-in (BB_DGRAD_GATHER=1): measured equal to the col2im path at B = 256 (c2 8+68 us vs 54+22 us, c3 8+50 us
-    // vs 36+18 us; the tcgen05 kernel is bound per 128x64x32 tile step, and the padded form runs 23-65 % more of
-    // them), so the proven path stays the default until the GEMM main loop is faster.
-    if (g.dypad && g.dg_rowbase && g.dg_wt && env_int("BB_TC", 1) && env_int("BB_DGRAD_GATHER", 0)) {
+    // Default since the whole-tile producer path of the tcgen05 kernel: DQN step 415 -> 382 us at B = 256 (c2: 9 + 41 us
+    // instead of 46 + 22 us for dY*W + col2im, c3: 9 + 36 us instead of 35 + 18 us).  BB_DGRAD_GATHER=0 keeps the col2im path.
+    if (g.dypad && g.dg_rowbase && g.dg_wt && env_int("BB_TC", 1) && env_int("BB_DGRAD_GATHER", 1)) {
         // dX[b][S hq + ph][S wq + pw][c] = sum_{jh,jw,oc} dYpad[b][hq + Jh-1-jh][wq + Jw-1-jw][oc] W[oc][S jh + ph][S jw + pw][c]:
         // one tcgen05 GEMM, no [M][K] column buffer and no col2im pass (the buffer was 42 MB for c2 at B = 256)
         const int Jh = g.KH / g.S, Jw = g.KW / g.S;

@@ -71,11 +71,12 @@ def test_dqn_parity_holds_on_the_cuda_core_path(monkeypatch):
     _run("mlp", 64, "SmoothL1", True, per=False, clip=False, steps=2)
 
 
-def test_dqn_parity_holds_with_the_gather_form_data_gradient(monkeypatch):
-    """BB_DGRAD_GATHER=1: conv data gradients as ONE tcgen05 GEMM over the zero-padded dY (transposed
-    convolution with separable gather operands and a separable output map) instead of dY*W + col2im."""
+@pytest.mark.parametrize("gather", ["1", "0"])
+def test_dqn_parity_holds_with_both_conv_data_gradient_forms(monkeypatch, gather):
+    """BB_DGRAD_GATHER=1 (default): conv data gradients as ONE tcgen05 GEMM over the zero-padded dY (transposed
+    convolution with separable gather operands and a separable output map); 0: dY*W + col2im."""
     monkeypatch.setenv("BB_TC", "1")
-    monkeypatch.setenv("BB_DGRAD_GATHER", "1")
+    monkeypatch.setenv("BB_DGRAD_GATHER", gather)
     from tests.test_dqn_gpu import _run
     _run("cnn", 32, "Mse", False, per=False, clip=False, steps=3, lr=1e-4)
     _run("cnn", 256, "SmoothL1", True, per=False, clip=False, steps=1, lr=1e-4)
