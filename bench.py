@@ -431,9 +431,9 @@ def other_workloads(dev, stream, timed, pk):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture of the same
 # step (profiles/r01_tc_gemm_ncu_full.txt, profiles/r01_misc_ncu_full.txt; cold-cache replays)
-NCU_TRAFFIC = {"c2.fwd": 13397760, "c3.fwd": 5583104, "l1.fwd": 9708032, "l1.wgrad": 3817472, "l1.dgrad": 10241792,
-               "c3.wgrad": 8654080, "c3.dgrad": 4136704 + 707840, "c2.wgrad": 18582528, "c2.dgrad": 6237184 + 987648,
-               "c1.wgrad": 20360704, "c1.fwd": 7693056}
+NCU_TRAFFIC = {"c2.fwd": 13400000, "c3.fwd": 5580000, "l1.fwd": 9700000, "l1.wgrad": 3810000, "l1.dgrad": 10200000,
+               "c3.wgrad": 8670000, "c3.dgrad": 13600000, "c2.wgrad": 18600000, "c2.dgrad": 21400000 + 11500,
+               "c1.wgrad": 20400000, "c1.fwd": 7693056}
 
 
 def roofline_for(label, ms, step_ms, pk):
@@ -448,8 +448,9 @@ def roofline_for(label, ms, step_ms, pk):
         return {"kernel": label, "bound": "tensor", "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": tf / pk["tf_sust"], "traffic": NCU_TRAFFIC.get(layer), "ms_per_launch": ms, "share_of_step": ms / step_ms,
                 "algorithmic_flop": flop, "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside the step)",
-                "note": ("tcgen05 kind::tf32, 3 MMA passes per product (3xTF32 for fp32 parity): algorithmic FLOPs are "
-                         "counted once, so the tensor pipe does 3x this; peak is the dense bf16 figure (TF32 peak is half)")
+                "note": ("tcgen05 kind::tf32, 3xTF32 for fp32 parity (hi*hi and hi*lo in one N=2*BN MMA, lo*hi in a second): "
+                         "algorithmic FLOPs are counted once, so the tensor pipe does 3x this; peak is the dense bf16 figure "
+                         "(TF32 peak is half)")
                 if on_tc else "fp32 CUDA-core implicit GEMM; peak is the dense bf16 tensor figure"}
     return {"kernel": label, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
             "traffic": None, "ms_per_launch": ms, "share_of_step": ms / step_ms, "peak_source": pk["src"]}
