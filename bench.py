@@ -268,15 +268,11 @@ def run_b200(args):
 
     # ---- env-steps/sec: Sampler::sample_and_push with a zero-cost synthetic env
     # (Policy::sample on a host obs + push), the reference's `samples_per_sec`
-    def env_step():
-        agent.sample(h_obs[:1])
-        rb.push(tr)
-
-    env_n = max(50, args.steps)
+    env_n = max(200, args.steps)
+    hl.env_steps(agent, rb, h_obs, h_next, h_rew, h_term, h_trunc, 20)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(env_n):
-        env_step()
+    hl.env_steps(agent, rb, h_obs, h_next, h_rew, h_term, h_trunc, env_n)  # C++ loop over the C ABI (bbh_env_steps)
     torch.cuda.synchronize()
     env_sps = world * env_n / (time.perf_counter() - t0)
 

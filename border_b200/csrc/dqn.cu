@@ -128,6 +128,12 @@ struct Dqn : Agent {
     // opt_with_record waits for THAT event only, so the host enqueues the next step while backward + Adam still run
     cudaEvent_t ev_rec = nullptr;
     float* h_rec = nullptr;  // pinned, 8 floats
+    // CUDA graph of the policy forward (H2D obs -> Q net -> D2H q), replayed per Policy::sample call
+    cudaGraphExec_t sgexec = nullptr;
+    size_t sg_n = 0;
+    const void* sg_stream = nullptr;
+    uint64_t sample_eager = 0;
+    bool sgraph_broken = false;
     uint8_t* d_obs_in = nullptr;  // policy input staging
     uint8_t* h_obs_in = nullptr;
     float* h_q = nullptr;
@@ -159,6 +165,7 @@ struct Dqn : Agent {
         qnet.release(); qnet_tgt.release();
         net.free_tables();
         if (gexec) cudaGraphExecDestroy(gexec);
+        if (sgexec) cudaGraphExecDestroy(sgexec);
         if (ev_rec) cudaEventDestroy(ev_rec);
         if (h_rec) cudaFreeHost(h_rec);
         cudaFree(d_td); cudaFree(d_out); cudaFree(d_obs_in);
@@ -332,11 +339,55 @@ struct Dqn : Agent {
             BB_CUDA(cudaMallocHost(&h_obs_in, obs_in_cap));
             BB_CUDA(cudaMallocHost(&h_q, n * net.out_dim * sizeof(float)));
             net.alloc_workspace(ws_act, (int)n, false);
+            if (sgexec) { cudaGraphExecDestroy(sgexec); sgexec = nullptr; }
         }
         memcpy(h_obs_in, obs, n * row);
-        BB_CUDA(cudaMemcpyAsync(d_obs_in, h_obs_in, n * row, cudaMemcpyHostToDevice, ctx.stream));
-        const float* q = net.forward(ctx, qnet.p, d_obs_in, net.in_elems, (int)n, ws_act);
-        BB_CUDA(cudaMemcpyAsync(h_q, q, n * net.out_dim * sizeof(float), cudaMemcpyDeviceToHost, ctx.stream));
+        const bool small_ok = n <= 8;  // one cooperative kernel (Net::forward_small): three stream operations need no graph
+        bool used_small = false;
+        auto enqueue = [&]() {
+            BB_CUDA(cudaMemcpyAsync(d_obs_in, h_obs_in, n * row, cudaMemcpyHostToDevice, ctx.stream));
+            const float* q = small_ok ? net.forward_small(ctx, qnet.p, d_obs_in, net.in_elems, (int)n, ws_act) : nullptr;
+            used_small = q != nullptr;
+            if (!q) q = net.forward(ctx, qnet.p, d_obs_in, net.in_elems, (int)n, ws_act);
+            BB_CUDA(cudaMemcpyAsync(h_q, q, n * net.out_dim * sizeof(float), cudaMemcpyDeviceToHost, ctx.stream));
+        };
+        // the forward is a chain of ~9 tiny launches: after two eager calls it is captured once per (n, stream) and
+        // replayed (every argument is launch-invariant: fixed staging buffers, the parameter vector's address)
+        const char* genv = getenv("BB_GRAPH");
+        const bool want = !small_ok && !(genv && atoi(genv) == 0) && !sgraph_broken && !ctx.prof && ctx.stream != nullptr &&
+                          ctx.stream != cudaStreamLegacy && ctx.stream != cudaStreamPerThread && sample_eager >= 2;
+        bool done = false;
+        if (want) {
+            if (sgexec && sg_n == n && sg_stream == (const void*)ctx.stream) {
+                BB_CUDA(cudaGraphLaunch(sgexec, ctx.stream));
+                done = true;
+            } else {
+                if (sgexec) { cudaGraphExecDestroy(sgexec); sgexec = nullptr; }
+                const uint64_t n0 = g_launch_count.load();
+                cudaGraph_t graph = nullptr;
+                bool ok = cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    try { enqueue(); } catch (...) { ok = false; }
+                    if (cudaStreamEndCapture(ctx.stream, &graph) != cudaSuccess || !graph) ok = false;
+                }
+                if (ok && cudaGraphInstantiate(&sgexec, graph, 0) != cudaSuccess) { ok = false; sgexec = nullptr; }
+                if (graph) cudaGraphDestroy(graph);
+                if (ok) {
+                    sg_n = n; sg_stream = (const void*)ctx.stream;
+                    BB_CUDA(cudaGraphLaunch(sgexec, ctx.stream));
+                    done = true;
+                } else {
+                    cudaGetLastError();
+                    sgraph_broken = true;
+                    g_launch_count.store(n0);
+                }
+            }
+        }
+        if (!done) {
+            enqueue();
+            sample_eager += 1;
+        }
+        (void)used_small;
         BB_CUDA(cudaStreamSynchronize(ctx.stream));
         int64_t* out = (int64_t*)act_out;
         const int A = net.out_dim;

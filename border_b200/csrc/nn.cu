@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include "gemm.cuh"
+#include <cooperative_groups.h>
 #include "nn.cuh"
 
 namespace bb {
@@ -852,6 +853,97 @@ const float* Net::forward(const Ctx& c, const float* p, const void* input, long 
         x = w.act[i];
         ldx = (long)l.out_elems_per_sample;
     }
+    return w.act.back();
+}
+
+// ---- small-batch forward (Policy::sample): one cooperative kernel for the whole net ------------------------------
+struct SmallLayer {
+    int type, M, N, K, relu, u8;   // type 0 linear, 1 conv (gather); output [M][N]
+    const int* rowbase;            // conv: [M]
+    const int* koff;               // conv: [K]
+    const void* in;
+    float* out;
+    long ld_in;                    // linear: row stride of the input
+    size_t w_off, b_off;
+};
+struct SmallNet {
+    SmallLayer l[8];
+    int n_layers;
+    const float* p;
+};
+
+__global__ void __launch_bounds__(256) small_forward_kernel(SmallNet P) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int lane = threadIdx.x & 31;
+    const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nw = (long)gridDim.x * (blockDim.x >> 5);
+    for (int li = 0; li < P.n_layers; ++li) {
+        const SmallLayer& L = P.l[li];
+        const float* W = P.p + L.w_off;
+        const float* bias = P.p + L.b_off;
+        const long total = (long)L.M * L.N;
+        for (long o = gw; o < total; o += nw) {
+            const int m = (int)(o / L.N), n = (int)(o % L.N);
+            const float* w = W + (size_t)n * L.K;
+            float acc = 0.f;
+            if (L.type == 1) {
+                const long base = L.rowbase[m];
+                if (L.u8) {
+                    const uint8_t* x = reinterpret_cast<const uint8_t*>(L.in) + base;
+                    const float s = 1.0f / 255.0f;
+                    for (int k = lane; k < L.K; k += 32) acc = fmaf((float)x[L.koff[k]] * s, w[k], acc);
+                } else {
+                    const float* x = reinterpret_cast<const float*>(L.in) + base;
+                    for (int k = lane; k < L.K; k += 32) acc = fmaf(x[L.koff[k]], w[k], acc);
+                }
+            } else {
+                const float* x = reinterpret_cast<const float*>(L.in) + (size_t)m * L.ld_in;
+                for (int k = lane; k < L.K; k += 32) acc = fmaf(x[k], w[k], acc);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (lane == 0) {
+                acc += bias[n];
+                if (L.relu) acc = fmaxf(acc, 0.f);
+                L.out[(size_t)m * L.N + n] = acc;
+            }
+        }
+        if (li + 1 < P.n_layers) grid.sync();
+    }
+}
+
+const float* Net::forward_small(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w) const {
+    if (B > 8 || layers.size() > 8 || layers.empty() || B > w.max_batch || !env_int("BB_POLICY_FUSED", 1)) return nullptr;
+    SmallNet P;
+    memset(&P, 0, sizeof(P));
+    P.n_layers = (int)layers.size();
+    P.p = p;
+    const void* x = input;
+    long ldx = ld_in;
+    for (size_t i = 0; i < layers.size(); ++i) {
+        const Layer& l = layers[i];
+        SmallLayer& s = P.l[i];
+        s.relu = l.relu ? 1 : 0; s.in = x; s.out = w.act[i]; s.w_off = l.w_off; s.b_off = l.b_off; s.ld_in = ldx;
+        if (l.type == 1) {
+            const ConvGeom& g = l.geom;
+            s.type = 1; s.M = B * g.OH * g.OW; s.N = g.OC; s.K = g.K(); s.u8 = g.u8_chw ? 1 : 0;
+            s.rowbase = w.rowbase[i]; s.koff = g.koff;
+        } else {
+            s.type = 0; s.M = B; s.N = l.out_dim; s.K = l.in_dim;
+        }
+        x = w.act[i];
+        ldx = (long)l.out_elems_per_sample;
+    }
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, small_forward_kernel, 256, 0));
+        ctas_per_sm = std::max(1, std::min(ctas_per_sm, 4));
+    }
+    void* args[] = {&P};
+    BB_CUDA(cudaLaunchCooperativeKernel((void*)small_forward_kernel, dim3(c.sms * ctas_per_sm), dim3(256), args, 0, c.stream));
+    BB_LAUNCHED();
+    c.phase = "policy"; c.layer = "forward";
+    c.mark("small_forward");
     return w.act.back();
 }
 

@@ -167,6 +167,10 @@ class Net {
     void init_params(const Ctx& c, float* p, uint64_t seed) const;
     // forward: input [B][in] (u8 CHW frames or float rows); returns ws.act.back()
     const float* forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w) const;
+    // Policy::sample-sized batches (B <= 8): the whole forward as ONE cooperative kernel, a warp per output element
+    // and a grid-wide barrier between layers (the per-layer GEMM launches are pure latency at B = 1).  Returns null
+    // when the net / batch does not qualify (caller falls back to forward()).
+    const float* forward_small(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w) const;
     // backward from d(output) in w.dact.back(); accumulates nothing: grads are overwritten.
     // g == nullptr skips the weight gradients (data gradient only).
     // d_input (may be null) receives the gradient wrt a float input [B][in].

@@ -156,4 +156,23 @@ int32_t bbh_e2e_steps(bb_agent* agent, bb_replay* replay, const void* obs, const
     BBH_END
 }
 
+/* n_steps x Sampler::sample_and_push with a zero-cost environment (trainer/sampler.rs:99-144): Policy::sample on a host
+ * observation (discrete action, DQN / IQN) + ExperienceBufferBase::push of the resulting host transition. */
+int32_t bbh_env_steps(bb_agent* agent, bb_replay* replay, const void* obs, const void* next_obs, const float* reward,
+                      const int8_t* is_terminated, const int8_t* is_truncated, uint64_t obs_row_bytes, uint64_t n_slots,
+                      uint64_t n_steps, int64_t* last_act) {
+    BBH_BEGIN
+    if (!agent || !replay || !obs || !next_obs || !reward || !is_terminated || !is_truncated || !n_slots)
+        throw Error("null argument");
+    int64_t act = 0;
+    for (uint64_t i = 0; i < n_steps; ++i) {
+        const uint64_t j = i % n_slots;
+        check(bb_agent_sample(agent, (const uint8_t*)obs + j * obs_row_bytes, 1, &act));
+        check(bb_replay_push(replay, (const uint8_t*)obs + j * obs_row_bytes, &act, (const uint8_t*)next_obs + j * obs_row_bytes,
+                             reward + j, is_terminated + j, is_truncated + j, 1, 0));
+    }
+    if (last_act) *last_act = act;
+    BBH_END
+}
+
 }  // extern "C"

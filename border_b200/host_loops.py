@@ -48,6 +48,8 @@ def host_lib():
                                       C.POINTER(bbh_trainer_cfg), C.POINTER(bbh_train_stat)]
         l.bbh_e2e_steps.restype = C.c_int32
         l.bbh_e2e_steps.argtypes = [C.c_void_p] * 8 + [C.c_uint64] * 4 + [C.POINTER(C.c_float)]
+        l.bbh_env_steps.restype = C.c_int32
+        l.bbh_env_steps.argtypes = [C.c_void_p] * 7 + [C.c_uint64] * 3 + [C.POINTER(C.c_int64)]
         _hl = l
     return _hl
 
@@ -96,3 +98,15 @@ def e2e_steps(agent, buffer, obs, act, next_obs, reward, is_terminated, is_trunc
     _check(host_lib().bbh_e2e_steps(agent.handle, buffer.handle, *[a.ctypes.data for a in arrs],
                                     arrs[0].nbytes // n, arrs[1].nbytes // n, n, n_steps, C.byref(loss)))
     return loss.value
+
+
+def env_steps(agent, buffer, obs, next_obs, reward, is_terminated, is_truncated, n_steps):
+    """n_steps x Sampler::sample_and_push (trainer/sampler.rs:99-144) with a zero-cost environment, in C++ over the C ABI:
+    Policy::sample on a host observation + push of the host transition.  Returns the last action."""
+    import numpy as np
+    n = len(reward)
+    arrs = [np.ascontiguousarray(a) for a in (obs, next_obs, reward, is_terminated, is_truncated)]
+    act = C.c_int64()
+    _check(host_lib().bbh_env_steps(agent.handle, buffer.handle, *[a.ctypes.data for a in arrs], arrs[0].nbytes // n, n,
+                                    n_steps, C.byref(act)))
+    return act.value

@@ -60,6 +60,12 @@ int32_t bbh_e2e_steps(bb_agent* agent, bb_replay* replay, const void* obs, const
                       uint64_t obs_row_bytes, uint64_t act_row_bytes, uint64_t n_slots, uint64_t n_steps,
                       float* last_loss);
 
+/* n_steps x Sampler::sample_and_push (border-core/src/trainer/sampler.rs:99-144) with a zero-cost environment:
+ * bb_agent_sample on the host observation of slot i % n_slots (discrete action) + bb_replay_push of that transition. */
+int32_t bbh_env_steps(bb_agent* agent, bb_replay* replay, const void* obs, const void* next_obs, const float* reward,
+                      const int8_t* is_terminated, const int8_t* is_truncated, uint64_t obs_row_bytes, uint64_t n_slots,
+                      uint64_t n_steps, int64_t* last_act);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,7 +63,7 @@ def test_errors_do_not_cross_the_abi():
 def test_host_loop_library_loads():
     from border_b200 import host_loops as H
     lib = H.host_lib()
-    for name in ("bbh_last_error", "bbh_trainer_cfg_default", "bbh_train", "bbh_train_async"):
+    for name in ("bbh_last_error", "bbh_trainer_cfg_default", "bbh_train", "bbh_train_async", "bbh_e2e_steps", "bbh_env_steps"):
         assert hasattr(lib, name)
     c = H.trainer_cfg()
     # TrainerConfig::default (trainer/config.rs:49-62), ActorManagerConfig::default n_buffer = 100
