@@ -222,6 +222,11 @@ def run_b200(args):
     # ---- device-resident throughput: K back-to-back opt() calls
     clocks = ClockSampler(dev)
     clocks.start()
+    # untimed pre-warm beyond the W warm-up steps: a fresh box ramps its clocks over more than the ~8 ms that 20 steps
+    # take (a first-process run measured 9 % low without it), and the update is graph-captured after 3 eager steps
+    for _ in range(300):
+        agent.opt(rb)
+    torch.cuda.synchronize()
     lib.bb_kernel_launch_count(None, 1)
     ms = timed(lambda: agent.opt(rb), args.steps, args.warmup)
     lib.bb_kernel_launch_count(__import__("ctypes").byref(n0), 0)

@@ -625,6 +625,8 @@ Replay::~Replay() {
     cudaFree(stage_dev); cudaFree(upd_ix); cudaFree(upd_td);
     if (stage_host) cudaFreeHost(stage_host);
     for (auto e : stage_events) if (e) cudaEventDestroy(e);
+    for (auto e : copy_events) if (e) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
 }
 
 void Replay::ensure_batch(size_t B) {
@@ -693,6 +695,7 @@ void Replay::push(const void* o, const void* a, const void* no, const float* r, 
             stage_dev = dev_alloc<uint8_t>(stage_cap * kStageSlots);
             for (int k = 0; k < kStageSlots; ++k) {
                 if (!stage_events[k]) BB_CUDA(cudaEventCreateWithFlags(&stage_events[k], cudaEventDisableTiming));
+                if (!copy_events[k]) BB_CUDA(cudaEventCreateWithFlags(&copy_events[k], cudaEventDisableTiming));
                 stage_busy[k] = false;
             }
             stage_slot = 0;
@@ -707,7 +710,10 @@ void Replay::push(const void* o, const void* a, const void* no, const float* r, 
         memcpy(h + off_r, r, 4 * n);
         memcpy(h + off_t, t, n);
         memcpy(h + off_tr, tr, n);
-        BB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
+        if (!copy_stream) BB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        BB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, copy_stream));
+        BB_CUDA(cudaEventRecord(copy_events[stage_slot], copy_stream));
+        BB_CUDA(cudaStreamWaitEvent(stream, copy_events[stage_slot], 0));
         used_slot = stage_slot;
         stage_slot = (stage_slot + 1) % kStageSlots;
         d_o = d + off_o; d_no = d + off_no; d_a = d + off_a; d_r = (const float*)(d + off_r);

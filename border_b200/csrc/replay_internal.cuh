@@ -58,6 +58,10 @@ struct Replay {
     size_t stage_cap = 0;
     int stage_slot = 0;
     cudaEvent_t stage_events[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    // host pushes: the H2D copy of the staging block runs on its own stream (copy engine) and the push kernel on
+    // `stream` waits for its event, so the copy overlaps whatever the stream is still computing (the previous update)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_events[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
     bool stage_busy[kStageSlots] = {false, false, false, false};
     // update_priority staging
     unsigned long long* upd_ix = nullptr;
