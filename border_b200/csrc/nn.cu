@@ -97,8 +97,115 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+// ---- skinny contractions: one dimension <= 16 (the A-wide output layer of a Q net, the 1-wide critic output, the
+// 2x8 actor heads).  The tile kernels need split-K + a reduce launch to fill the GPU on these (9 + 4 us for the DQN
+// output layer, 22 + 13 us for the SAC critic's); a warp (or a thread) per output element does them in one ~3 us
+// launch.  Dense fp32 operands only; same epilogue semantics (bias, ReLU, mask).
+// forward: C[m][n] = act(sum_k A[m*lda+k] B[n*ldb+k] + bias[n]), N <= 16: a warp per output element
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                         float* __restrict__ C, int M, int N, int K, long lda, long ldb,
+                                                         int ldc, const float* __restrict__ bias, int relu,
+                                                         const float* __restrict__ mask) {
+    pdl_sync();
+    const int lane = threadIdx.x & 31;
+    const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (long)gridDim.x * (blockDim.x >> 5);
+    for (long o = gw; o < (long)M * N; o += nw) {
+        const int m = (int)(o / N), n = (int)(o % N);
+        const float* a = A + (size_t)m * lda;
+        const float* b = B + (size_t)n * ldb;
+        float acc = 0.f;
+        for (int k = lane; k < K; k += 32) acc = fmaf(a[k], b[k], acc);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) {
+            if (bias) acc += bias[n];
+            if (relu) acc = fmaxf(acc, 0.f);
+            if (mask) acc = mask[(size_t)m * ldc + n] > 0.f ? acc : 0.f;
+            C[(size_t)m * ldc + n] = acc;
+        }
+    }
+}
+// data gradient: C[m][n] = (sum_k A[m*lda+k] B[k*ldb+n]) * (mask > 0), K <= 16: a thread per output element
+__global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                           float* __restrict__ C, int M, int N, int K, long lda, long ldb,
+                                                           int ldc, const float* __restrict__ mask) {
+    pdl_sync();
+    const size_t total = (size_t)M * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i % N);
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc = fmaf(A[(size_t)m * lda + k], B[(size_t)k * ldb + n], acc);
+        if (mask) acc = mask[(size_t)m * ldc + n] > 0.f ? acc : 0.f;
+        C[(size_t)m * ldc + n] = acc;
+    }
+}
+// weight gradient: C[m][n] = sum_k A[k*lda+m] B[k*ldb+n], M <= 16: 32 columns x 8 k-groups per CTA, partial sums
+// folded in shared memory in k-group order (deterministic)
+__global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                           float* __restrict__ C, int M, int N, int K, long lda, long ldb,
+                                                           int ldc) {
+    pdl_sync();
+    __shared__ float part[8][16][33];
+    const int col = threadIdx.x & 31, kg = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + col;
+    float acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+    if (n < N)
+        for (int k = kg; k < K; k += 8) {
+            const float b = B[(size_t)k * ldb + n];
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+                if (m < M) acc[m] = fmaf(A[(size_t)k * lda + m], b, acc[m]);
+        }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) part[kg][m][col] = acc[m];
+    __syncthreads();
+    // thread (col, kg) finishes rows m = kg, kg + 8
+    for (int m = kg; m < M; m += 8) {
+        float t = 0.f;
+#pragma unroll
+        for (int g2 = 0; g2 < 8; ++g2) t += part[g2][m][col];
+        if (n < N) C[(size_t)m * ldc + n] = t;
+    }
+}
+
+static bool gemm_skinny(const Ctx& c, GemmMode mode, const GemmArgs& a) {
+    if (!env_int("BB_SKINNY", 1)) return false;
+    if (a.a_rowbase || a.a_koff || a.b_rowbase || a.b_noff || a.trans_out || a.c_rowoff) return false;
+    const float* A = reinterpret_cast<const float*>(a.A);
+    const float* B = reinterpret_cast<const float*>(a.B);
+    if (mode == G_FWD && a.N <= 16 && a.K >= 32) {
+        long warps = (long)a.M * a.N;
+        int blocks = (int)std::min<long>((warps + 7) / 8, (long)c.sms * 8);
+        launch_pdl(skinny_fwd_kernel, dim3(blocks), dim3(256), 0, c.stream, A, B, a.C, a.M, a.N, a.K, a.lda, a.ldb, a.ldc,
+                   a.bias, a.relu, a.mask);
+        BB_LAUNCHED();
+        c.mark("skinny_fwd");
+        return true;
+    }
+    if (mode == G_NN && a.K <= 16 && !a.bias && !a.relu) {
+        size_t total = (size_t)a.M * a.N;
+        int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
+        launch_pdl(skinny_dgrad_kernel, dim3(blocks), dim3(256), 0, c.stream, A, B, a.C, a.M, a.N, a.K, a.lda, a.ldb, a.ldc,
+                   a.mask);
+        BB_LAUNCHED();
+        c.mark("skinny_dgrad");
+        return true;
+    }
+    if (mode == G_WGRAD && a.M <= 16 && !a.bias && !a.relu && !a.mask) {
+        launch_pdl(skinny_wgrad_kernel, dim3((a.N + 31) / 32), dim3(256), 0, c.stream, A, B, a.C, a.M, a.N, a.K, a.lda, a.ldb,
+                   a.ldc);
+        BB_LAUNCHED();
+        c.mark("skinny_wgrad");
+        return true;
+    }
+    return false;
+}
+
 void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
     if (a.M <= 0 || a.N <= 0) return;
+    if (gemm_skinny(c, mode, a)) return;
     const int use_tc = env_int("BB_TC", 1);  // read per call so tests can flip it (0 = fp32 CUDA-core tiles)
     // tcgen05 path (tc_gemm.cu); tiny problems (policy forward, the 6-wide output layer) stay on CUDA cores
     if (use_tc && a.M >= 64 && (long)a.M * a.N * a.K >= (1L << 22) && a.N >= 16 && tc_gemm(c, mode, a)) return;
