@@ -4,10 +4,6 @@
 #include <vector>
 #include "nn.cuh"
 #include "tc_gemm.cuh"
-#include "tc_gemm2.cuh"
-#include "tc_gemm3.cuh"
-#include "tc_gemm4.cuh"
-#include "tc_gemm5.cuh"
 
 namespace bb {
 
@@ -36,111 +32,13 @@ static void tc_launch(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t 
     BB_LAUNCHED();
 }
 
-template <int BN, int STAGES, int PF>
-static void tc_launch_persist(GemmMode mode, const GemmArgs& a, int tm, int tn, int total, int ctas, cudaStream_t s) {
-    constexpr size_t smem = (size_t)STAGES * (2 * tc::BM * 128 + 2 * BN * 128) + 1024;
-#define BB_TC_LAUNCH(AK, BK_, AU, BU)                                                                           \
-    do {                                                                                                        \
-        auto kern = tc_gemm_persist_kernel<BN, STAGES, PF, AK, BK_, AU, BU>;                                    \
-        static bool configured = false;                                                                         \
-        if (!configured) {                                                                                      \
-            BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-            configured = true;                                                                                  \
-        }                                                                                                       \
-        kern<<<ctas, tc2::NTHREADS, smem, s>>>(a, tm, tn, total);                                               \
-    } while (0)
-    switch (mode) {
-        case G_FWD: BB_TC_LAUNCH(true, true, false, false); break;
-        case G_FWD_U8: BB_TC_LAUNCH(true, true, true, false); break;
-        case G_NN: BB_TC_LAUNCH(true, false, false, false); break;
-        case G_WGRAD: BB_TC_LAUNCH(false, false, false, false); break;
-        case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true); break;
-        case G_WGRAD_AU8: BB_TC_LAUNCH(false, false, true, false); break;
-    }
-#undef BB_TC_LAUNCH
-    BB_LAUNCHED();
-}
-
-template <int BN>
-static void tc_launch_tmem(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
-    constexpr size_t smem = (size_t)tc3::STAGES * (2 * BN * 128) + 1024;
-#define BB_TC_LAUNCH(AK, BK_, AU, BU)                                                                           \
-    do {                                                                                                        \
-        auto kern = tc_gemm_tmem_kernel<BN, AK, BK_, AU, BU>;                                                   \
-        static bool configured = false;                                                                         \
-        if (!configured) {                                                                                      \
-            BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-            configured = true;                                                                                  \
-        }                                                                                                       \
-        kern<<<grid, tc3::NTHREADS, smem, s>>>(a);                                                              \
-    } while (0)
-    switch (mode) {
-        case G_FWD: BB_TC_LAUNCH(true, true, false, false); break;
-        case G_FWD_U8: BB_TC_LAUNCH(true, true, true, false); break;
-        case G_NN: BB_TC_LAUNCH(true, false, false, false); break;
-        case G_WGRAD: BB_TC_LAUNCH(false, false, false, false); break;
-        case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true); break;
-        case G_WGRAD_AU8: BB_TC_LAUNCH(false, false, true, false); break;
-    }
-#undef BB_TC_LAUNCH
-    BB_LAUNCHED();
-}
-
-template <int BN, int STAGES, int DEPTH, int MINB>
-static void tc_launch_async(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
-    constexpr int B_LD = (BN * 8 + tc::NPROD - 1) / tc::NPROD;
-    constexpr size_t smem = (size_t)STAGES * (2 * tc::BM * 128 + 2 * BN * 128) + (size_t)DEPTH * (4 + B_LD) * tc::NPROD * 16 + 1024;
-#define BB_TC_LAUNCH(AK, BK_, AU, BU)                                                                           \
-    do {                                                                                                        \
-        auto kern = tc_gemm_async_kernel<BN, STAGES, DEPTH, MINB, AK, BK_, AU, BU>;                             \
-        static bool configured = false;                                                                         \
-        if (!configured) {                                                                                      \
-            BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-            configured = true;                                                                                  \
-        }                                                                                                       \
-        kern<<<grid, tc::NTHREADS, smem, s>>>(a);                                                               \
-    } while (0)
-    switch (mode) {
-        case G_FWD: BB_TC_LAUNCH(true, true, false, false); break;
-        case G_FWD_U8: BB_TC_LAUNCH(true, true, true, false); break;
-        case G_NN: BB_TC_LAUNCH(true, false, false, false); break;
-        case G_WGRAD: BB_TC_LAUNCH(false, false, false, false); break;
-        case G_WGRAD_U8: BB_TC_LAUNCH(false, false, false, true); break;
-        case G_WGRAD_AU8: BB_TC_LAUNCH(false, false, true, false); break;
-    }
-#undef BB_TC_LAUNCH
-    BB_LAUNCHED();
-}
-
-template <int BN, int S, int RD, int MINB>
-static bool tc_launch_ta(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t s) {
-    constexpr size_t smem = tc5::smem_bytes(BN, S, RD);
-#define BB_TC_LAUNCH(AK, BK_, AU)                                                                               \
-    do {                                                                                                        \
-        auto kern = tc_gemm_ta_kernel<BN, S, RD, MINB, AK, BK_, AU>;                                            \
-        static bool configured = false;                                                                         \
-        if (!configured) {                                                                                      \
-            BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-            configured = true;                                                                                  \
-        }                                                                                                       \
-        kern<<<grid, tc5::NTHREADS, smem, s>>>(a);                                                              \
-    } while (0)
-    switch (mode) {
-        case G_FWD: BB_TC_LAUNCH(true, true, false); break;
-        case G_FWD_U8: BB_TC_LAUNCH(true, true, true); break;
-        case G_NN: BB_TC_LAUNCH(true, false, false); break;
-        case G_WGRAD: BB_TC_LAUNCH(false, false, false); break;
-        default: return false;
-    }
-#undef BB_TC_LAUNCH
-    BB_LAUNCHED();
-    return true;
-}
-
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                      int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask);
 __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                       int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask);
+
+bool tc_gemm_variant(const Ctx& c, int cfg2, int avar, GemmMode mode, const GemmArgs& a, dim3 grid, int BN, int tm, int tn,
+                     int split, bool v1_only, bool mapped_out, const char** tag);  // tc_gemm_variants.cu
 
 bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     static const int fill_pct = getenv("BB_TC_FILL") ? atoi(getenv("BB_TC_FILL")) : 100;  // target CTAs, % of SMs
@@ -179,31 +77,10 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     dim3 grid(tn, tm, split);
     const bool v1_only = a.trans_out || mode == G_WGRAD_AU8 || mapped_out;  // transposed store / u8 m-contiguous A live in tc_gemm.cuh
     static const int avar = getenv("BB_TC_ASYNC") ? atoi(getenv("BB_TC_ASYNC")) : 0;
-    bool ta_done = false;
-    if (cfg2 == 6 && !mapped_out) {  // A in tensor memory + cp.async staging (tc_gemm5.cuh)
-        if (avar == 0) ta_done = BN == 32 ? tc_launch_ta<32, 3, 1, 2>(mode, a, grid, c.stream) : tc_launch_ta<64, 3, 1, 2>(mode, a, grid, c.stream);
-        else ta_done = BN == 32 ? tc_launch_ta<32, 6, 2, 1>(mode, a, grid, c.stream) : tc_launch_ta<64, 6, 2, 1>(mode, a, grid, c.stream);
-    }
-    if (ta_done) {
-    } else if (cfg2 == 5 && !mapped_out) {  // cp.async operand pipeline (tc_gemm4.cuh)
-        if (avar == 0) {
-            if (BN == 32) tc_launch_async<32, 2, 4, 1>(mode, a, grid, c.stream);
-            else tc_launch_async<64, 2, 4, 1>(mode, a, grid, c.stream);
-        } else if (avar == 1) {
-            if (BN == 32) tc_launch_async<32, 1, 2, 2>(mode, a, grid, c.stream);
-            else tc_launch_async<64, 1, 2, 2>(mode, a, grid, c.stream);
-        } else {
-            if (BN == 32) tc_launch_async<32, 2, 3, 1>(mode, a, grid, c.stream);
-            else tc_launch_async<64, 2, 3, 1>(mode, a, grid, c.stream);
-        }
-    } else if (cfg2 == 4 && !v1_only) {  // A operand in tensor memory (tc_gemm3.cuh)
-        if (BN == 32) tc_launch_tmem<32>(mode, a, grid, c.stream);
-        else tc_launch_tmem<64>(mode, a, grid, c.stream);
-    } else if (cfg2 == 3 && !v1_only) {  // persistent, flat-pipelined kernel (tc_gemm2.cuh)
-        int total = tm * tn * split;
-        int ctas = std::min(total, c.sms);
-        if (BN == 32) tc_launch_persist<32, 4, 3>(mode, a, tm, tn, total, ctas, c.stream);
-        else tc_launch_persist<64, 4, 3>(mode, a, tm, tn, total, ctas, c.stream);
+    // experimental variants (BB_TC_CFG 3..6: persistent, A in tensor memory, cp.async ring, both) live in their own
+    // translation unit (tc_gemm_variants.cu); all measured slower than the default kernel on B200
+    const char* vtag = nullptr;
+    if (cfg2 >= 3 && cfg2 <= 6 && tc_gemm_variant(c, cfg2, avar, mode, a, grid, BN, tm, tn, split, v1_only, mapped_out, &vtag)) {
     } else if (cfg2 >= 1) {
         // branch-free producer loads when every tile and k-slice is whole and every 4-group is 16-byte aligned
         static const int fast_env = getenv("BB_TC_FAST") ? atoi(getenv("BB_TC_FAST")) : 1;
@@ -223,7 +100,7 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
             default: tc_launch<128, 3, 3, 1>(mode, a, grid, c.stream); break;
         }
     }
-    c.mark(ta_done ? (BN == 32 ? "tc_ta128x32" : "tc_ta128x64") : cfg2 == 5 ? (BN == 32 ? "tc_async128x32" : "tc_async128x64") : cfg2 == 4 ? (BN == 32 ? "tc_tmem128x32" : "tc_tmem128x64") : cfg2 == 3 ? (BN == 32 ? "tc_persist128x32" : "tc_persist128x64") : (BN == 32 ? "tc_gemm128x32" : (BN == 64 ? "tc_gemm128x64" : "tc_gemm128x128")));
+    c.mark(vtag ? vtag : (BN == 32 ? "tc_gemm128x32" : (BN == 64 ? "tc_gemm128x64" : "tc_gemm128x128")));
     if (split > 1) {
         size_t total = (size_t)a.M * a.N;
         const int rows = a.trans_out ? a.N : a.M, cols = a.trans_out ? a.M : a.N;  // layout of the partials = layout of C

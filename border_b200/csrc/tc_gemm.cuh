@@ -28,7 +28,7 @@ namespace bb {
 
 static __device__ int g_tc_error = 0;  // per translation unit (tc_gemm.cu reads its own copy)
 // debug trace (BB_TC_DEBUG bit 16): clock64 stamps of CTA (0,0,0)'s producer thread 0 and MMA thread
-__device__ long long g_tc_trace[2][64][8];
+static __device__ long long g_tc_trace[2][64][8];  // per translation unit
 
 namespace tc {
 

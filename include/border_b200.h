@@ -72,6 +72,8 @@ int32_t bb_bench_conv1(int32_t device, int32_t B, int32_t C, int32_t iters, floa
 
 /* Debug hook: clock64 stamps [2 roles][64 k-slices][4 points] of the last traced tcgen05 launch. */
 int32_t bb_debug_tc_trace(int64_t* out);
+/* the same for the experimental kernel variants (BB_TC_CFG 3..6, tc_gemm_variants.cu) */
+int32_t bb_debug_tc_trace_variants(int64_t* out);
 
 /* ------------------------------------------------------------------------------------------
  * Replay buffer: SimpleReplayBuffer<O, A> (border-core/src/generic_replay_buffer/base.rs:86-426)

@@ -9,7 +9,7 @@ mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 ms = C.c_float()
 L.check(lib.bb_bench_gemm(0, mode, 1, M, N, K, 3, C.byref(ms)))
 t = np.zeros((2, 64, 8), np.int64)
-L.check(lib.bb_debug_tc_trace(t.ctypes.data))
+L.check(lib.bb_debug_tc_trace_variants(t.ctypes.data))
 t0 = t[t > 0].min()
 print("env", {k: v for k, v in os.environ.items() if k.startswith("BB_")}, "ms", ms.value)
 print("prod order: pre_wait after_cpwait after_empty after_A after_B after_issue after_waitst after_arrive\nks | prod: pre_wait after_cpwait after_empty after_arrive | mma: pre_full after_full after_fence after_commit")
