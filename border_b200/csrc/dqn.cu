@@ -227,6 +227,8 @@ struct Dqn : Agent {
         if (conc) ctx.fork_to(rctx);
         BB_CUDA(cudaMemcpyAsync(h_rec, d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, rctx.stream));
         BB_CUDA(cudaEventRecordWithFlags(ev_rec, rctx.stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+        ctx.layer = "record";
+        ctx.mark("d2h_32B");  // (profiled runs are serial: without its own mark the copy's latency lands on the next kernel)
         ctx.phase = "backward";
         // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
         net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0);

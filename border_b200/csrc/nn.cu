@@ -146,34 +146,36 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
                                                            int ldc) {
     pdl_sync();
     __shared__ float part[8][16][33];
+    __shared__ float sa[256][16];   // one 256-row slab of A (the skinny operand), reused by all 32 columns
     const int col = threadIdx.x & 31, kg = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + col;
     float acc[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) acc[m] = 0.f;
-    if (n < N) {
-        // four k per trip: the loads of a trip are independent, so 4 x (1 + M) of them are in flight (the plain loop was
-        // one load latency per k: 20 us for 6 x 512 x 256)
-        int k = kg;
-        for (; k + 24 < K; k += 32) {
-            float b[4];
+    for (int k0 = 0; k0 < K; k0 += 256) {
+        const int kn = min(256, K - k0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kn * M; i += 256) sa[i / M][i % M] = A[(size_t)(k0 + i / M) * lda + i % M];
+        __syncthreads();
+        if (n < N) {
+            // eight k per trip: the B loads of a trip are independent (the plain loop paid one load latency per k)
+            int k = kg;
+            for (; k + 56 < kn; k += 64) {
+                float b[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) b[u] = B[(size_t)(k + 8 * u) * ldb + n];
+                for (int u = 0; u < 8; ++u) b[u] = B[(size_t)(k0 + k + 8 * u) * ldb + n];
 #pragma unroll
-            for (int m = 0; m < 16; ++m)
-                if (m < M) {
-                    float a[4];
+                for (int u = 0; u < 8; ++u)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) a[u] = A[(size_t)(k + 8 * u) * lda + m];
+                    for (int m = 0; m < 16; ++m)
+                        if (m < M) acc[m] = fmaf(sa[k + 8 * u][m], b[u], acc[m]);
+            }
+            for (; k < kn; k += 8) {
+                const float b = B[(size_t)(k0 + k) * ldb + n];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) acc[m] = fmaf(a[u], b[u], acc[m]);
-                }
-        }
-        for (; k < K; k += 8) {
-            const float b = B[(size_t)k * ldb + n];
-#pragma unroll
-            for (int m = 0; m < 16; ++m)
-                if (m < M) acc[m] = fmaf(A[(size_t)k * lda + m], b, acc[m]);
+                for (int m = 0; m < 16; ++m)
+                    if (m < M) acc[m] = fmaf(sa[k][m], b, acc[m]);
+            }
         }
     }
 #pragma unroll
