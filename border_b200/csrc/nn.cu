@@ -49,29 +49,41 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
     }
 }
 
-// Many splits of a small tile (weight gradients): 8 lanes per output element, lane g sums splits
-// g, g+8, ... then a fixed-order shuffle tree (deterministic; keeps many loads in flight).
+// Many splits of a small tile (weight gradients): a CTA takes 32 consecutive output elements x 8 split groups; warp g
+// sums splits g, g+8, ... of its 32 elements (coalesced 128-byte loads, four independent partial sums in flight), the
+// eight group sums are folded in group order through shared memory (deterministic).
 __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                       int splits, const float* __restrict__ bias, int relu,
                                       const float* __restrict__ mask) {
     pdl_sync();
-    size_t total = (size_t)M * N;
-    const int g = threadIdx.x & 7;
-    for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3; i < ((total + 31) & ~(size_t)31);
-         i += ((size_t)gridDim.x * blockDim.x) >> 3) {
+    __shared__ float part[8][33];
+    const size_t total = (size_t)M * N;
+    const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+    for (size_t c0 = (size_t)blockIdx.x * 32; c0 < total; c0 += (size_t)gridDim.x * 32) {
+        const size_t i = c0 + e;
         const bool ok = i < total;
-        float s = 0.f;
-        if (ok)
-            for (int z = g; z < splits; z += 8) s += ws[(size_t)z * total + i];
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (!ok || g != 0) continue;
-        int m = (int)(i / N), n = (int)(i % N);
-        if (bias) s += bias[n];
-        if (relu) s = fmaxf(s, 0.f);
-        if (mask) s = mask[(size_t)m * ldc + n] > 0.f ? s : 0.f;
-        C[(size_t)m * ldc + n] = s;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (ok) {
+            int z = g;
+            for (; z + 24 < splits; z += 32) {
+                a0 += ws[(size_t)z * total + i]; a1 += ws[(size_t)(z + 8) * total + i];
+                a2 += ws[(size_t)(z + 16) * total + i]; a3 += ws[(size_t)(z + 24) * total + i];
+            }
+            for (; z < splits; z += 8) a0 += ws[(size_t)z * total + i];
+        }
+        __syncthreads();  // the previous chunk's readers are done with `part`
+        part[g][e] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (g == 0 && ok) {
+            float s = part[0][e];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) s += part[k][e];
+            int m = (int)(i / N), n = (int)(i % N);
+            if (bias) s += bias[n];
+            if (relu) s = fmaxf(s, 0.f);
+            if (mask) s = mask[(size_t)m * ldc + n] > 0.f ? s : 0.f;
+            C[(size_t)m * ldc + n] = s;
+        }
     }
 }
 
@@ -333,8 +345,18 @@ __global__ void colsum_fused_kernel(const float* __restrict__ Y, float* __restri
     int n = blockIdx.x * 32 + threadIdx.x;
     int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
     float acc = 0.f;
-    if (n < N)
-        for (int m = r0 + threadIdx.y; m < r1; m += 8) acc += Y[(size_t)m * N + n];
+    if (n < N) {
+        // four independent partial sums: four loads in flight per thread (the single chain paid one load latency per row:
+        // 22 us for the 102400 x 32 conv1 bias gradient)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int m = r0 + threadIdx.y;
+        for (; m + 24 < r1; m += 32) {
+            a0 += Y[(size_t)m * N + n]; a1 += Y[(size_t)(m + 8) * N + n];
+            a2 += Y[(size_t)(m + 16) * N + n]; a3 += Y[(size_t)(m + 24) * N + n];
+        }
+        for (; m < r1; m += 8) a0 += Y[(size_t)m * N + n];
+        acc = (a0 + a1) + (a2 + a3);
+    }
     s[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.y == 0 && n < N) {
