@@ -155,7 +155,9 @@ extern "C" int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, in
     else if (mode == 2) { gm = G_NN; a.lda = K; a.ldb = N; }
     else if (mode == 3) { gm = G_WGRAD; a.lda = M; a.ldb = N; }
     else throw Error("bb_test_gemm: mode must be 0, 2 or 3");
-    if (use_tc) {
+    if (use_tc == 2) {
+        gemm(c, gm, a);  // the dispatcher the layers use: skinny kernels, tcgen05 tiles or CUDA-core tiles by shape
+    } else if (use_tc) {
         tc_gemm(c, gm, a);
     } else {
         gemm_simt(c, gm, a);

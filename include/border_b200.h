@@ -56,8 +56,8 @@ int32_t bb_device_count(int32_t* out);
 /* glibc powf restated on the device (sum_tree.rs:76,96,134,139 use f32::powf); test hook. */
 int32_t bb_test_powf(int32_t device, const float* host_x, const float* host_y, float* host_out, size_t n);
 
-/* Test hook: one dense GEMM on the device through the tcgen05 path (use_tc = 1) or the fp32
- * CUDA-core path (0).  mode 0: C = A[M][K] B[N][K]^T (+bias, relu); 2: C = A[M][K] B[K][N];
+/* Test hook: one dense GEMM on the device through the tcgen05 path (use_tc = 1), the fp32
+ * CUDA-core path (0) or the shape dispatcher the layers use (2: skinny kernels / tcgen05 / CUDA-core tiles).  mode 0: C = A[M][K] B[N][K]^T (+bias, relu); 2: C = A[M][K] B[K][N];
  * 3: C = A[K][M]^T B[K][N].  All pointers are host memory. */
 int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, int32_t N, int32_t K,
                      const float* A, const float* B, const float* bias, int32_t relu, float* C_out);

@@ -80,3 +80,30 @@ def test_dqn_parity_holds_with_both_conv_data_gradient_forms(monkeypatch, gather
     from tests.test_dqn_gpu import _run
     _run("cnn", 32, "Mse", False, per=False, clip=False, steps=3, lr=1e-4)
     _run("cnn", 256, "SmoothL1", True, per=False, clip=False, steps=1, lr=1e-4)
+
+
+# (mode, M, N, K): skinny contractions (one dimension <= 16: warp / thread per output element), ragged column counts,
+# k not a multiple of the unroll, and split-K-heavy shapes that end in the coalesced reduce kernels
+DISPATCH_SHAPES = [(0, 256, 6, 512), (0, 512, 1, 256), (0, 300, 16, 100), (0, 1, 6, 512), (0, 37, 3, 33),
+                   (2, 256, 512, 6), (2, 512, 256, 1), (2, 77, 50, 16),
+                   (3, 6, 512, 256), (3, 1, 256, 512), (3, 16, 70, 300), (3, 5, 33, 1000),
+                   (3, 64, 100, 20000), (3, 32, 256, 40000), (0, 40, 48, 9000)]
+
+
+@pytest.mark.parametrize("case", DISPATCH_SHAPES)
+def test_layer_gemm_dispatcher_matches_float64(case):
+    mode, M, N, K = case
+    rng = np.random.default_rng(M * 131 + N * 17 + K + mode)
+    if mode == 0:
+        A, B = rng.standard_normal((M, K)), rng.standard_normal((N, K))
+    elif mode == 2:
+        A, B = rng.standard_normal((M, K)), rng.standard_normal((K, N))
+    else:
+        A, B = rng.standard_normal((K, M)), rng.standard_normal((K, N))
+    A, B = A.astype(np.float32), B.astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32) if mode == 0 else None
+    relu = 1 if mode == 0 and K % 2 == 0 else 0
+    ref = _ref(mode, A, B, bias, relu)
+    got = _run(mode, 2, A, B, M, N, K, bias, relu)
+    mag = np.abs(ref).max() + 1.0
+    assert np.abs(got - ref).max() <= 1.2e-5 * mag * max(1.0, (K / 4096.0) ** 0.5), (np.abs(got - ref).max(), mag)
