@@ -151,16 +151,17 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
         C[(size_t)m * ldc + n] = acc;
     }
 }
-// weight gradient: C[m][n] = sum_k A[k*lda+m] B[k*ldb+n], M <= 16: 32 columns x 8 k-groups per CTA, partial sums
-// folded in shared memory in k-group order (deterministic)
+// weight gradient: C[m][n] = sum_k A[k*lda+m] B[k*ldb+n], M <= 16: 8 columns x 32 k-groups per CTA (N/8 CTAs: with 32
+// columns per CTA a 256-wide layer kept only 8 SMs busy, 18-23 us), the skinny operand staged in shared memory, partial
+// sums folded in k-group order (deterministic)
 __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                            float* __restrict__ C, int M, int N, int K, long lda, long ldb,
                                                            int ldc) {
     pdl_sync();
-    __shared__ float part[8][16][33];
-    __shared__ float sa[256][16];   // one 256-row slab of A (the skinny operand), reused by all 32 columns
-    const int col = threadIdx.x & 31, kg = threadIdx.x >> 5;
-    const int n = blockIdx.x * 32 + col;
+    __shared__ float part[32][16][9];
+    __shared__ float sa[256][16];   // one 256-row slab of A, reused by all 8 columns
+    const int col = threadIdx.x & 7, kg = threadIdx.x >> 3;
+    const int n = blockIdx.x * 8 + col;
     float acc[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) acc[m] = 0.f;
@@ -170,35 +171,28 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
         for (int i = threadIdx.x; i < kn * M; i += 256) sa[i / M][i % M] = A[(size_t)(k0 + i / M) * lda + i % M];
         __syncthreads();
         if (n < N) {
-            // eight k per trip: the B loads of a trip are independent (the plain loop paid one load latency per k)
-            int k = kg;
-            for (; k + 56 < kn; k += 64) {
-                float b[8];
+            // all (up to 8) k of this thread in one trip: independent loads in flight
+            float b[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) b[u] = B[(size_t)(k0 + k + 8 * u) * ldb + n];
+            for (int u = 0; u < 8; ++u) b[u] = (kg + 32 * u < kn) ? B[(size_t)(k0 + kg + 32 * u) * ldb + n] : 0.f;
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < 8; ++u)
+                if (kg + 32 * u < kn) {
 #pragma unroll
                     for (int m = 0; m < 16; ++m)
-                        if (m < M) acc[m] = fmaf(sa[k + 8 * u][m], b[u], acc[m]);
-            }
-            for (; k < kn; k += 8) {
-                const float b = B[(size_t)(k0 + k) * ldb + n];
-#pragma unroll
-                for (int m = 0; m < 16; ++m)
-                    if (m < M) acc[m] = fmaf(sa[k][m], b, acc[m]);
-            }
+                        if (m < M) acc[m] = fmaf(sa[kg + 32 * u][m], b[u], acc[m]);
+                }
         }
     }
 #pragma unroll
     for (int m = 0; m < 16; ++m) part[kg][m][col] = acc[m];
     __syncthreads();
-    // thread (col, kg) finishes rows m = kg, kg + 8
-    for (int m = kg; m < M; m += 8) {
+    // thread (col, kg) finishes row m = kg
+    if (kg < M && n < N) {
         float t = 0.f;
 #pragma unroll
-        for (int g2 = 0; g2 < 8; ++g2) t += part[g2][m][col];
-        if (n < N) C[(size_t)m * ldc + n] = t;
+        for (int g2 = 0; g2 < 32; ++g2) t += part[g2][kg][col];
+        C[(size_t)kg * ldc + n] = t;
     }
 }
 
@@ -226,7 +220,7 @@ static bool gemm_skinny(const Ctx& c, GemmMode mode, const GemmArgs& a) {
         return true;
     }
     if (mode == G_WGRAD && a.M <= 16 && !a.bias && !a.relu && !a.mask) {
-        launch_pdl(skinny_wgrad_kernel, dim3((a.N + 31) / 32), dim3(256), 0, c.stream, A, B, a.C, a.M, a.N, a.K, a.lda, a.ldb,
+        launch_pdl(skinny_wgrad_kernel, dim3((a.N + 7) / 8), dim3(256), 0, c.stream, A, B, a.C, a.M, a.N, a.K, a.lda, a.ldb,
                    a.ldc);
         BB_LAUNCHED();
         c.mark("skinny_wgrad");
