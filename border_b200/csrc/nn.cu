@@ -219,7 +219,8 @@ static bool gemm_skinny(const Ctx& c, GemmMode mode, const GemmArgs& a) {
         c.mark("skinny_dgrad");
         return true;
     }
-    if (mode == G_WGRAD && a.M <= 16 && !a.bias && !a.relu && !a.mask) {
+    // (short contractions only: each CTA walks all of K; IQN's 4 x 512 x 16384 took 486 us here against 25 + 8 us as split-K tiles)
+    if (mode == G_WGRAD && a.M <= 16 && a.K <= 2048 && !a.bias && !a.relu && !a.mask) {
         launch_pdl(skinny_wgrad_kernel, dim3((a.N + 7) / 8), dim3(256), 0, c.stream, A, B, a.C, a.M, a.N, a.K, a.lda, a.ldb,
                    a.ldc);
         BB_LAUNCHED();
