@@ -288,7 +288,7 @@ def run_b200(args):
         for k, v in run:
             agg[k] = agg.get(k, 0.0) + v / len(prof_runs)
     step_ms_prof = sum(agg.values())
-    # dominant kernel = tc_gemm_kernel (tc_gemm.cuh), 13 launches per step (c2/c3/l1 x {forward of both nets, data
+    # dominant kernel = tc_gemm_kernel (tc_gemm.cuh), 12 launches per step (c2/c3/l1 x {forward of both nets, data
     # gradient, weight gradient}): achieved = their algorithmic FLOPs / their device time, per launch = the averages.
     # The slowest and fastest single launches are reported beside it.  (At N>1 the profiled Adam also absorbs the ranks'
     # skew in its peer barrier, which is waiting, not work.)
