@@ -212,3 +212,32 @@ def test_full_size_ring_properties():
     assert np.array_equal(b1.act, b2.act) and set(np.unique(b1.act)) <= set(range(6))
     # next_obs of row r is obs of row r+1 unless terminated (SURVEY 8d synthetic contract)
     assert b1.obs.dtype == np.uint8 and 100 < b1.obs.mean() < 155
+
+
+@pytest.mark.parametrize("capacity,n,distinct", [(1000, 1024, 7), (1024, 1024, 1), (37, 300, 37), (4099, 1500, 50),
+                                                 (4096, 2500, 4096), (1000, 1, 1)])
+def test_update_priority_large_batches_and_heavy_duplicates_bit_exact(capacity, n, distinct):
+    """SumTree::update in batch order (sum_tree.rs:93-107) on the device is a stable per-depth partition + parallel
+    run folds: whole-tree bit equality with the sequential oracle for batches up to several 1024-chunks, all-equal
+    indices, non-2^k capacities and a pushed ring (max-priority drift included)."""
+    per = dict(alpha=0.6, beta_0=0.4, beta_final=1.0, n_opts_final=30, normalize="All")
+    dev, orc = _pair(capacity, 7, (4,), np.float32, (1,), np.int64, per=per)
+    rng = np.random.default_rng(capacity * 13 + n)
+    tr = _tr(rng, capacity, (4,), np.float32, (1,), np.int64)
+    dev.push(tr)
+    orc.push(*tr.unpack()[:6])
+    pool = rng.choice(capacity, size=min(distinct, capacity), replace=False)
+    for k in range(3):
+        ix = rng.choice(pool, size=n).astype(np.uint64)
+        td = (rng.random(n) * (10.0 ** rng.integers(-3, 3))).astype(np.float32)
+        dev.update_priority(ix, td)
+        orc.update_priority(ix, td)
+        t_dev, _, no = dev.dump_sum_tree()
+        t_orc, _ = orc.sum_tree()
+        assert np.array_equal(t_dev.view(np.uint32), t_orc.view(np.uint32)), (k, capacity, n, distinct)
+        assert no == k + 1
+    # a push after the updates re-derives the max priority from the max tree (sum_tree.rs:73-77)
+    tr2 = _tr(rng, 5, (4,), np.float32, (1,), np.int64)
+    dev.push(tr2)
+    orc.push(*tr2.unpack()[:6])
+    assert np.array_equal(dev.dump_sum_tree()[0].view(np.uint32), orc.sum_tree()[0].view(np.uint32))
