@@ -45,7 +45,53 @@ def run_per_trace(normalize, capacity=1000, pushes=1500, rounds=40, batch=64):
     return out
 
 
+def dqn_mlp_setup():
+    """The fixed DQN-MLP case of the agent fixture: parameters, ring contents and the oracle agent (seeds only)."""
+    import torch
+    from oracle import agent_oracle as ao
+    rng = np.random.default_rng(7)
+    gen = torch.Generator().manual_seed(0)
+    params = ao.mlp_params(4, [64, 64], 2, gen)
+    n, cap = 280, 300
+    obs = rng.standard_normal((n, 4)).astype(np.float32)
+    nxt = rng.standard_normal((n, 4)).astype(np.float32)
+    act = rng.integers(0, 2, (n, 1)).astype(np.int64)
+    reward = rng.standard_normal(n).astype(np.float32)
+    term = (rng.random(n) < 0.2).astype(np.int8)
+    trunc = np.zeros(n, np.int8)
+    return params, (obs, act, nxt, reward, term, trunc), cap
+
+
+def run_dqn_mlp_trace(steps=5, B=32, lr=1e-3):
+    """DQN (dqn/base.rs:60-200) on an Mlp[64,64] Q net: SmoothL1, double DQN, soft update every 2 opts with tau 0.5,
+    uniform replay seed 42 -- losses, sampled indices and the parameters after `steps` updates."""
+    import torch
+    from oracle import agent_oracle as ao
+    params, tr, cap = dqn_mlp_setup()
+    orc = ro.ReplayOracle(cap, 42, (4,), np.float32, (1,), np.int64)
+    orc.push(*tr)
+    oracle = ao.DqnOracle(params, lambda p, x: ao.mlp_forward(p, x, 3), lr, B, 0.99, 0.5, 2, 1, True, None, "SmoothL1")
+    losses, ixs = [], []
+
+    def sample():
+        b = orc.batch(B)
+        ixs.append(np.asarray(b["ix_sample"], dtype=np.uint64))
+        return dict(obs=torch.from_numpy(b["obs"]), act=torch.from_numpy(b["act"]), next_obs=torch.from_numpy(b["next_obs"]),
+                    reward=torch.from_numpy(b["reward"]), is_terminated=torch.from_numpy(b["is_terminated"]),
+                    ix_sample=b["ix_sample"])
+
+    for _ in range(steps):
+        losses.append(oracle.opt_(sample))
+    out = {"losses": np.asarray(losses, np.float64), "ixs": np.stack(ixs)}
+    for k, v in oracle.qnet.items():
+        out["qnet." + k] = v.detach().numpy().copy()
+    for k, v in oracle.qnet_tgt.items():
+        out["qnet_tgt." + k] = v.detach().numpy().copy()
+    return out
+
+
 def main():
+    np.savez_compressed(os.path.join(HERE, "dqn_mlp_trace.npz"), **run_dqn_mlp_trace())
     r = ro.StdRng(42)
     json.dump({"seed": 42, "words": [r.next_u32() for _ in range(64)]},
               open(os.path.join(HERE, "stdrng_seed42.json"), "w"))
