@@ -41,7 +41,9 @@ bool tc_gemm_variant(const Ctx& c, int cfg2, int avar, GemmMode mode, const Gemm
                      int split, bool v1_only, bool mapped_out, const char** tag);  // tc_gemm_variants.cu
 
 bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
-    static const int fill_pct = getenv("BB_TC_FILL") ? atoi(getenv("BB_TC_FILL")) : 100;  // target CTAs, % of SMs
+    // target CTAs of a split-K launch, % of SMs.  A/B on the DQN step (us): 40: 361.5, 50: 357.2, 60: 350.2, 75: 349.1,
+    // 100: 354.7, 150: 368.4 -- the split launches share the GPU with the other streams' kernels
+    static const int fill_pct = getenv("BB_TC_FILL") ? atoi(getenv("BB_TC_FILL")) : 75;
     // 0: 3 stages, 1 CTA/SM; 1: two CTAs/SM for BN <= 64; 2 (default, fastest on B200): BN <= 64 always, two
     // CTAs/SM; 3: persistent flat-pipelined kernel (tc_gemm2.cuh)
     static const int cfg2 = getenv("BB_TC_CFG") ? atoi(getenv("BB_TC_CFG")) : 2;
