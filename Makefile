@@ -5,8 +5,8 @@ NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
 CSRC      := border_b200/csrc
 OBJDIR    := build/obj
 LIB       := border_b200/libborder_b200.so
-SRCS      := common.cu replay.cu nn.cu agent.cu dqn.cu sac.cu iqn.cu tc_gemm.cu tc_gemm_variants.cu conv1_tc.cu
-SRCS      := $(filter $(notdir $(wildcard $(CSRC)/*.cu)),$(SRCS)) $(if $(wildcard $(CSRC)/sac.cu),,stubs.cu)
+SRCS      := common.cu replay.cu nn.cu agent.cu dqn.cu sac.cu iqn.cu tc_gemm.cu tma_gemm.cu conv1_tc.cu
+SRCS      := $(filter $(notdir $(wildcard $(CSRC)/*.cu)),$(SRCS))
 OBJS      := $(patsubst %.cu,$(OBJDIR)/%.o,$(SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.inc) include/border_b200.h
 

@@ -93,9 +93,9 @@ _SIGS = {
     "bb_test_powf": (C.c_int32, [C.c_int32, _P, _P, _P, C.c_size_t]),
     "bb_test_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P,
                                  C.c_int32, _P]),
+    "bb_tma_stats": (C.c_int32, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int32]),
     "bb_bench_gemm": (C.c_int32, [C.c_int32] * 7 + [C.POINTER(C.c_float)]),
     "bb_debug_tc_trace": (C.c_int32, [_P]),
-    "bb_debug_tc_trace_variants": (C.c_int32, [_P]),
     "bb_bench_conv1": (C.c_int32, [C.c_int32] * 4 + [C.POINTER(C.c_float)]),
     "bb_replay_cfg_default": (None, [C.POINTER(bb_replay_cfg)]),
     "bb_replay_create": (C.c_int32, [C.POINTER(bb_replay_cfg), C.POINTER(_P)]),

@@ -14,7 +14,7 @@ namespace bb {
 
 void Model::alloc(bool with_opt) {
     has_opt = with_opt;
-    p = dev_alloc_zero<float>(n);
+    p = dev_alloc_zero<float>(2 * n);  // parameters + their lo plane
     if (with_opt) {
         g = dev_alloc_zero<float>(n);
         m = dev_alloc_zero<float>(n);
@@ -40,8 +40,9 @@ const ParamInfo* Model::find(const std::string& nm) const {
 }
 void Model::copy_params_from(const Model& src, cudaStream_t s) {
     BB_CHECK(src.n == n, "VarStore size mismatch");
-    BB_CUDA(cudaMemcpyAsync(p, src.p, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    BB_CUDA(cudaMemcpyAsync(p, src.p, 2 * n * sizeof(float), cudaMemcpyDeviceToDevice, s));  // both planes
 }
+void Model::refresh_lo(const Ctx& c) { make_lo(c, p, p_lo(), n); }
 
 // ------------------------------------------------------------------------------- Agent base
 
@@ -54,8 +55,7 @@ void Agent::init_base(int dev) {
     ctx.device = dev;
     ctx.sms = num_sms(dev);
     ctx.stream = device_stream(dev);
-    ctx.ws_floats = 8u << 20;  // 32 MB split-K / reduction workspace
-    ctx.ws = dev_alloc_zero<float>(ctx.ws_floats, ctx.stream);  // the tail holds colsum's block counters (must start at 0)
+    ctx.alloc_scratch(8u << 20);  // 32 MB split-K / reduction workspace
     BB_CUDA(cudaMallocHost(&h_scratch, 4096 * sizeof(float)));
     d_scratch = dev_alloc<float>(1 << 20);
     BB_CUDA(cudaEventCreateWithFlags(&ctx.ev, cudaEventDisableTiming));
@@ -64,8 +64,12 @@ void Agent::init_base(int dev) {
         Ctx& s = side_ctx[i];
         s.device = dev; s.sms = ctx.sms;
         BB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        s.ws_floats = ctx.ws_floats;
-        s.ws = dev_alloc_zero<float>(s.ws_floats, ctx.stream);
+        {
+            cudaStream_t own = s.stream;
+            s.stream = ctx.stream;  // zero on the main stream (synchronised below)
+            s.alloc_scratch(ctx.ws_floats);
+            s.stream = own;
+        }
         BB_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
         if (!serial) ctx.side[i] = &s;
     }
@@ -74,11 +78,11 @@ void Agent::init_base(int dev) {
 Agent::~Agent() {
     for (int i = 0; i < 2; ++i) {
         if (side_ctx[i].stream) { cudaStreamSynchronize(side_ctx[i].stream); cudaStreamDestroy(side_ctx[i].stream); }
-        cudaFree(side_ctx[i].ws);
+        side_ctx[i].free_scratch();
         if (side_ctx[i].ev) cudaEventDestroy(side_ctx[i].ev);
     }
     if (ctx.ev) cudaEventDestroy(ctx.ev);
-    cudaFree(ctx.ws);
+    ctx.free_scratch();
     cudaFree(d_scratch);
     cudaFree(my_flags);
     if (h_scratch) cudaFreeHost(h_scratch);
@@ -129,7 +133,7 @@ void Agent::grad_sync_end() {
 }
 void Agent::synced_adam(Model& m) {
     if (world <= 1) {
-        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1);
+        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1, m.p_lo());
         return;
     }
     const char* e = getenv("BB_GRAD_SYNC");
@@ -138,9 +142,9 @@ void Agent::synced_adam(Model& m) {
     if (sharded) {
         grad_reduce_scatter(ctx, peer_grad, m.n, rank, world);
         peer_barrier(this);  // every slice of the mean has landed in this rank's buffer (and nobody still reads the old one)
-        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1);
+        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1, m.p_lo());
     } else {
-        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, peer_grad, world);
+        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, peer_grad, world, m.p_lo());
         peer_barrier(this);  // everyone done reading before anyone overwrites
     }
 }
@@ -227,6 +231,7 @@ void Agent::load_params(const char* dir) {
         }
         if (!f) throw Error("read failed: " + path);
         BB_CUDA(cudaMemcpy(m->p, hp.data(), m->n * 4, cudaMemcpyHostToDevice));
+        m->refresh_lo(ctx);
         if (m->has_opt && has_opt) {
             BB_CUDA(cudaMemcpy(m->m, hm.data(), m->n * 4, cudaMemcpyHostToDevice));
             BB_CUDA(cudaMemcpy(m->v, hv.data(), m->n * 4, cudaMemcpyHostToDevice));
@@ -452,6 +457,7 @@ int32_t bb_agent_set_param(bb_agent* a, const char* model, const char* name, con
     bb::param_to_internal(*pi, host_in, tmp.data());
     BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
     BB_CUDA(cudaMemcpy(m->p + pi->offset, tmp.data(), pi->numel * 4, cudaMemcpyHostToDevice));
+    bb::make_lo(ag.ctx, m->p + pi->offset, m->p_lo() + pi->offset, pi->numel);
     BB_API_END
 }
 int32_t bb_agent_get_opt_state(bb_agent* a, const char* model, const char* name, float* host_m, float* host_v, size_t n,
@@ -511,6 +517,7 @@ int32_t bb_agent_sync_model(bb_agent* a, const float* host_in, size_t n) {
     }
     BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
     BB_CUDA(cudaMemcpy(m->p, h.data(), m->n * 4, cudaMemcpyHostToDevice));
+    m->refresh_lo(ag.ctx);
     BB_API_END
 }
 int32_t bb_agent_sync_model_from(bb_agent* dst, bb_agent* src) {

@@ -58,6 +58,11 @@ struct Model {
     std::vector<ParamInfo> params;
     size_t n = 0;  // floats (padded)
     float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+    // p is followed by its lo plane (p_lo()[i] = p[i] - tf32_trunc(p[i]), the second operand plane of the TMA-fed GEMMs):
+    // Adam and the Polyak update refresh it in the same kernel, host-side writers call refresh_lo()
+    float* p_lo() const { return p + n; }
+    long plane() const { return (long)n; }
+    void refresh_lo(const Ctx& c);
     uint64_t step = 0;
     AdamHyper hyper{};
     bool has_opt = true;

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <map>
 #include <mutex>
+#include <string.h>
 #include "../../include/border_b200.h"
 
 namespace bb {
@@ -11,6 +12,25 @@ std::string& last_error() {
 }
 void set_error(const std::string& msg) { last_error() = msg; }
 std::atomic<uint64_t> g_launch_count{0};
+
+int* device_error_flag() {
+    static int* flag = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!flag) {
+        BB_CUDA(cudaHostAlloc(&flag, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(flag, 0, 64);
+    }
+    return flag;
+}
+void check_device_error(const char* where) {
+    volatile int* f = device_error_flag();
+    if (*f != 0) {
+        char b[256];
+        snprintf(b, sizeof(b), "%s: a device-side bounded wait timed out (code %d): results of this handle are invalid", where, *f);
+        throw Error(b);
+    }
+}
 
 // ------------------------------------------------------------------------------- streams
 

@@ -124,6 +124,11 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     launch_pdl_if(pdl_enabled(), kern, grid, block, smem, s, std::forward<Args>(args)...);
 }
 
+// Sticky device-side failure flag (a bounded mbarrier / peer-barrier wait timed out): ONE int in pinned, mapped host
+// memory, so kernels store to it directly and every host entry point can test it without a copy or a sync.
+int* device_error_flag();
+void check_device_error(const char* where);  // throws bb::Error when the flag is set
+
 cudaStream_t device_stream(int device);  // one non-blocking stream per (host thread, device)
 void stream_wait(cudaStream_t waiter, cudaStream_t signaler);
 

@@ -28,7 +28,6 @@
 #include <vector>
 #include "nn.cuh"
 #include "tc_gemm.cuh"
-#include "tc_gemm3.cuh"
 
 namespace bb {
 static __device__ int g_tc_error_c1 = 0;
@@ -42,6 +41,7 @@ struct Args {
     const float* Wt;       // [32][C*64] (OIHW)
     const float* bias;     // [32]
     float* Y;              // [M][32] NHWC
+    long y_plane;          // != 0: also store lo(Y) = Y - tf32_trunc(Y) at Y + y_plane (operand plane of the next layer's TMA loads)
     const int* rowbase;    // [M]
     int M, C, HW, W, relu;
     int n_tiles;
@@ -195,6 +195,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv1_fwd_kernel(Args g) {
                     v.z = __uint_as_float(r[j + 2]) + bj.z; v.w = __uint_as_float(r[j + 3]) + bj.w;
                     if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     dst[j >> 2] = v;
+                    if (g.y_plane)
+                        reinterpret_cast<float4*>(g.Y + g.y_plane + (size_t)m * OC)[j >> 2] =
+                            make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                                        v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
                 }
             }
         }
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1_wgrad_kernel(Args g) {
 }  // namespace c1w
 
 __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
-                                      int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask);
+                                      int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask, long c_plane);
 
 // dW[32][64C] of the AtariCnn first layer; false => geometry not handled (generic path).
 bool conv1_wgrad_tc(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW) {
@@ -467,7 +471,7 @@ bool conv1_wgrad_tc(const Ctx& c, const ConvGeom& g, const float* dY, const void
     c.mark("tc_conv1_wgrad");
     const size_t total = (size_t)32 * K;
     const int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
-    launch_pdl(splitk_reduce8_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, dW, 32, K, K, ctas, nullptr, 0, nullptr);
+    launch_pdl(splitk_reduce8_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, dW, 32, K, K, ctas, nullptr, 0, nullptr, 0L);
     BB_LAUNCHED();
     c.mark("splitk_reduce");
     return true;
@@ -480,7 +484,7 @@ bool conv1_fwd_tc(const Ctx& c, const ConvGeom& g, const void* X, const float* W
     if (!on || !g.u8_chw || g.KH != 8 || g.KW != 8 || g.S != 4 || g.OC != 32 || g.C < 1 || g.C > 8 || (g.W & 3) || g.M() < 1024)
         return false;
     c1::Args a;
-    a.X = (const uint8_t*)X; a.Wt = W; a.bias = b; a.Y = Y; a.rowbase = g.rowbase; a.M = g.M(); a.C = g.C;
+    a.X = (const uint8_t*)X; a.Wt = W; a.bias = b; a.Y = Y; a.y_plane = g.y_plane; a.rowbase = g.rowbase; a.M = g.M(); a.C = g.C;
     a.HW = g.H * g.W; a.W = g.W; a.relu = relu ? 1 : 0; a.n_tiles = (a.M + 127) / 128;
     static const int dbg = getenv("BB_CONV1_DEBUG") ? atoi(getenv("BB_CONV1_DEBUG")) : 0;
     a.dbg = dbg;

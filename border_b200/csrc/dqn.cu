@@ -149,6 +149,7 @@ struct Dqn : Agent {
         // qnet_tgt = qnet.clone(): own VarStore AND own optimizer in the reference (never stepped)
         qnet_tgt.name = "qnet_tgt"; qnet_tgt.params = net.params; qnet_tgt.n = net.n_params; qnet_tgt.alloc(false);
         net.init_params(ctx, qnet.p, c.init_seed);
+        qnet.refresh_lo(ctx);
         qnet_tgt.copy_params_from(qnet, ctx.stream);
         models = {&qnet, &qnet_tgt};
         d_td = dev_alloc<float>(65536);
@@ -198,16 +199,16 @@ struct Dqn : Agent {
         const Ctx& tctx = conc ? *ctx.side[0] : ctx;
         if (conc) ctx.fork_to(tctx);
         ctx.phase = "fwd_online";
-        const float* q = net.forward(ctx, qnet.p, bv.obs, ld_in, B, ws_online);         // :71-74
+        const float* q = net.forward(ctx, qnet.p, bv.obs, ld_in, B, ws_online, qnet.plane());         // :71-74
         const float* q_next = nullptr;
         ctx.phase = "fwd_target";
         if (cfg.double_dqn) {                                                              // :93-99
             // online net on next_obs: borrow the target workspace first, keep its Q in d_scratch
-            const float* qn = net.forward(tctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt);
+            const float* qn = net.forward(tctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt, qnet.plane());
             BB_CUDA(cudaMemcpyAsync(d_scratch, qn, (size_t)B * net.out_dim * 4, cudaMemcpyDeviceToDevice, tctx.stream));
             q_next = d_scratch;
         }
-        const float* qt = net.forward(tctx, qnet_tgt.p, bv.next_obs, ld_in, B, ws_tgt);  // :100-103
+        const float* qt = net.forward(tctx, qnet_tgt.p, bv.next_obs, ld_in, B, ws_tgt, qnet_tgt.plane());  // :100-103
         if (conc) ctx.join_from(tctx);
         DqnLossParams lp;
         lp.q = q; lp.q_tgt = qt; lp.q_next = q_next; lp.act = (const long long*)bv.act;
@@ -231,7 +232,7 @@ struct Dqn : Agent {
         ctx.mark("d2h_32B");  // (profiled runs are serial: without its own mark the copy's latency lands on the next kernel)
         ctx.phase = "backward";
         // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
-        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0);
+        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0, qnet.plane());
         if (conc) ctx.join_from(rctx);  // (backward joins the side streams it used; this one may not be among them)
     }
 
@@ -320,7 +321,7 @@ struct Dqn : Agent {
         if (soft_update_counter == cfg.soft_update_interval) {
             soft_update_counter = 0;
             ctx.phase = "target_update";
-            track(ctx, qnet_tgt.p, qnet.p, qnet.n, cfg.tau);
+            track(ctx, qnet_tgt.p, qnet.p, qnet.n, cfg.tau, qnet_tgt.p_lo());
         }
         n_opts += 1;
         if (rec) rec->n_opts = n_opts;

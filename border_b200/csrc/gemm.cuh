@@ -24,6 +24,14 @@
 
 namespace bb {
 
+// An NHWC float tensor walked as the implicit-GEMM operand of a convolution by TMA im2col loads (tma_gemm.cu):
+// rows = filter positions (n, oh, ow), columns = (kh, kw, c).
+struct TmaConv {
+    int N, H, W, C;   // tensor dims
+    int KH, KW, S;    // filter taps and traversal stride
+    int flip;         // 1: tap offsets run backwards (transposed convolution over a zero-padded gradient)
+};
+
 struct GemmArgs {
     const void* A;       // float (or u8 when a_u8)
     const void* B;       // float (or u8 when b_u8)
@@ -59,6 +67,10 @@ struct GemmArgs {
     // tcgen05 path only: every gather-table entry in use is a multiple of 4 elements (conv tables with C % 4 == 0), so
     // whole-tile problems may take the branch-free producer loads (tc_gemm_kernel<..., FAST>)
     int tables_vec4;
+    // TMA path (tma_gemm.cu): element offset of the operand's "lo" plane (x - tf32_trunc(x)) from its fp32 plane; 0 = the
+    // tensor has none (the SIMT-producer kernels are used).  c_plane != 0: the epilogue also stores lo(C) at C + c_plane.
+    long a_plane, b_plane, c_plane;
+    const TmaConv* a_conv;  // A's gather tables describe this convolution (im2col tensor maps instead of the tables)
 };
 
 constexpr int kBK = 16;
@@ -303,6 +315,9 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmArgs g)
                     }
                 }
                 float* dst = out + (size_t)m * ldo + n;
+                if (direct && g.c_plane)
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < g.N) dst[g.c_plane + j] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
                 if (n + 3 < g.N && ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0))
                     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                 else
@@ -316,6 +331,6 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmArgs g)
 // the bias / ReLU / ReLU-mask epilogue.
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                      int splits, const float* __restrict__ bias, int relu,
-                                     const float* __restrict__ mask);
+                                     const float* __restrict__ mask, long c_plane);
 
 }  // namespace bb

@@ -21,6 +21,17 @@ void Ctx::mark(const char* kernel) const {
     prof->marks.emplace_back(phase + ":" + layer + ":" + kernel, e);
 }
 
+void Ctx::alloc_scratch(size_t floats) {
+    ws_floats = floats;
+    ws = dev_alloc_zero<float>(ws_floats, stream);  // the tail holds colsum's block counters (must start at 0)
+    n_tickets = 4096;
+    tickets = dev_alloc_zero<unsigned int>(n_tickets, stream);
+}
+void Ctx::free_scratch() {
+    cudaFree(ws); cudaFree(tickets);
+    ws = nullptr; tickets = nullptr;
+}
+
 void Ctx::fork_to(const Ctx& s) const {
     BB_CUDA(cudaEventRecord(ev, stream));
     BB_CUDA(cudaStreamWaitEvent(s.stream, ev, 0));
@@ -33,9 +44,11 @@ void Ctx::join_from(const Ctx& s) const {
 // ------------------------------------------------------------------------------- split-K reduce
 
 // Few splits of a large tile: one thread per output element, coalesced across elements.
+__device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                      int splits, const float* __restrict__ bias, int relu,
-                                     const float* __restrict__ mask) {
+                                     const float* __restrict__ mask, long c_plane) {
     pdl_sync();
     size_t total = (size_t)M * N;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -46,6 +59,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
         if (relu) s = fmaxf(s, 0.f);
         if (mask) s = mask[(size_t)m * ldc + n] > 0.f ? s : 0.f;
         C[(size_t)m * ldc + n] = s;
+        if (c_plane) C[c_plane + (size_t)m * ldc + n] = lo_of(s);
     }
 }
 
@@ -54,7 +68,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
 // eight group sums are folded in group order through shared memory (deterministic).
 __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                       int splits, const float* __restrict__ bias, int relu,
-                                      const float* __restrict__ mask) {
+                                      const float* __restrict__ mask, long c_plane) {
     pdl_sync();
     __shared__ float part[8][33];
     const size_t total = (size_t)M * N;
@@ -83,6 +97,7 @@ __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __res
             if (relu) s = fmaxf(s, 0.f);
             if (mask) s = mask[(size_t)m * ldc + n] > 0.f ? s : 0.f;
             C[(size_t)m * ldc + n] = s;
+            if (c_plane) C[c_plane + (size_t)m * ldc + n] = lo_of(s);
         }
     }
 }
@@ -117,7 +132,7 @@ static int env_int(const char* name, int dflt) {
 __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                          float* __restrict__ C, int M, int N, int K, long lda, long ldb,
                                                          int ldc, const float* __restrict__ bias, int relu,
-                                                         const float* __restrict__ mask) {
+                                                         const float* __restrict__ mask, long c_plane) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (long)gridDim.x * (blockDim.x >> 5);
@@ -134,13 +149,14 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict
             if (relu) acc = fmaxf(acc, 0.f);
             if (mask) acc = mask[(size_t)m * ldc + n] > 0.f ? acc : 0.f;
             C[(size_t)m * ldc + n] = acc;
+            if (c_plane) C[c_plane + (size_t)m * ldc + n] = lo_of(acc);
         }
     }
 }
 // data gradient: C[m][n] = (sum_k A[m*lda+k] B[k*ldb+n]) * (mask > 0), K <= 16: a thread per output element
 __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                            float* __restrict__ C, int M, int N, int K, long lda, long ldb,
-                                                           int ldc, const float* __restrict__ mask) {
+                                                           int ldc, const float* __restrict__ mask, long c_plane) {
     pdl_sync();
     const size_t total = (size_t)M * N;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -149,6 +165,7 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
         for (int k = 0; k < K; ++k) acc = fmaf(A[(size_t)m * lda + k], B[(size_t)k * ldb + n], acc);
         if (mask) acc = mask[(size_t)m * ldc + n] > 0.f ? acc : 0.f;
         C[(size_t)m * ldc + n] = acc;
+        if (c_plane) C[c_plane + (size_t)m * ldc + n] = lo_of(acc);
     }
 }
 // weight gradient: C[m][n] = sum_k A[k*lda+m] B[k*ldb+n], M <= 16: 8 columns x 32 k-groups per CTA (N/8 CTAs: with 32
@@ -205,7 +222,7 @@ static bool gemm_skinny(const Ctx& c, GemmMode mode, const GemmArgs& a) {
         long warps = (long)a.M * a.N;
         int blocks = (int)std::min<long>((warps + 7) / 8, (long)c.sms * 8);
         launch_pdl(skinny_fwd_kernel, dim3(blocks), dim3(256), 0, c.stream, A, B, a.C, a.M, a.N, a.K, a.lda, a.ldb, a.ldc,
-                   a.bias, a.relu, a.mask);
+                   a.bias, a.relu, a.mask, a.c_plane);
         BB_LAUNCHED();
         c.mark("skinny_fwd");
         return true;
@@ -214,7 +231,7 @@ static bool gemm_skinny(const Ctx& c, GemmMode mode, const GemmArgs& a) {
         size_t total = (size_t)a.M * a.N;
         int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
         launch_pdl(skinny_dgrad_kernel, dim3(blocks), dim3(256), 0, c.stream, A, B, a.C, a.M, a.N, a.K, a.lda, a.ldb, a.ldc,
-                   a.mask);
+                   a.mask, a.c_plane);
         BB_LAUNCHED();
         c.mark("skinny_dgrad");
         return true;
@@ -234,8 +251,11 @@ void gemm(const Ctx& c, GemmMode mode, GemmArgs a) {
     if (a.M <= 0 || a.N <= 0) return;
     if (gemm_skinny(c, mode, a)) return;
     const int use_tc = env_int("BB_TC", 1);  // read per call so tests can flip it (0 = fp32 CUDA-core tiles)
-    // tcgen05 path (tc_gemm.cu); tiny problems (policy forward, the 6-wide output layer) stay on CUDA cores
-    if (use_tc && a.M >= 64 && (long)a.M * a.N * a.K >= (1L << 22) && a.N >= 16 && tc_gemm(c, mode, a)) return;
+    // tcgen05 paths; tiny problems (policy forward, the 6-wide output layer) stay on CUDA cores.  TMA-fed kernel
+    // (tma_gemm.cu) when both operands carry lo planes, else the SIMT-producer kernel (tc_gemm.cu).
+    const bool tc_size = a.M >= 64 && (long)a.M * a.N * a.K >= (1L << 22) && a.N >= 16;
+    if (use_tc && tc_size && tma_gemm(c, mode, a)) return;
+    if (use_tc && tc_size && tc_gemm(c, mode, a)) return;
     gemm_simt(c, mode, a);
 }
 
@@ -294,10 +314,10 @@ void gemm_simt(const Ctx& c, GemmMode mode, GemmArgs a) {
         size_t total = (size_t)a.M * a.N;
         if (split >= 16) {
             int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
-            launch_pdl(splitk_reduce8_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+            launch_pdl(splitk_reduce8_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask, a.c_plane);
         } else {
             int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
-            launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask);
+            launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, a.M, a.N, a.ldc, split, a.bias, a.relu, a.mask, a.c_plane);
         }
         BB_LAUNCHED();
         c.mark("splitk_reduce");
@@ -398,36 +418,44 @@ void colsum(const Ctx& c, const float* dY, float* db, int M, int N) {
 // ------------------------------------------------------------------------------- linear
 
 void linear_fwd(const Ctx& c, const float* X, long ldx, const float* W, const float* b, float* Y, int M, int N, int K,
-                bool relu) {
+                bool relu, long x_plane, long w_plane, long y_plane) {
     GemmArgs a = zero_args();
     a.A = X; a.lda = ldx; a.B = W; a.ldb = K; a.C = Y; a.ldc = N; a.M = M; a.N = N; a.K = K;
     a.bias = b; a.relu = relu;
+    a.a_plane = x_plane; a.b_plane = w_plane; a.c_plane = y_plane;
     gemm(c, G_FWD, a);
 }
 
 void linear_bwd_data(const Ctx& c, const float* dY, const float* W, float* dX, long lddx, int M, int N, int K,
-                     const float* mask) {
+                     const float* mask, long dy_plane, long w_plane, long dx_plane) {
     // dX[M][K] = dY[M][N] * W[N][K]
     GemmArgs a = zero_args();
     a.A = dY; a.lda = N; a.B = W; a.ldb = K; a.C = dX; a.ldc = (int)lddx; a.M = M; a.N = K; a.K = N;
     a.mask = mask;
+    a.a_plane = dy_plane; a.b_plane = w_plane; a.c_plane = dx_plane;
     gemm(c, G_NN, a);
 }
 
 void linear_bwd_weight(const Ctx& c, const float* dY, const float* X, long ldx, float* dW, float* db, int M, int N,
-                       int K) {
+                       int K, long dy_plane, long x_plane) {
     // dW[N][K] = sum_m dY[m][N]^T X[m][K]
     GemmArgs a = zero_args();
     a.A = dY; a.lda = N; a.B = X; a.ldb = ldx; a.C = dW; a.ldc = K; a.M = N; a.N = K; a.K = M;
+    a.a_plane = dy_plane; a.b_plane = x_plane;
     gemm(c, G_WGRAD, a);
     if (db) colsum(c, dY, db, M, N);
 }
 
 // ------------------------------------------------------------------------------- conv
 
+static TmaConv tma_conv_of(const ConvGeom& g) { return TmaConv{g.B, g.H, g.W, g.C, g.KH, g.KW, g.S, 0}; }
+
 void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu) {
     if (g.u8_chw && env_int("BB_TC", 1) && conv1_fwd_tc(c, g, X, W, b, Y, relu)) return;
     GemmArgs a = zero_args();
+    const TmaConv cv = tma_conv_of(g);
+    if (!g.u8_chw) { a.a_conv = &cv; a.a_plane = g.x_plane; a.b_plane = g.w_plane; }
+    a.c_plane = g.y_plane;
     a.A = X; a.a_rowbase = g.rowbase; a.a_koff = g.koff; a.B = W; a.ldb = g.K(); a.C = Y; a.ldc = g.OC;
     a.M = g.M(); a.N = g.OC; a.K = g.K(); a.bias = b; a.relu = relu;
     a.tables_vec4 = !g.u8_chw && g.C % 4 == 0;
@@ -450,7 +478,9 @@ void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const voi
         t.A = X; t.a_rowbase = g.koff; t.a_koff = g.rowbase; t.B = dY; t.ldb = g.OC; t.C = dW; t.ldc = g.K();
         t.M = g.K(); t.N = g.OC; t.K = g.M(); t.trans_out = 1;
         t.tables_vec4 = g.C % 4 == 0;
-        if (tc_gemm(c, g.u8_chw ? G_WGRAD_AU8 : G_WGRAD, t)) {
+        const TmaConv cv = tma_conv_of(g);
+        t.a_conv = &cv; t.a_plane = g.x_plane; t.b_plane = g.y_plane;
+        if (tma_gemm(c, G_WGRAD, t) || tc_gemm(c, g.u8_chw ? G_WGRAD_AU8 : G_WGRAD, t)) {
             if (db) colsum(c, dY, db, g.M(), g.OC);
             return;
         }
@@ -464,7 +494,7 @@ void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const voi
 
 // dX[b][h][w][c] = sum over the kernel taps that touch (h, w) of col[(b,oh,ow)][(kh,kw,c)]
 __global__ void col2im_nhwc_kernel(const float* __restrict__ col, float* __restrict__ dX, const float* __restrict__ mask,
-                                   int B, int C, int H, int W, int KH, int KW, int S, int OH, int OW) {
+                                   int B, int C, int H, int W, int KH, int KW, int S, int OH, int OW, long dx_plane) {
     pdl_sync();
     const int C4 = C / 4;
     size_t total = (size_t)B * H * W * C4;
@@ -494,6 +524,7 @@ __global__ void col2im_nhwc_kernel(const float* __restrict__ col, float* __restr
             acc.z = mk.z > 0.f ? acc.z : 0.f; acc.w = mk.w > 0.f ? acc.w : 0.f;
         }
         *reinterpret_cast<float4*>(dX + o) = acc;
+        if (dx_plane) *reinterpret_cast<float4*>(dX + dx_plane + o) = make_float4(lo_of(acc.x), lo_of(acc.y), lo_of(acc.z), lo_of(acc.w));
     }
 }
 
@@ -503,7 +534,7 @@ __global__ void col2im_nhwc_kernel(const float* __restrict__ col, float* __restr
 __global__ void dgrad_prep_kernel(const float4* __restrict__ dY, float4* __restrict__ pad, int B, int OH, int OW, int OC4,
                                   int OHp, int OWp, int offh, int offw, int pad_blocks, const float* __restrict__ W,
                                   float* __restrict__ Wt, const int* __restrict__ brow, const int* __restrict__ bnoff,
-                                  int N, int K) {
+                                  int N, int K, long dy_plane4, long pad_plane4, long w_plane, long wt_plane) {
     if ((int)blockIdx.x < pad_blocks) {
         size_t total = (size_t)B * OH * OW * OC4;
         for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)pad_blocks * blockDim.x) {
@@ -512,14 +543,18 @@ __global__ void dgrad_prep_kernel(const float4* __restrict__ dY, float4* __restr
             int ow = (int)(t % OW); t /= OW;
             int oh = (int)(t % OH);
             size_t b = t / OH;
-            pad[((b * OHp + oh + offh) * OWp + ow + offw) * OC4 + c] = dY[i];
+            const size_t o = ((b * OHp + oh + offh) * OWp + ow + offw) * OC4 + c;
+            pad[o] = dY[i];
+            if (pad_plane4) pad[pad_plane4 + o] = dY[dy_plane4 + i];   // the lo plane travels with it
         }
     } else {
         const int wb = gridDim.x - pad_blocks;
         const int total = N * K;
         for (int i = (blockIdx.x - pad_blocks) * blockDim.x + threadIdx.x; i < total; i += wb * blockDim.x) {
             int k = i % K, n = i / K;
-            Wt[i] = W[brow[k] + bnoff[n]];
+            const int src = brow[k] + bnoff[n];
+            Wt[i] = W[src];
+            if (wt_plane) Wt[wt_plane + i] = w_plane ? W[w_plane + src] : lo_of(W[src]);
         }
     }
 }
@@ -539,7 +574,8 @@ void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float
         int w_blocks = std::min((N * K + 255) / 256, c.sms * 2);
         dgrad_prep_kernel<<<pad_blocks + w_blocks, 256, 0, c.stream>>>(
             reinterpret_cast<const float4*>(dY), reinterpret_cast<float4*>(g.dypad), g.B, g.OH, g.OW, g.OC / 4, g.dg_hp(),
-            g.dg_wp(), Jh - 1, Jw - 1, pad_blocks, W, g.dg_wt, g.dg_brow, g.dg_bnoff, N, K);
+            g.dg_wp(), Jh - 1, Jw - 1, pad_blocks, W, g.dg_wt, g.dg_brow, g.dg_bnoff, N, K,
+            g.y_plane && g.dypad_plane ? g.y_plane / 4 : 0, g.y_plane && g.dypad_plane ? g.dypad_plane / 4 : 0, g.w_plane, g.wt_plane);
         BB_LAUNCHED();
         c.mark("dgrad_prep");
         GemmArgs a = zero_args();
@@ -548,15 +584,21 @@ void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float
         a.C = dX; a.ldc = N; a.c_rowoff = g.dg_crow; a.c_coloff = g.dg_ccol; a.mask = mask;
         a.M = g.B * (g.H / g.S) * (g.W / g.S); a.N = N; a.K = K;
         a.tables_vec4 = 1;  // OC % 4 == 0 and C % 4 == 0 (dgrad_gather_ok)
+        // TMA form: a stride-1 im2col walk of the padded dY with the tap offsets running backwards
+        const TmaConv cv{g.B, g.dg_hp(), g.dg_wp(), g.OC, Jh, Jw, 1, 1};
+        if (g.y_plane && g.dypad_plane) { a.a_conv = &cv; a.a_plane = g.dypad_plane; a.b_plane = g.wt_plane; }
+        a.c_plane = g.dx_plane;
+        if (tma_gemm(c, G_FWD, a)) return;
         if (tc_gemm(c, G_FWD, a)) return;
     }
     BB_CHECK(col != nullptr, "conv_bwd_data: no column buffer for the col2im path");
     GemmArgs a = zero_args();
     a.A = dY; a.lda = g.OC; a.B = W; a.ldb = g.K(); a.C = col; a.ldc = g.K(); a.M = g.M(); a.N = g.K(); a.K = g.OC;
+    a.a_plane = g.y_plane; a.b_plane = g.w_plane;
     gemm(c, G_NN, a);
     size_t total = (size_t)g.B * g.H * g.W * (g.C / 4);
     int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 16);
-    launch_pdl(col2im_nhwc_kernel, dim3(blocks), dim3(256), 0, c.stream, col, dX, mask, g.B, g.C, g.H, g.W, g.KH, g.KW, g.S, g.OH, g.OW);
+    launch_pdl(col2im_nhwc_kernel, dim3(blocks), dim3(256), 0, c.stream, col, dX, mask, g.B, g.C, g.H, g.W, g.KH, g.KW, g.S, g.OH, g.OW, g.dx_plane);
     BB_LAUNCHED();
     c.mark("col2im");
 }
@@ -613,7 +655,7 @@ __device__ __forceinline__ float mean_over_ranks1(const PeerPtrs& peers, size_t 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float b1, float b2, float one_m_b1, float one_m_b2,
                             float eps, float bc2_sqrt, float neg_step, float wd, float decay, int adamw,
-                            PeerPtrs peers, int world) {
+                            PeerPtrs peers, int world, float* __restrict__ p_lo) {
     const size_t n4 = n >> 2;
     const float inv_world = 1.0f;
     (void)inv_world;
@@ -630,6 +672,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         adam_elem(pi.z, gi.z, mi.z, vi.z, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
         adam_elem(pi.w, gi.w, mi.w, vi.w, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
         reinterpret_cast<float4*>(m)[i] = mi; reinterpret_cast<float4*>(v)[i] = vi; reinterpret_cast<float4*>(p)[i] = pi;
+        if (p_lo) reinterpret_cast<float4*>(p_lo)[i] = make_float4(lo_of(pi.x), lo_of(pi.y), lo_of(pi.z), lo_of(pi.w));
     }
     for (size_t i = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float gi;
@@ -641,6 +684,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         float pi = p[i], mi = m[i], vi = v[i];
         adam_elem(pi, gi, mi, vi, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
         m[i] = mi; v[i] = vi; p[i] = pi;
+        if (p_lo) p_lo[i] = lo_of(pi);
     }
 }
 
@@ -676,7 +720,7 @@ void grad_reduce_scatter(const Ctx& c, const float* const* peer_grads, size_t n,
 }
 
 void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
-               uint64_t step, const float* const* peer_grads, int world) {
+               uint64_t step, const float* const* peer_grads, int world, float* p_lo) {
     double bc1 = 1.0 - pow(h.beta1, (double)step);
     double bc2 = 1.0 - pow(h.beta2, (double)step);
     double step_size = h.lr / bc1;
@@ -688,20 +732,23 @@ void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_
     adam_kernel<<<blocks, 256, 0, c.stream>>>(p, g, m, v, n, (float)h.beta1, (float)h.beta2, (float)(1.0 - h.beta1),
                                               (float)(1.0 - h.beta2), (float)h.eps, (float)sqrt(bc2),
                                               (float)(-step_size), (float)h.wd, (float)(1.0 - h.lr * h.wd),
-                                              h.adamw ? 1 : 0, pp, peer_grads ? world : 1);
+                                              h.adamw ? 1 : 0, pp, peer_grads ? world : 1, p_lo);
     BB_LAUNCHED();
     c.layer = "";
     c.mark("adam");
 }
 
 __global__ void track_kernel(float* __restrict__ dest, const float* __restrict__ src, size_t n, float tau,
-                             float one_m_tau) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        dest[i] = __fadd_rn(__fmul_rn(tau, src[i]), __fmul_rn(one_m_tau, dest[i]));
+                             float one_m_tau, float* __restrict__ dest_lo) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float d = __fadd_rn(__fmul_rn(tau, src[i]), __fmul_rn(one_m_tau, dest[i]));
+        dest[i] = d;
+        if (dest_lo) dest_lo[i] = lo_of(d);
+    }
 }
-void track(const Ctx& c, float* dest, const float* src, size_t n, double tau) {
+void track(const Ctx& c, float* dest, const float* src, size_t n, double tau, float* dest_lo) {
     int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)c.sms * 8);
-    track_kernel<<<blocks, 256, 0, c.stream>>>(dest, src, n, (float)tau, (float)(1.0 - tau));
+    track_kernel<<<blocks, 256, 0, c.stream>>>(dest, src, n, (float)tau, (float)(1.0 - tau), dest_lo);
     BB_LAUNCHED();
     c.layer = "";
     c.mark("track");
@@ -745,6 +792,7 @@ void NetWorkspace::release() {
     for (auto p : dg_wt) cudaFree(p);
     cudaFree(col);
     act.clear(); dact.clear(); rowbase.clear(); dg_rowbase.clear(); dg_crow.clear(); dypad.clear(); dg_wt.clear(); col = nullptr;
+    plane.clear(); dypad_plane.clear(); wt_plane.clear();
 }
 
 static void add_param(Net& n, const std::string& name, std::vector<int64_t> shape, int perm, int pc, int ph, int pw,
@@ -906,9 +954,11 @@ void Net::alloc_workspace(NetWorkspace& w, int max_batch, bool with_grad) const 
     size_t col = 0;
     for (size_t i = 0; i < layers.size(); ++i) {
         const Layer& l = layers[i];
-        size_t n = (size_t)max_batch * l.out_elems_per_sample;
-        w.act.push_back(dev_alloc<float>(n));
-        w.dact.push_back(with_grad ? dev_alloc<float>(n) : nullptr);
+        // every buffer is followed by its lo plane (x - tf32_trunc(x)), the second operand plane of the TMA-fed GEMMs
+        size_t n = ((size_t)max_batch * l.out_elems_per_sample + 3) / 4 * 4;
+        w.plane.push_back((long)n);
+        w.act.push_back(dev_alloc<float>(2 * n));
+        w.dact.push_back(with_grad ? dev_alloc<float>(2 * n) : nullptr);
         if (l.type == 1) {
             const ConvGeom& g = l.geom;
             size_t M = (size_t)max_batch * g.OH * g.OW;
@@ -926,6 +976,7 @@ void Net::alloc_workspace(NetWorkspace& w, int max_batch, bool with_grad) const 
             w.rowbase.push_back(d);
             int *dgr = nullptr, *dgc = nullptr;
             float *pad = nullptr, *wt = nullptr;
+            long pad_plane = 0, wt_plane_ = 0;
             if (with_grad && i > 0 && g.dg_koff) {  // gather-form data gradient: per-batch row tables + padded dY
                 const int Hq = g.H / g.S, Wq = g.W / g.S, OHp = g.dg_hp(), OWp = g.dg_wp();
                 size_t Mq = (size_t)max_batch * Hq * Wq;
@@ -941,17 +992,20 @@ void Net::alloc_workspace(NetWorkspace& w, int max_batch, bool with_grad) const 
                 dgr = dev_alloc<int>(Mq); dgc = dev_alloc<int>(Mq);
                 BB_CUDA(cudaMemcpy(dgr, rb.data(), Mq * sizeof(int), cudaMemcpyHostToDevice));
                 BB_CUDA(cudaMemcpy(dgc, cr.data(), Mq * sizeof(int), cudaMemcpyHostToDevice));
-                size_t pn = (size_t)max_batch * OHp * OWp * g.OC;
-                pad = dev_alloc<float>(pn);
-                BB_CUDA(cudaMemset(pad, 0, pn * sizeof(float)));
-                wt = dev_alloc<float>((size_t)g.K() * g.OC);
+                size_t pn = (size_t)max_batch * OHp * OWp * g.OC;   // OC % 4 == 0
+                pad = dev_alloc<float>(2 * pn);
+                BB_CUDA(cudaMemset(pad, 0, 2 * pn * sizeof(float)));
+                wt = dev_alloc<float>(2 * (size_t)g.K() * g.OC);
+                pad_plane = (long)pn; wt_plane_ = (long)g.K() * g.OC;
             }
             // the col2im path (CUDA-core fallback, BB_TC=0 / BB_DGRAD_GATHER=0) keeps its column buffer
             if (with_grad && i > 0) col = std::max(col, M * (size_t)g.K());
             w.dg_rowbase.push_back(dgr); w.dg_crow.push_back(dgc); w.dypad.push_back(pad); w.dg_wt.push_back(wt);
+            w.dypad_plane.push_back(pad_plane); w.wt_plane.push_back(wt_plane_);
         } else {
             w.rowbase.push_back(nullptr);
             w.dg_rowbase.push_back(nullptr); w.dg_crow.push_back(nullptr); w.dypad.push_back(nullptr); w.dg_wt.push_back(nullptr);
+            w.dypad_plane.push_back(0); w.wt_plane.push_back(0);
         }
     }
     w.col_floats = col;
@@ -980,19 +1034,23 @@ std::string Net::layer_name(size_t i) const {
     return "layer" + std::to_string(i);
 }
 
-const float* Net::forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w) const {
+const float* Net::forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w, long p_plane) const {
     BB_CHECK(B <= w.max_batch, "batch larger than the workspace");
     const void* x = input;
     long ldx = ld_in;
     for (size_t i = 0; i < layers.size(); ++i) {
         const Layer& l = layers[i];
         c.layer = layer_name(i) + ".fwd";
+        // lo planes: the network input has none; every layer output gets one when the parameters carry one
+        const long x_plane = (p_plane && i) ? w.plane[i - 1] : 0, y_plane = p_plane ? w.plane[i] : 0;
         if (l.type == 1) {
             ConvGeom g = l.geom;
             g.B = B; g.rowbase = w.rowbase[i];
+            g.x_plane = x_plane; g.w_plane = p_plane; g.y_plane = y_plane;
             conv_fwd(c, g, x, p + l.w_off, p + l.b_off, w.act[i], l.relu);
         } else {
-            linear_fwd(c, (const float*)x, ldx, p + l.w_off, p + l.b_off, w.act[i], B, l.out_dim, l.in_dim, l.relu);
+            linear_fwd(c, (const float*)x, ldx, p + l.w_off, p + l.b_off, w.act[i], B, l.out_dim, l.in_dim, l.relu, x_plane,
+                       p_plane, y_plane);
         }
         x = w.act[i];
         ldx = (long)l.out_elems_per_sample;
@@ -1097,7 +1155,7 @@ __global__ void relu_mask_kernel(float* __restrict__ d, const float* __restrict_
 }
 
 void Net::backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
-                   float* d_input, long ld_din) const {
+                   float* d_input, long ld_din, long p_plane) const {
     BB_CHECK(w.with_grad, "workspace was allocated without gradient buffers");
     int L = (int)layers.size();
     // d(output) arrives in w.dact[L-1] as the gradient wrt the post-activation output
@@ -1105,6 +1163,12 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
         size_t n = (size_t)B * layers[L - 1].out_elems_per_sample;
         relu_mask_kernel<<<(int)std::min<size_t>((n + 255) / 256, (size_t)c.sms * 8), 256, 0, c.stream>>>(w.dact[L - 1], w.act[L - 1], n);
         BB_LAUNCHED();
+    }
+    // d(output) comes from a loss kernel without a lo plane: a wide last layer (tensor-core contraction) needs one
+    bool dy_lo = false;   // does dact[i] carry a valid lo plane?
+    if (p_plane && layers[L - 1].out_elems_per_sample > 16) {
+        make_lo(c, w.dact[L - 1], w.dact[L - 1] + w.plane[L - 1], (size_t)B * layers[L - 1].out_elems_per_sample);
+        dy_lo = true;
     }
     const bool conc = c.concurrent() && g;
     int n_side = 0;
@@ -1127,10 +1191,15 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
             bc = c.side[n_side++ & 1];
             c.fork_to(*bc);
         }
+        // lo planes of this layer's operands: X = act[i-1] (forward wrote it), dY = dact[i], dX = dact[i-1]
+        const long x_plane = (p_plane && i) ? w.plane[i - 1] : 0, dy_plane = dy_lo ? w.plane[i] : 0;
+        const long dx_plane = (p_plane && i) ? w.plane[i - 1] : 0;
         if (l.type == 1) {
             ConvGeom cg = l.geom;
             cg.B = B; cg.rowbase = w.rowbase[i];
             cg.dg_rowbase = w.dg_rowbase[i]; cg.dg_crow = w.dg_crow[i]; cg.dypad = w.dypad[i]; cg.dg_wt = w.dg_wt[i];
+            cg.x_plane = x_plane; cg.y_plane = dy_plane; cg.w_plane = p_plane; cg.dx_plane = dx_plane;
+            cg.dypad_plane = p_plane ? w.dypad_plane[i] : 0; cg.wt_plane = p_plane ? w.wt_plane[i] : 0;
             if (g) {
                 c.layer = layer_name(i) + ".wgrad";
                 if (bc) colsum(*bc, w.dact[i], g + l.b_off, cg.M(), cg.OC);
@@ -1141,11 +1210,13 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
         } else {
             if (g) {
                 c.layer = layer_name(i) + ".wgrad";
-                linear_bwd_weight(*wc, w.dact[i], (const float*)x, ldx, g + l.w_off, g + l.b_off, B, l.out_dim, l.in_dim);
+                linear_bwd_weight(*wc, w.dact[i], (const float*)x, ldx, g + l.w_off, g + l.b_off, B, l.out_dim, l.in_dim, dy_plane,
+                                  x_plane);
             }
             c.layer = layer_name(i) + ".dgrad";
-            if (dx) linear_bwd_data(c, w.dact[i], p + l.w_off, dx, lddx, B, l.out_dim, l.in_dim, mask);
+            if (dx) linear_bwd_data(c, w.dact[i], p + l.w_off, dx, lddx, B, l.out_dim, l.in_dim, mask, dy_plane, p_plane, dx_plane);
         }
+        dy_lo = p_plane != 0;  // every data-gradient epilogue above wrote the lo plane of dact[i-1]
     }
     if (n_side > 0) c.join_from(*c.side[0]);
     if (n_side > 1) c.join_from(*c.side[1]);

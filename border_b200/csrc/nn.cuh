@@ -30,6 +30,10 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     float* ws = nullptr;  // split-K / reduction workspace
     size_t ws_floats = 0;
+    unsigned int* tickets = nullptr;  // per-tile arrival counters of the in-kernel split-K finish (tma_gemm.cuh), zero between launches
+    size_t n_tickets = 0;
+    void alloc_scratch(size_t floats);  // ws + tickets (zeroed on `stream`)
+    void free_scratch();
     Profiler* prof = nullptr;
     mutable std::string phase, layer;
     void mark(const char* kernel) const;  // no-op unless prof is set
@@ -48,18 +52,22 @@ enum GemmMode { G_FWD = 0, G_FWD_U8, G_NN, G_WGRAD, G_WGRAD_U8, G_WGRAD_AU8 /* t
 void gemm(const Ctx& c, GemmMode mode, GemmArgs a);          // nn.cu: picks tcgen05 or CUDA-core tiles
 void gemm_simt(const Ctx& c, GemmMode mode, GemmArgs a);     // nn.cu: fp32 CUDA-core tiles only
 bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a);      // tc_gemm.cu: false => not handled
+bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a);     // tma_gemm.cu: TMA-fed tcgen05 kernel; false => not handled
+void make_lo(const Ctx& c, const float* x, float* lo, size_t n);  // lo = x - tf32_trunc(x) (the second operand plane)
 GemmArgs zero_args();
 
 // ---- primitives (all row-major fp32) -------------------------------------------------------
+// The *_plane arguments are the element offsets of the tensors' lo planes (x - tf32_trunc(x), see tma_gemm.cuh);
+// 0 = the tensor has none / none is wanted for the output.
 // Y[M][N] = act(X[M][K] W[N][K]^T + b)
 void linear_fwd(const Ctx& c, const float* X, long ldx, const float* W, const float* b, float* Y, int M, int N, int K,
-                bool relu);
+                bool relu, long x_plane = 0, long w_plane = 0, long y_plane = 0);
 // dX[M][K] = (dY[M][N] W[N][K]) * (mask > 0)
 void linear_bwd_data(const Ctx& c, const float* dY, const float* W, float* dX, long lddx, int M, int N, int K,
-                     const float* mask);
+                     const float* mask, long dy_plane = 0, long w_plane = 0, long dx_plane = 0);
 // dW[N][K] = dY^T X ; db[N] = colsum(dY)
 void linear_bwd_weight(const Ctx& c, const float* dY, const float* X, long ldx, float* dW, float* db, int M, int N,
-                       int K);
+                       int K, long dy_plane = 0, long x_plane = 0);
 void colsum(const Ctx& c, const float* dY, float* db, int M, int N);
 
 struct ConvGeom {
@@ -78,6 +86,8 @@ struct ConvGeom {
     const int* dg_ccol = nullptr;     // [S*S*C]
     float* dypad = nullptr;           // [B][H/S + KH/S - 1][W/S + KW/S - 1][OC] per workspace, borders stay zero
     float* dg_wt = nullptr;           // [S*S*C][(KH/S)*(KW/S)*OC] per workspace: the weights re-laid k-contiguous per step
+    // lo planes (element offsets; 0 = none): input X, output Y / its gradient dY, weights, input gradient dX, dypad, dg_wt
+    long x_plane = 0, y_plane = 0, w_plane = 0, dx_plane = 0, dypad_plane = 0, wt_plane = 0;
     int M() const { return B * OH * OW; }
     int K() const { return C * KH * KW; }
     bool dgrad_gather_ok() const {
@@ -100,12 +110,13 @@ struct AdamHyper {
     double lr, beta1, beta2, eps, wd;
     bool adamw;
 };
+// p_lo != null: the kernel also refreshes the parameters' lo plane (operand of the TMA-fed GEMMs)
 void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
-               uint64_t step /* 1-based */, const float* const* peer_grads = nullptr, int world = 1);
+               uint64_t step /* 1-based */, const float* const* peer_grads = nullptr, int world = 1, float* p_lo = nullptr);
 // mean of all ranks' gradients, slice-owner computes and stores it into every rank's buffer (peer memory)
 void grad_reduce_scatter(const Ctx& c, const float* const* peer_grads, size_t n, int rank, int world);
 // dest = tau*src + (1-tau)*dest  (util.rs:43)
-void track(const Ctx& c, float* dest, const float* src, size_t n, double tau);
+void track(const Ctx& c, float* dest, const float* src, size_t n, double tau, float* dest_lo = nullptr);
 void fill_uniform(const Ctx& c, float* p, size_t n, float bound, uint64_t seed);
 void fill_const(const Ctx& c, float* p, size_t n, float v);
 
@@ -134,8 +145,10 @@ struct Layer {
 struct NetWorkspace {
     int max_batch = 0;
     bool with_grad = false;
-    std::vector<float*> act;    // output of each layer [B][out]
-    std::vector<float*> dact;   // grad wrt output of each layer
+    std::vector<float*> act;    // output of each layer [B][out], followed by its lo plane at + plane[i]
+    std::vector<float*> dact;   // grad wrt output of each layer, same
+    std::vector<long> plane;    // elements between a buffer's fp32 plane and its lo plane
+    std::vector<long> dypad_plane, wt_plane;
     std::vector<int*> rowbase;  // per conv layer
     std::vector<int*> dg_rowbase, dg_crow;  // per layer (null unless the gather-form data gradient applies)
     std::vector<float*> dypad, dg_wt;
@@ -166,7 +179,9 @@ class Net {
     void alloc_workspace(NetWorkspace& w, int max_batch, bool with_grad) const;
     void init_params(const Ctx& c, float* p, uint64_t seed) const;
     // forward: input [B][in] (u8 CHW frames or float rows); returns ws.act.back()
-    const float* forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w) const;
+    // p_plane != 0: the parameter vector carries a valid lo plane at p + p_plane; the layers then write the lo planes of
+    // their outputs and the TMA-fed tensor-core GEMMs are used wherever both operands have one.
+    const float* forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w, long p_plane = 0) const;
     // Policy::sample-sized batches (B <= 8): the whole forward as ONE cooperative kernel, a warp per output element
     // and a grid-wide barrier between layers (the per-layer GEMM launches are pure latency at B = 1).  Returns null
     // when the net / batch does not qualify (caller falls back to forward()).
@@ -177,7 +192,7 @@ class Net {
     // With c.concurrent() the weight gradients of all layers but the first run on the side contexts
     // while the data-gradient chain continues on c.stream; everything is joined before returning.
     void backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
-                  float* d_input, long ld_din) const;
+                  float* d_input, long ld_din, long p_plane = 0) const;
     void free_tables();
     std::string layer_name(size_t i) const;
 };

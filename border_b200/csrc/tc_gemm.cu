@@ -1,5 +1,6 @@
 // tc_gemm.cu -- launcher of the tcgen05 GEMM (tc_gemm.cuh) and its test hook.
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 #include <vector>
 #include "nn.cuh"
@@ -33,28 +34,23 @@ static void tc_launch(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t 
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
-                                     int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask);
+                                     int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask, long c_plane);
 __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
-                                      int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask);
-
-bool tc_gemm_variant(const Ctx& c, int cfg2, int avar, GemmMode mode, const GemmArgs& a, dim3 grid, int BN, int tm, int tn,
-                     int split, bool v1_only, bool mapped_out, const char** tag);  // tc_gemm_variants.cu
+                                      int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask, long c_plane);
 
 bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     // target CTAs of a split-K launch, % of SMs.  A/B on the DQN step (us): 40: 361.5, 50: 357.2, 60: 350.2, 75: 349.1,
     // 100: 354.7, 150: 368.4 -- the split launches share the GPU with the other streams' kernels
     static const int fill_pct = getenv("BB_TC_FILL") ? atoi(getenv("BB_TC_FILL")) : 75;
-    // 0: 3 stages, 1 CTA/SM; 1: two CTAs/SM for BN <= 64; 2 (default, fastest on B200): BN <= 64 always, two
-    // CTAs/SM; 3: persistent flat-pipelined kernel (tc_gemm2.cuh)
-    static const int cfg2 = getenv("BB_TC_CFG") ? atoi(getenv("BB_TC_CFG")) : 2;
-    int BN = a.N <= 32 ? 32 : ((a.N <= 64 || cfg2 >= 2) ? 64 : 128);
+    // BN <= 64 with two CTAs/SM measured fastest on B200 (3 stages x 1 CTA/SM and 128-wide tiles lose on these shapes)
+    int BN = a.N <= 32 ? 32 : 64;
     // Both operands of an untransposed weight gradient are stored transposed (scalar st.shared): the producer cost per
     // k-slice is per ROW loaded, so the wider 128x128 tile (3 stages, 1 CTA/SM) wins there -- l1.wgrad 30.8 -> 24.6 us,
     // 64x512x20736 71 -> 49 us on the box -- while it loses on the forward / dgrad shapes (l1.fwd 24.5 -> 35.9 us).
     const bool wgrad_mode = mode == G_WGRAD || mode == G_WGRAD_U8 || mode == G_WGRAD_AU8;
     // Only for long contractions (IQN's 512x3136x16384: 1561 -> 913 us): the 1-CTA/SM, 200 KB tile keeps other streams'
     // CTAs off its SMs, which cost the DQN step 26 us when its small l1.wgrad (K = 256, side stream) took it.
-    if (cfg2 == 2 && wgrad_mode && !a.trans_out && a.N >= 128 && a.M >= 64 && a.K >= 4096) BN = 128;
+    if (wgrad_mode && !a.trans_out && a.N >= 128 && a.M >= 64 && a.K >= 4096) BN = 128;
     int tm = (a.M + tc::BM - 1) / tc::BM, tn = (a.N + BN - 1) / BN;
     long tiles = (long)tm * tn;
     int kt = (a.K + tc::BK - 1) / tc::BK;
@@ -77,13 +73,7 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     static const int debug = getenv("BB_TC_DEBUG") ? atoi(getenv("BB_TC_DEBUG")) : 0;  // 1: no global loads, 2: no MMA
     a.fence_mode = fence_mode | (debug << 4);
     dim3 grid(tn, tm, split);
-    const bool v1_only = a.trans_out || mode == G_WGRAD_AU8 || mapped_out;  // transposed store / u8 m-contiguous A live in tc_gemm.cuh
-    static const int avar = getenv("BB_TC_ASYNC") ? atoi(getenv("BB_TC_ASYNC")) : 0;
-    // experimental variants (BB_TC_CFG 3..6: persistent, A in tensor memory, cp.async ring, both) live in their own
-    // translation unit (tc_gemm_variants.cu); all measured slower than the default kernel on B200
-    const char* vtag = nullptr;
-    if (cfg2 >= 3 && cfg2 <= 6 && tc_gemm_variant(c, cfg2, avar, mode, a, grid, BN, tm, tn, split, v1_only, mapped_out, &vtag)) {
-    } else if (cfg2 >= 1) {
+    {
         // branch-free producer loads when every tile and k-slice is whole and every 4-group is 16-byte aligned
         static const int fast_env = getenv("BB_TC_FAST") ? atoi(getenv("BB_TC_FAST")) : 1;
         const bool a_tab = a.a_rowbase || a.a_koff, b_tab = a.b_rowbase || a.b_noff;
@@ -95,23 +85,17 @@ bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
             case 64: tc_launch<64, 2, 2, 2>(mode, a, grid, c.stream, fast); break;
             default: tc_launch<128, 3, 3, 1>(mode, a, grid, c.stream, fast); break;
         }
-    } else {
-        switch (BN) {
-            case 32: tc_launch<32, 3, 3, 1>(mode, a, grid, c.stream); break;
-            case 64: tc_launch<64, 3, 3, 1>(mode, a, grid, c.stream); break;
-            default: tc_launch<128, 3, 3, 1>(mode, a, grid, c.stream); break;
-        }
     }
-    c.mark(vtag ? vtag : (BN == 32 ? "tc_gemm128x32" : (BN == 64 ? "tc_gemm128x64" : "tc_gemm128x128")));
+    c.mark((BN == 32 ? "tc_gemm128x32" : (BN == 64 ? "tc_gemm128x64" : "tc_gemm128x128")));
     if (split > 1) {
         size_t total = (size_t)a.M * a.N;
         const int rows = a.trans_out ? a.N : a.M, cols = a.trans_out ? a.M : a.N;  // layout of the partials = layout of C
         if (split >= 16) {
             int blocks = (int)std::min<size_t>((total * 8 + 255) / 256, (size_t)c.sms * 8);
-            launch_pdl(splitk_reduce8_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask);
+            launch_pdl(splitk_reduce8_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask, a.c_plane);
         } else {
             int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 8);
-            launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask);
+            launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, c.stream, c.ws, a.C, rows, cols, a.ldc, split, a.bias, a.relu, a.mask, a.c_plane);
         }
         BB_LAUNCHED();
         c.mark("splitk_reduce");
@@ -140,12 +124,14 @@ extern "C" int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, in
     DeviceGuard g(device);
     Ctx c;
     c.device = device; c.sms = num_sms(device); c.stream = device_stream(device);
-    c.ws_floats = 8u << 20;
-    c.ws = dev_alloc_zero<float>(c.ws_floats, c.stream);
-    size_t na = (size_t)M * K, nb = (size_t)N * K, nc = (size_t)M * N;
-    float *dA = dev_alloc<float>(na), *dB = dev_alloc<float>(nb), *dC = dev_alloc_zero<float>(nc, c.stream), *dbias = nullptr;
-    BB_CUDA(cudaMemcpyAsync(dA, A, na * 4, cudaMemcpyHostToDevice, c.stream));
-    BB_CUDA(cudaMemcpyAsync(dB, B, nb * 4, cudaMemcpyHostToDevice, c.stream));
+    c.alloc_scratch(8u << 20);
+    // every operand is followed by its lo plane (use_tc = 3: the TMA-fed kernel needs them; C's is checked below)
+    const size_t na = ((size_t)M * K + 3) / 4 * 4, nb = ((size_t)N * K + 3) / 4 * 4, nc = ((size_t)M * N + 3) / 4 * 4;
+    float *dA = dev_alloc<float>(2 * na), *dB = dev_alloc<float>(2 * nb), *dC = dev_alloc_zero<float>(2 * nc, c.stream), *dbias = nullptr;
+    BB_CUDA(cudaMemcpyAsync(dA, A, (size_t)M * K * 4, cudaMemcpyHostToDevice, c.stream));
+    BB_CUDA(cudaMemcpyAsync(dB, B, (size_t)N * K * 4, cudaMemcpyHostToDevice, c.stream));
+    make_lo(c, dA, dA + na, (size_t)M * K);
+    make_lo(c, dB, dB + nb, (size_t)N * K);
     if (bias) {
         dbias = dev_alloc<float>(N);
         BB_CUDA(cudaMemcpyAsync(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice, c.stream));
@@ -157,19 +143,37 @@ extern "C" int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, in
     else if (mode == 2) { gm = G_NN; a.lda = K; a.ldb = N; }
     else if (mode == 3) { gm = G_WGRAD; a.lda = M; a.ldb = N; }
     else throw Error("bb_test_gemm: mode must be 0, 2 or 3");
-    if (use_tc == 2) {
+    if (use_tc == 3) { a.a_plane = (long)na; a.b_plane = (long)nb; }
+    if (use_tc >= 2) a.c_plane = (long)nc;
+    if (use_tc == 3) {
+        BB_CHECK(tma_gemm(c, gm, a), "bb_test_gemm: the TMA path declined this problem");
+    } else if (use_tc == 2) {
         gemm(c, gm, a);  // the dispatcher the layers use: skinny kernels, tcgen05 tiles or CUDA-core tiles by shape
     } else if (use_tc) {
         tc_gemm(c, gm, a);
     } else {
         gemm_simt(c, gm, a);
     }
-    BB_CUDA(cudaMemcpyAsync(C_out, dC, nc * 4, cudaMemcpyDeviceToHost, c.stream));
+    BB_CUDA(cudaMemcpyAsync(C_out, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost, c.stream));
+    std::vector<float> lo;
+    if (use_tc >= 2) {
+        lo.resize((size_t)M * N);
+        BB_CUDA(cudaMemcpyAsync(lo.data(), dC + nc, (size_t)M * N * 4, cudaMemcpyDeviceToHost, c.stream));
+    }
     cudaError_t e = cudaStreamSynchronize(c.stream);
     int flag = tc_error_flag();
-    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dbias); cudaFree(c.ws);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dbias); c.free_scratch();
     BB_CUDA(e);
     BB_CHECK(flag == 0, "tcgen05 pipeline timed out (g_tc_error)");
+    check_device_error("bb_test_gemm");
+    for (size_t i = 0; i < lo.size(); ++i) {   // every writer of a planed tensor must also write its lo plane
+        uint32_t u;
+        memcpy(&u, &C_out[i], 4);
+        u &= 0xffffe000u;
+        float hi;
+        memcpy(&hi, &u, 4);
+        BB_CHECK(lo[i] == C_out[i] - hi, "bb_test_gemm: the lo plane of C is not C - tf32_trunc(C)");
+    }
     BB_API_END
 }
 
@@ -182,14 +186,16 @@ extern "C" int32_t bb_bench_gemm(int32_t device, int32_t mode, int32_t use_tc, i
     DeviceGuard g(device);
     Ctx c;
     c.device = device; c.sms = num_sms(device); c.stream = device_stream(device);
-    c.ws_floats = 8u << 20;
-    c.ws = dev_alloc_zero<float>(c.ws_floats, c.stream);
-    size_t na = (size_t)M * K, nb = (size_t)N * K, nc = (size_t)M * N;
-    float *dA = dev_alloc<float>(na), *dB = dev_alloc<float>(nb), *dC = dev_alloc_zero<float>(nc, c.stream);
+    c.alloc_scratch(8u << 20);
+    size_t na = ((size_t)M * K + 3) / 4 * 4, nb = ((size_t)N * K + 3) / 4 * 4, nc = ((size_t)M * N + 3) / 4 * 4;
+    float *dA = dev_alloc<float>(2 * na), *dB = dev_alloc<float>(2 * nb), *dC = dev_alloc_zero<float>(2 * nc, c.stream);
     fill_uniform(c, dA, na, 1.0f, 1);
     fill_uniform(c, dB, nb, 1.0f, 2);
+    make_lo(c, dA, dA + na, na);
+    make_lo(c, dB, dB + nb, nb);
     GemmArgs a = zero_args();
     a.A = dA; a.B = dB; a.C = dC; a.M = M; a.N = N; a.K = K; a.ldc = N;
+    if (use_tc == 3) { a.a_plane = (long)na; a.b_plane = (long)nb; a.c_plane = (long)nc; }
     GemmMode gm;
     if (mode == 0) { gm = G_FWD; a.lda = K; a.ldb = K; }
     else if (mode == 2) { gm = G_NN; a.lda = K; a.ldb = N; }
@@ -197,17 +203,24 @@ extern "C" int32_t bb_bench_gemm(int32_t device, int32_t mode, int32_t use_tc, i
     cudaEvent_t e0, e1;
     BB_CUDA(cudaEventCreate(&e0));
     BB_CUDA(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) { GemmArgs b = a; if (use_tc) tc_gemm(c, gm, b); else gemm_simt(c, gm, b); }
+    auto run = [&]() {
+        GemmArgs b = a;
+        if (use_tc == 3) BB_CHECK(tma_gemm(c, gm, b), "bb_bench_gemm: the TMA path declined this problem");
+        else if (use_tc) tc_gemm(c, gm, b);
+        else gemm_simt(c, gm, b);
+    };
+    for (int i = 0; i < 3; ++i) run();
     BB_CUDA(cudaEventRecord(e0, c.stream));
-    for (int i = 0; i < iters; ++i) { GemmArgs b = a; if (use_tc) tc_gemm(c, gm, b); else gemm_simt(c, gm, b); }
+    for (int i = 0; i < iters; ++i) run();
     BB_CUDA(cudaEventRecord(e1, c.stream));
     BB_CUDA(cudaStreamSynchronize(c.stream));
     float ms = 0.f;
     BB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *ms_out = ms / iters;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(c.ws);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); c.free_scratch();
     BB_CHECK(tc_error_flag() == 0, "tcgen05 pipeline timed out (g_tc_error)");
+    check_device_error("bb_bench_gemm");
     BB_API_END
 }
 

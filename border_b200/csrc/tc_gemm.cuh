@@ -128,6 +128,24 @@ __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 1
 
 }  // namespace tc
 
+// A operand in tensor memory (used by conv1_tc.cu): register -> TMEM stores and the [a_tmem] MMA form
+namespace tc3 {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::
+            "r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+}  // namespace tc3
+
 // A_KSRC: A(m,k) is k-contiguous (dense rows or gather rowbase[m] + koff[k]); else A(m,k) = A[k*lda + m].
 // B_KSRC: B(k,n) = B[n*ldb + k]; else n-contiguous (dense B[k*ldb + n] or gather rowbase[k] + noff[n]).
 // STAGES shared-memory stages, PF register sets of prefetched operand data per producer thread,
@@ -486,6 +504,10 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                         v.z = k4[gi].z > 0.f ? v.z : 0.f; v.w = k4[gi].w > 0.f ? v.w : 0.f;
                     }
                     *reinterpret_cast<float4*>(out + rowo + colo[gi]) = v;
+                    if (direct && g.c_plane)
+                        *reinterpret_cast<float4*>(out + g.c_plane + rowo + colo[gi]) =
+                            make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                                        v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
                 }
             }
         } else {
@@ -526,6 +548,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, MINB) tc_gemm_kernel(GemmArgs g)
                             continue;
                         }
                         float* dst = out + rowo + colo;
+                        if (direct && g.c_plane)
+                            for (int j = 0; j < 4; ++j)
+                                if (n + j < g.N) dst[g.c_plane + j] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
                         if (n + 3 < g.N && (((rowo + colo) & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0))
                             *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                         else

@@ -1,0 +1,317 @@
+// tma_gemm.cu -- host side of the TMA-fed tcgen05 GEMM (tma_gemm.cuh): tensor-map construction and cache,
+// eligibility, tile / split-K choice, launch; plus the lo-plane helper kernels.
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
+#include "gemm.cuh"
+#include "nn.cuh"
+#include "tma_gemm.cuh"
+
+namespace bb {
+
+// ------------------------------------------------------------------------------- driver entry points
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static void* driver_fn(const char* name) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return fn;
+}
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn f = (EncodeTiledFn)driver_fn("cuTensorMapEncodeTiled");
+    return f;
+}
+static EncodeIm2colFn encode_im2col() {
+    static EncodeIm2colFn f = (EncodeIm2colFn)driver_fn("cuTensorMapEncodeIm2col");
+    return f;
+}
+
+// ------------------------------------------------------------------------------- tensor-map cache
+// A map depends only on (base pointer, geometry); the buffers of a workspace never move, so the ~30 maps of an update are
+// built once (first eager steps) and the CUDA graph keeps its own copies (they are __grid_constant__ kernel parameters).
+
+struct MapKey {
+    const void* p;
+    long v[16];
+    bool operator<(const MapKey& o) const {
+        if (p != o.p) return p < o.p;
+        return memcmp(v, o.v, sizeof(v)) < 0;
+    }
+};
+static std::map<MapKey, CUtensorMap>& map_cache() {
+    static std::map<MapKey, CUtensorMap> c;
+    return c;
+}
+static std::mutex g_map_mu;
+std::atomic<uint64_t> g_tma_launches{0}, g_tma_rejects{0};
+
+// dims/strides innermost first; strides in BYTES for dims 1..rank-1
+static bool tiled_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                      const uint32_t* box) {
+    MapKey k;
+    memset(&k, 0, sizeof(k));
+    k.p = base; k.v[0] = 100 + rank;
+    for (int i = 0; i < rank; ++i) { k.v[1 + i] = (long)dims[i]; k.v[6 + i] = (long)box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) k.v[11 + i] = (long)strides_b[i];
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = map_cache().find(k);
+    if (it != map_cache().end()) { *out = it->second; return true; }
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    cuuint64_t gd[5], gs[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_b[i];
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    map_cache()[k] = m;
+    *out = m;
+    return true;
+}
+
+// NHWC float tensor [N][H][W][C] walked by a KH x KW filter with traversal stride S (no padding): box = 32 channels x
+// `pixels` filter positions.  Bounding box of the filter base: lower corner 0, upper corner -(K-1).
+static bool im2col_map(CUtensorMap* out, const float* base, const TmaConv& cv, int pixels) {
+    MapKey k;
+    memset(&k, 0, sizeof(k));
+    k.p = base; k.v[0] = 200; k.v[1] = cv.N; k.v[2] = cv.H; k.v[3] = cv.W; k.v[4] = cv.C; k.v[5] = cv.KH; k.v[6] = cv.KW;
+    k.v[7] = cv.S; k.v[8] = pixels;
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = map_cache().find(k);
+    if (it != map_cache().end()) { *out = it->second; return true; }
+    EncodeIm2colFn enc = encode_im2col();
+    if (!enc) return false;
+    cuuint64_t gd[4] = {(cuuint64_t)cv.C, (cuuint64_t)cv.W, (cuuint64_t)cv.H, (cuuint64_t)cv.N};
+    cuuint64_t gs[3] = {(cuuint64_t)cv.C * 4, (cuuint64_t)cv.W * cv.C * 4, (cuuint64_t)cv.H * cv.W * cv.C * 4};
+    int lower[2] = {0, 0};
+    int upper[2] = {-(cv.KW - 1), -(cv.KH - 1)};
+    cuuint32_t es[4] = {1, (cuuint32_t)cv.S, (cuuint32_t)cv.S, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gd, gs, lower, upper, 32, (cuuint32_t)pixels, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    // Drivers up to 13.1 mis-encode im2col maps of tensors under 128 KiB (the same correction CUTLASS applies in
+    // cute/atom/copy_traits_sm90_im2col.hpp): clear bit 21 of the second descriptor word.
+    int drv = 0;
+    if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (size_t)cv.N * cv.H * cv.W * cv.C * 4 < 131072)
+        reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+    map_cache()[k] = m;
+    *out = m;
+    return true;
+}
+
+void tma_forget_maps() {  // buffers were freed: their addresses may be reused with another geometry (keys include the geometry, so
+                          // stale entries are harmless; this only bounds the cache)
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (map_cache().size() > 4096) map_cache().clear();
+}
+
+// ------------------------------------------------------------------------------- lo planes
+
+__global__ void make_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) lo[i] = tg::tf32_lo(x[i]);
+}
+void make_lo(const Ctx& c, const float* x, float* lo, size_t n) {
+    if (!n) return;
+    make_lo_kernel<<<(int)std::min<size_t>((n + 255) / 256, (size_t)c.sms * 8), 256, 0, c.stream>>>(x, lo, n);
+    BB_LAUNCHED();
+    c.mark("make_lo");
+}
+
+// ------------------------------------------------------------------------------- launch
+
+static int env_i(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int BN, int STAGES, int AK, int BKIND, int PASSES, int MINB>
+static void launch_one(const CUtensorMap& ta, const CUtensorMap& tal, const CUtensorMap& tb, const tg::Args& g, dim3 grid, cudaStream_t s) {
+    constexpr int NPL = PASSES == 3 ? 2 : 1;
+    constexpr size_t smem = (size_t)STAGES * NPL * (tg::BM * 128 + BN * 128) + 1024;
+    auto kern = tma_gemm_kernel<BN, STAGES, AK, BKIND, PASSES, MINB>;
+    static std::atomic<uint32_t> configured{0};  // bit per device: the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured.load() & (1u << dev))) {
+        BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.fetch_or(1u << dev);
+    }
+    launch_pdl(kern, grid, dim3(tg::NTHREADS), smem, s, ta, tal, tb, g);
+    BB_LAUNCHED();
+}
+
+template <int AK, int BKIND, int PASSES>
+static void launch_cfg(int BN, int cfg, const CUtensorMap& ta, const CUtensorMap& tal, const CUtensorMap& tb, const tg::Args& g, dim3 grid,
+                       cudaStream_t s) {
+    // cfg 0: deep ring, one CTA per SM; cfg 1: two co-resident CTAs with short rings (one's prologue / epilogue overlaps
+    // the other's main loop)
+    if (BN == 32) {
+        if (cfg == 1) launch_one<32, 2, AK, BKIND, PASSES, 2>(ta, tal, tb, g, grid, s);
+        else launch_one<32, 4, AK, BKIND, PASSES, 1>(ta, tal, tb, g, grid, s);
+    } else if (BN == 64) {
+        if (cfg == 1) launch_one<64, 2, AK, BKIND, PASSES, 2>(ta, tal, tb, g, grid, s);
+        else launch_one<64, 4, AK, BKIND, PASSES, 1>(ta, tal, tb, g, grid, s);
+    } else {
+        launch_one<128, 3, AK, BKIND, PASSES, 1>(ta, tal, tb, g, grid, s);
+    }
+}
+
+// false => not handled (the caller falls back to the SIMT-producer tcgen05 kernel or the CUDA-core tiles)
+bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
+    using namespace tg;
+    if (!env_i("BB_TMA", 1)) return false;
+    const int passes = env_i("BB_TMA_PASSES", 3) == 1 ? 1 : 3;
+    if (mode != G_FWD && mode != G_NN && mode != G_WGRAD) return false;
+    if (!c.tickets) return false;
+    if (!a.a_plane || !a.b_plane) return false;   // operands without lo planes
+    if ((a.a_plane & 3) || (a.b_plane & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return false;
+    if (a.c_rowoff && !a.tables_vec4) return false;
+    const bool a_gather = a.a_rowbase || a.a_koff;
+    if (a_gather && !a.a_conv) return false;
+    if (a.b_rowbase || a.b_noff) return false;
+    const float* A = reinterpret_cast<const float*>(a.A);
+    const float* B = reinterpret_cast<const float*>(a.B);
+    const uint32_t npl = passes == 3 ? 2u : 1u;
+
+    int AK, BKIND;
+    CUtensorMap ta, tal, tb;
+    memset(&ta, 0, sizeof(ta)); memset(&tal, 0, sizeof(tal)); memset(&tb, 0, sizeof(tb));
+    Args g;
+    memset(&g, 0, sizeof(g));
+    g.ga.flip_w = g.ga.flip_h = -1;
+    const int BN = a.N >= 64 ? 64 : 32;
+
+    // ---- A
+    if (mode == G_FWD || mode == G_NN) {
+        if (a.a_conv) {
+            const TmaConv& cv = *a.a_conv;
+            if (cv.C % 32) return false;
+            AK = OP_K_IM2COL;
+            const int OH = (cv.H - cv.KH) / cv.S + 1, OW = (cv.W - cv.KW) / cv.S + 1;
+            if (a.M != cv.N * OH * OW || a.K != cv.KH * cv.KW * cv.C) return false;
+            if (!im2col_map(&ta, A, cv, 128) || !im2col_map(&tal, A + a.a_plane, cv, 128)) { g_tma_rejects++; return false; }
+            g.ga.ow = OW; g.ga.ohw = OH * OW; g.ga.stride = cv.S; g.ga.kw = cv.KW; g.ga.cblocks = cv.C / 32;
+            if (cv.flip) { g.ga.flip_w = cv.KW - 1; g.ga.flip_h = cv.KH - 1; }
+        } else {
+            if (a.lda & 3) return false;
+            AK = OP_K_TILED;
+            uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.M, npl};
+            uint64_t st[2] = {(uint64_t)a.lda * 4, (uint64_t)a.a_plane * 4};
+            uint32_t box[3] = {32, 128, npl};
+            if (!tiled_map(&ta, A, 3, dims, st, box)) { g_tma_rejects++; return false; }
+        }
+    } else {  // G_WGRAD: A(m, k) m-contiguous
+        if (a.a_conv) {
+            // transposed im2col matrix: GEMM rows = (kh, kw, c), contraction over filter positions
+            const TmaConv& cv = *a.a_conv;
+            if (cv.C % 32) return false;
+            AK = OP_MN_IM2COL;
+            const int OH = (cv.H - cv.KH) / cv.S + 1, OW = (cv.W - cv.KW) / cv.S + 1;
+            if (a.K != cv.N * OH * OW || a.M != cv.KH * cv.KW * cv.C) return false;
+            if (!im2col_map(&ta, A, cv, 32) || !im2col_map(&tal, A + a.a_plane, cv, 32)) { g_tma_rejects++; return false; }
+            g.ga.ow = OW; g.ga.ohw = OH * OW; g.ga.stride = cv.S; g.ga.kw = cv.KW; g.ga.cblocks = cv.C / 32;
+            g.ga.nblocks = cv.KH * cv.KW * (cv.C / 32);
+        } else {
+            if ((a.lda & 3) || (a.M & 31)) return false;
+            AK = OP_MN_TILED;
+            uint64_t dims[4] = {32, (uint64_t)a.K, (uint64_t)a.M / 32, npl};
+            uint64_t st[3] = {(uint64_t)a.lda * 4, 128, (uint64_t)a.a_plane * 4};
+            uint32_t box[4] = {32, 32, 4, npl};
+            if (!tiled_map(&ta, A, 4, dims, st, box)) { g_tma_rejects++; return false; }
+        }
+    }
+    // ---- B
+    if (mode == G_FWD) {
+        if (a.ldb & 3) return false;
+        BKIND = OP_K_TILED;
+        uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.N, npl};
+        uint64_t st[2] = {(uint64_t)a.ldb * 4, (uint64_t)a.b_plane * 4};
+        uint32_t box[3] = {32, (uint32_t)BN, npl};
+        if (!tiled_map(&tb, B, 3, dims, st, box)) { g_tma_rejects++; return false; }
+    } else {
+        if ((a.ldb & 3) || (a.N & 31)) return false;
+        BKIND = OP_MN_TILED;
+        uint64_t dims[4] = {32, (uint64_t)a.K, (uint64_t)a.N / 32, npl};
+        uint64_t st[3] = {(uint64_t)a.ldb * 4, 128, (uint64_t)a.b_plane * 4};
+        uint32_t box[4] = {32, 32, (uint32_t)BN / 32, npl};
+        if (!tiled_map(&tb, B, 4, dims, st, box)) { g_tma_rejects++; return false; }
+    }
+
+    // ---- tiles and split-K (finished inside the kernel by the last CTA of each tile)
+    const int tm = (a.M + BM - 1) / BM, tn = (a.N + BN - 1) / BN;
+    const long tiles = (long)tm * tn;
+    const int nks = (a.K + BK - 1) / BK;
+    static const int fill_pct = env_i("BB_TMA_FILL", 100);
+    const long want = (long)c.sms * fill_pct / 100;
+    int split = 1;
+    if (tiles * 2 <= want && nks >= 8) {
+        split = (int)std::min<long>((want + tiles - 1) / tiles, nks / 4);
+        const size_t per = (size_t)a.M * a.N;
+        const size_t usable = c.ws_floats - 1024;
+        if (per * split > usable) split = (int)(usable / per);
+        if (split < 1) split = 1;
+    }
+    if (tiles > (long)c.n_tickets) split = 1;
+    int sps = (nks + split - 1) / split;
+    split = (nks + sps - 1) / sps;
+    g.M = a.M; g.N = a.N; g.K = a.K;
+    g.slices_per_split = sps; g.split_k = split;
+    g.C = a.C; g.c_plane = a.c_plane; g.ldc = a.ldc;
+    g.bias = a.bias; g.mask = a.mask; g.relu = a.relu; g.trans_out = a.trans_out;
+    g.c_rowoff = a.c_rowoff; g.c_coloff = a.c_coloff;
+    g.workspace = c.ws; g.counters = c.tickets; g.error = device_error_flag();
+    dim3 grid(tn, tm, split);
+    static const int cfg = env_i("BB_TMA_CFG", 0);
+    // debugging aid: BB_TMA_MASK bit i enables operand combination i (dense forward, conv forward / data gradient,
+    // linear data gradient, linear weight gradient, conv weight gradient); the others fall back to tc_gemm.cu
+    const int combo = (AK == OP_K_TILED && BKIND == OP_K_TILED) ? 0 : (AK == OP_K_IM2COL && BKIND == OP_K_TILED) ? 1
+                    : (AK == OP_K_TILED && BKIND == OP_MN_TILED) ? 2 : (AK == OP_MN_TILED && BKIND == OP_MN_TILED) ? 3
+                    : (AK == OP_MN_IM2COL && BKIND == OP_MN_TILED) ? 4 : 5;
+    if (!((env_i("BB_TMA_MASK", 0x1f) >> combo) & 1)) return false;
+
+#define BB_TMA_GO(AK_, BK_)                                                                       \
+    do {                                                                                          \
+        if (passes == 3) launch_cfg<AK_, BK_, 3>(BN, cfg, ta, tal, tb, g, grid, c.stream);        \
+        else launch_cfg<AK_, BK_, 1>(BN, cfg, ta, tal, tb, g, grid, c.stream);                    \
+    } while (0)
+    if (AK == OP_K_TILED && BKIND == OP_K_TILED) BB_TMA_GO(OP_K_TILED, OP_K_TILED);
+    else if (AK == OP_K_IM2COL && BKIND == OP_K_TILED) BB_TMA_GO(OP_K_IM2COL, OP_K_TILED);
+    else if (AK == OP_K_TILED && BKIND == OP_MN_TILED) BB_TMA_GO(OP_K_TILED, OP_MN_TILED);
+    else if (AK == OP_MN_TILED && BKIND == OP_MN_TILED) BB_TMA_GO(OP_MN_TILED, OP_MN_TILED);
+    else if (AK == OP_MN_IM2COL && BKIND == OP_MN_TILED) BB_TMA_GO(OP_MN_IM2COL, OP_MN_TILED);
+    else return false;
+#undef BB_TMA_GO
+    g_tma_launches++;
+    c.mark(BN == 32 ? "tma_gemm128x32" : "tma_gemm128x64");
+    return true;
+}
+
+}  // namespace bb
+
+// launches that took the TMA path / tensor-map constructions the driver rejected (tests assert the path is live)
+extern "C" int32_t bb_tma_stats(uint64_t* launches, uint64_t* rejects, int32_t reset) {
+    BB_API_BEGIN
+    if (launches) *launches = bb::g_tma_launches.load();
+    if (rejects) *rejects = bb::g_tma_rejects.load();
+    if (reset) { bb::g_tma_launches.store(0); bb::g_tma_rejects.store(0); }
+    BB_API_END
+}

@@ -1,0 +1,444 @@
+// tma_gemm.cuh -- TMA-fed tcgen05 tile GEMM, 3xTF32, warp-specialised (the round-2 replacement of tc_gemm.cuh's
+// SIMT producers).
+//
+// Same contraction as gemm.cuh / tc_gemm.cuh,  C[M,N] = sum_k A(m,k) B(k,n),  for the layers of border-tch-agent's
+// networks (cnn/base.rs:23-36 conv2d/linear, mlp/base.rs:13-41 linear) and the backward passes libtorch autograd
+// derives for opt.rs:74-83.  What changed is WHO moves the operands:
+//
+//   * every fp32 tensor a GEMM consumes carries a second "lo" plane next to it,  lo = x - tf32_trunc(x), written by
+//     whoever produces the tensor (GEMM epilogues, the Adam / Polyak kernels for the weights).  The tensor core
+//     ignores the low 13 mantissa bits of a TF32 operand, so the fp32 plane itself IS the "hi" operand:
+//     x*y ~= x.y + lo(x).y + x.lo(y)  with three tcgen05.mma.kind::tf32 products accumulated in fp32 (error ~2^-21,
+//     what keeps the 1e-4 loss parity with the libtorch-CPU oracle).
+//   * ONE thread issues cp.async.bulk.tensor (TMA) loads that land the tiles of both planes in shared memory in the
+//     canonical SWIZZLE_128B UMMA layouts -- tiled boxes for dense operands, im2col boxes (cuTensorMapEncodeIm2col)
+//     for the implicit-GEMM rows of a convolution -- and arms an mbarrier with the byte count.  No SIMT producer, no
+//     st.shared, no generic->async proxy fence.
+//   * ONE thread issues the MMAs (M = 128, K = 8 per instruction).  K-major operands (k contiguous in memory) and
+//     MN-major operands (m or n contiguous: weight gradients, the linear data gradient) both feed the tensor core
+//     directly: the instruction descriptor's major bits select the layout, nothing is transposed.
+//     "Stacked" 3xTF32: the hi and lo tiles of B are adjacent, so one descriptor spans [B_hi; B_lo] as 2*BN columns:
+//     A x [B_hi; B_lo] gives x.y in TMEM columns [0,BN) and x.lo(y) in [BN,2BN); lo(A) x B_hi accumulates into
+//     [0,BN).  tcgen05.commit hands the stage back to the TMA thread.
+//   * four epilogue warps read the accumulator (tcgen05.ld 32x32b), add the halves, apply bias / ReLU / ReLU-mask,
+//     and store C together with its lo plane (row-major, transposed, or through a separable output map).
+//   * split-K without a second launch: every split stores its partial tile, the LAST CTA of a tile (atomic ticket)
+//     adds the partials in split order -- deterministic -- and runs the epilogue.
+//
+// Tile 128 x BN x 32, STAGES-deep TMA ring, 192 threads.  Every mbarrier wait is bounded: a mis-programmed
+// pipeline raises the error flag (checked by the host after every update) instead of hanging the GPU.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace bb {
+namespace tg {
+
+constexpr int BM = 128, BK = 32, NTHREADS = 192;
+
+enum OpKind {
+    OP_K_TILED = 0,    // k contiguous, dense rows:            map (k, row, plane), box (32, rows, planes)
+    OP_K_IM2COL = 1,   // k contiguous, conv rows (A only):     im2col map (c, w, h, n), box 32 channels x 128 pixels
+    OP_MN_TILED = 2,   // m / n contiguous, dense:              map (32, k, mn/32, plane), box (32, 32, blocks, planes)
+    OP_MN_IM2COL = 3,  // m contiguous conv rows (A only):      im2col map, box 32 channels x 32 pixels per 32-row block
+};
+
+// Pixel traversal of an NHWC tensor the way an im2col tensor map walks it.
+struct Im2col {
+    int ow, ohw;         // filter positions per image row / per image
+    int stride;          // traversal stride (the convolution's stride)
+    int kw;              // filter taps per filter row (tap = kh * kw + kw)
+    int cblocks;         // 32-channel blocks per tap
+    int flip_w, flip_h;  // < 0: offset = tap coordinate; >= 0: offset = flip - tap coordinate (transposed convolution)
+    int nblocks;         // OP_MN_IM2COL: number of 32-row blocks (taps * cblocks)
+};
+
+struct Args {
+    int M, N, K;
+    int slices_per_split;  // k-slices of 32 per blockIdx.z
+    int split_k;
+    float* C;
+    long c_plane;          // != 0: also store lo(C) at C + c_plane
+    int ldc;
+    const float* bias;     // [N] or null
+    const float* mask;     // C *= (mask > 0), read through the same addressing as C; or null
+    int relu;
+    int trans_out;         // element (m, n) at C[n*ldc + m]
+    const int* c_rowoff;   // separable output map: element (m, n) at C[c_rowoff[m] + c_coloff[n]]
+    const int* c_coloff;
+    float* workspace;      // [split_k][M][N] partial tiles
+    unsigned int* counters;  // [tiles] tickets, zero between launches
+    int* error;            // device flag: a bounded wait timed out
+    Im2col ga;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.b32 %0, 1, 0, P1;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); ++it)
+        if (mbar_try_wait(bar, parity)) return true;
+    *reinterpret_cast<volatile int*>(err) = 1;  // pinned, mapped host memory (common.cuh: device_error_flag)
+    __threadfence_system();
+    return false;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
+        "{%7, %8};" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+
+// UMMA shared-memory descriptors, SWIZZLE_128B (layout type 2), descriptor version 1.
+//   K-major : rows of 128 B (32 tf32 along k), 8-row groups 1024 B apart (SBO); LBO unused.  k-step (8 tf32) = +32 B.
+//   MN-major: atoms of 8 k-rows x 128 B (32 tf32 along m/n); next 32 m/n = +LBO (4096 B: a [32 k][128 B] block), next 8 k =
+//             +SBO (1024 B).  k-step (8 k-rows) = +1024 B.
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+        "%14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// (n, h, w) of the filter base of linear position p
+__device__ __forceinline__ void pixel_of(const Im2col& g, int p, int& n, int& h, int& w) {
+    n = p / g.ohw;
+    const int r = p - n * g.ohw;
+    const int oh = r / g.ow;
+    h = oh * g.stride;
+    w = (r - oh * g.ow) * g.stride;
+}
+
+}  // namespace tg
+
+// PASSES = 3: 3xTF32 (fp32 parity); PASSES = 1: one TF32 product per fp32 product (the `fast` precision mode; only the
+// hi planes are loaded).
+template <int BN, int STAGES, int AK, int BKIND, int PASSES, int MINB>
+__global__ void __launch_bounds__(tg::NTHREADS, MINB)
+tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB, tg::Args g) {
+    using namespace tg;
+    static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
+    constexpr bool A_MN = AK == OP_MN_TILED || AK == OP_MN_IM2COL;
+    constexpr bool B_MN = BKIND == OP_MN_TILED;
+    constexpr int NPL = PASSES == 3 ? 2 : 1;                        // planes per operand in shared memory
+    constexpr uint32_t A_TILE = BM * 128, B_TILE = BN * 128;        // bytes per plane
+    constexpr uint32_t STAGE_BYTES = NPL * (A_TILE + B_TILE);
+    constexpr uint32_t ACC_COLS = PASSES == 3 ? 2 * BN : BN;
+    constexpr uint32_t TMEM_COLS = ACC_COLS < 32 ? 32 : ACC_COLS;
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nks_total = (g.K + BK - 1) / BK;
+    const int ks0 = blockIdx.z * g.slices_per_split;
+    const int nks = max(0, min(nks_total - ks0, g.slices_per_split));
+    const uint32_t tiles = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // SWIZZLE_128B atoms are 1024 B aligned
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&accum_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (AK == OP_K_IM2COL || AK == OP_MN_IM2COL) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    pdl_sync();  // barriers / tensor memory are set up while the previous kernel of the stream drains
+
+    if (warp == 0) {
+        // ================================================================ TMA producer (one thread)
+        if (lane == 0) {
+            int pn = 0, ph = 0, pw = 0;                 // OP_K_IM2COL: filter base of the tile's first row
+            if (AK == OP_K_IM2COL) pixel_of(g.ga, m0, pn, ph, pw);
+            int bc[4] = {0, 0, 0, 0};                    // OP_MN_IM2COL: channel / tap offsets of the tile's four 32-row blocks
+            uint16_t bw[4] = {0, 0, 0, 0}, bh[4] = {0, 0, 0, 0};
+            if (AK == OP_MN_IM2COL) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int q = min(m0 / 32 + j, g.ga.nblocks - 1);   // rows past M repeat the last block (never stored)
+                    const int tap = q / g.ga.cblocks;
+                    bc[j] = (q - tap * g.ga.cblocks) * 32;
+                    const int th = tap / g.ga.kw, tw = tap - th * g.ga.kw;
+                    bw[j] = (uint16_t)(g.ga.flip_w >= 0 ? g.ga.flip_w - tw : tw);
+                    bh[j] = (uint16_t)(g.ga.flip_h >= 0 ? g.ga.flip_h - th : th);
+                }
+            }
+            bool alive = true;
+            for (int i = 0; i < nks && alive; ++i) {
+                const int s = i % STAGES;
+                const uint32_t phs = (uint32_t)(i / STAGES) & 1u;
+                if (!mbar_wait(smem_u32(&empty_bar[s]), phs ^ 1u, g.error)) { alive = false; break; }
+                const uint32_t bar = smem_u32(&full_bar[s]);
+                mbar_expect_tx(bar, STAGE_BYTES);
+                const int ks = ks0 + i;
+                const uint32_t a_hi = tiles + s * STAGE_BYTES, b_hi = a_hi + NPL * A_TILE;
+                if (AK == OP_K_TILED) {
+                    tma_load_3d(a_hi, &tmA, bar, ks * BK, m0, 0);
+                } else if (AK == OP_MN_TILED) {
+                    tma_load_4d(a_hi, &tmA, bar, 0, ks * BK, m0 / 32, 0);
+                } else if (AK == OP_K_IM2COL) {
+                    const int tap = ks / g.ga.cblocks;
+                    const int c = (ks - tap * g.ga.cblocks) * 32;
+                    const int th = tap / g.ga.kw, tw = tap - th * g.ga.kw;
+                    const uint16_t ow_ = (uint16_t)(g.ga.flip_w >= 0 ? g.ga.flip_w - tw : tw);
+                    const uint16_t oh_ = (uint16_t)(g.ga.flip_h >= 0 ? g.ga.flip_h - th : th);
+                    tma_load_im2col(a_hi, &tmA, bar, c, pw, ph, pn, ow_, oh_);
+                    if (PASSES == 3) tma_load_im2col(a_hi + A_TILE, &tmA_lo, bar, c, pw, ph, pn, ow_, oh_);
+                } else {  // OP_MN_IM2COL: contraction over pixels, 32 per k-slice
+                    int n_, h_, w_;
+                    pixel_of(g.ga, ks * BK, n_, h_, w_);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        tma_load_im2col(a_hi + j * 4096, &tmA, bar, bc[j], w_, h_, n_, bw[j], bh[j]);
+                        if (PASSES == 3) tma_load_im2col(a_hi + A_TILE + j * 4096, &tmA_lo, bar, bc[j], w_, h_, n_, bw[j], bh[j]);
+                    }
+                }
+                if (BKIND == OP_K_TILED) tma_load_3d(b_hi, &tmB, bar, ks * BK, n0, 0);
+                else tma_load_4d(b_hi, &tmB, bar, 0, ks * BK, n0 / 32, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer (one thread)
+        if (lane == 0) {
+            // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), major bits 15 / 16 (1 = MN-major),
+            // N >> 3 at bit 17, M >> 4 at bit 24
+            constexpr uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                            ((uint32_t)(BM >> 4) << 24);
+            constexpr uint32_t idesc1 = idesc_base | ((uint32_t)(BN >> 3) << 17);
+            constexpr uint32_t idesc2 = idesc_base | ((uint32_t)((2 * BN) >> 3) << 17);
+            constexpr uint64_t a_adv = A_MN ? (1024 >> 4) : 2, b_adv = B_MN ? (1024 >> 4) : 2;
+            bool alive = true;
+            for (int i = 0; i < nks && alive; ++i) {
+                const int s = i % STAGES;
+                const uint32_t phs = (uint32_t)(i / STAGES) & 1u;
+                if (!mbar_wait(smem_u32(&full_bar[s]), phs, g.error)) { alive = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = tiles + s * STAGE_BYTES, b_hi = a_hi + NPL * A_TILE;
+                const uint64_t da_hi = A_MN ? desc_mn(a_hi) : desc_k(a_hi);
+                const uint64_t da_lo = A_MN ? desc_mn(a_hi + A_TILE) : desc_k(a_hi + A_TILE);
+                const uint64_t db = B_MN ? desc_mn(b_hi) : desc_k(b_hi);
+#pragma unroll
+                for (int k4 = 0; k4 < BK / 8; ++k4) {
+                    const uint32_t acc = (i | k4) ? 1u : 0u;
+                    if (PASSES == 3) {
+                        mma_tf32(tmem_base, da_hi + a_adv * k4, db + b_adv * k4, idesc2, acc);
+                        mma_tf32(tmem_base, da_lo + a_adv * k4, db + b_adv * k4, idesc1, 1u);
+                    } else {
+                        mma_tf32(tmem_base, da_hi + a_adv * k4, db + b_adv * k4, idesc1, acc);
+                    }
+                }
+                mma_commit(smem_u32(&empty_bar[s]));  // frees the stage once the MMAs above have read it
+            }
+            if (nks > 0) mma_commit(smem_u32(&accum_bar));
+        }
+    } else {
+        // ================================================================ epilogue (4 warps, one accumulator row per thread)
+        const int q = warp & 3;                      // the TMEM lane quarter this warp may read
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < g.M;
+        const bool split = g.split_k > 1;
+        const bool mapped = g.c_rowoff != nullptr;
+        const size_t rowo = row_ok ? (mapped ? (size_t)g.c_rowoff[m] : (g.trans_out ? (size_t)m : (size_t)m * g.ldc)) : 0;
+        // 16-byte vector stores / loads along n: plain row-major output with aligned rows, or a 4-contiguous output map
+        const bool vec = !g.trans_out && (g.N & 3) == 0 && (mapped || (g.ldc & 3) == 0) && (g.c_plane & 3) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(g.C) | reinterpret_cast<uintptr_t>(g.mask) | reinterpret_cast<uintptr_t>(g.bias)) & 15) == 0;
+
+        // final values of 16 consecutive columns of this thread's row -> C (+ lo plane)
+        auto emit = [&](int col, float* v) {
+            if (!row_ok) return;
+#pragma unroll
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+                const int n = n0 + col + j4;
+                if (n >= g.N) break;
+                const size_t colo = mapped ? (size_t)g.c_coloff[n] : (g.trans_out ? (size_t)n * g.ldc : (size_t)n);
+                if (vec) {
+                    float4 x = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+                    if (g.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+                        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+                    }
+                    if (g.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                    if (g.mask) {
+                        const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + rowo + colo));
+                        x.x = k.x > 0.f ? x.x : 0.f; x.y = k.y > 0.f ? x.y : 0.f; x.z = k.z > 0.f ? x.z : 0.f; x.w = k.w > 0.f ? x.w : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(g.C + rowo + colo) = x;
+                    if (g.c_plane)
+                        *reinterpret_cast<float4*>(g.C + g.c_plane + rowo + colo) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (n + j >= g.N) break;
+                        float x = v[j4 + j];
+                        const size_t o = rowo + (mapped ? (size_t)g.c_coloff[n + j] : (g.trans_out ? (size_t)(n + j) * g.ldc : (size_t)(n + j)));
+                        if (g.bias) x += g.bias[n + j];
+                        if (g.relu) x = fmaxf(x, 0.f);
+                        if (g.mask) x = g.mask[o] > 0.f ? x : 0.f;
+                        g.C[o] = x;
+                        if (g.c_plane) g.C[g.c_plane + o] = tf32_lo(x);
+                    }
+                }
+            }
+        };
+
+        bool alive = true;
+        if (nks > 0) alive = mbar_wait(smem_u32(&accum_bar), 0, g.error);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* part = split ? g.workspace + ((size_t)blockIdx.z * g.M + (row_ok ? m : 0)) * g.N : nullptr;
+        const bool pvec = (g.N & 3) == 0;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            if (nks > 0 && alive) {
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                tmem_ld16(ta, r);
+                if (PASSES == 3) {
+                    uint32_t r2[16];
+                    tmem_ld16(ta + BN, r2);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (!split) {
+                emit(c0, v);
+            } else if (row_ok) {
+#pragma unroll
+                for (int j4 = 0; j4 < 16; j4 += 4) {
+                    const int n = n0 + c0 + j4;
+                    if (n >= g.N) break;
+                    if (pvec) *reinterpret_cast<float4*>(part + n) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+                    else
+                        for (int j = 0; j < 4 && n + j < g.N; ++j) part[n + j] = v[j4 + j];
+                }
+            }
+        }
+        if (split) {
+            // the last CTA of this tile to arrive folds the partials in split order (deterministic) and runs the epilogue
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
+            if (tid == 64) {
+                const unsigned int t = atomicAdd(&g.counters[tile], 1u);
+                s_last = (t == (unsigned int)g.split_k - 1u) ? 1 : 0;
+                if (s_last) g.counters[tile] = 0u;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_last) {
+                __threadfence();
+                const size_t zs = (size_t)g.M * g.N;
+                const float* p0 = g.workspace + (size_t)(row_ok ? m : 0) * g.N;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    if (n0 + c0 >= g.N) break;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    if (row_ok) {
+                        for (int z = 0; z < g.split_k; ++z) {
+                            const float* pz = p0 + (size_t)z * zs + n0 + c0;
+#pragma unroll
+                            for (int j4 = 0; j4 < 16; j4 += 4) {
+                                if (n0 + c0 + j4 >= g.N) break;
+                                if (pvec) {
+                                    const float4 x = __ldcg(reinterpret_cast<const float4*>(pz + j4));
+                                    v[j4] += x.x; v[j4 + 1] += x.y; v[j4 + 2] += x.z; v[j4 + 3] += x.w;
+                                } else {
+                                    for (int j = 0; j < 4 && n0 + c0 + j4 + j < g.N; ++j) v[j4 + j] += __ldcg(pz + j4 + j);
+                                }
+                            }
+                        }
+                    }
+                    emit(c0, v);
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace bb

@@ -56,11 +56,15 @@ int32_t bb_device_count(int32_t* out);
 /* glibc powf restated on the device (sum_tree.rs:76,96,134,139 use f32::powf); test hook. */
 int32_t bb_test_powf(int32_t device, const float* host_x, const float* host_y, float* host_out, size_t n);
 
-/* Test hook: one dense GEMM on the device through the tcgen05 path (use_tc = 1), the fp32
- * CUDA-core path (0) or the shape dispatcher the layers use (2: skinny kernels / tcgen05 / CUDA-core tiles).  mode 0: C = A[M][K] B[N][K]^T (+bias, relu); 2: C = A[M][K] B[K][N];
+/* Test hook: one dense GEMM on the device through the SIMT-producer tcgen05 path (use_tc = 1), the fp32
+ * CUDA-core path (0), the shape dispatcher the layers use (2: skinny kernels / tcgen05 / CUDA-core tiles) or the
+ * TMA-fed tcgen05 kernel (3; operands get their lo planes, and for 2 and 3 the lo plane of C is verified).  mode 0: C = A[M][K] B[N][K]^T (+bias, relu); 2: C = A[M][K] B[K][N];
  * 3: C = A[K][M]^T B[K][N].  All pointers are host memory. */
 int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, int32_t N, int32_t K,
                      const float* A, const float* B, const float* bias, int32_t relu, float* C_out);
+
+/* GEMM launches that took the TMA-fed path / tensor-map constructions the driver refused, since the last reset. */
+int32_t bb_tma_stats(uint64_t* launches, uint64_t* rejects, int32_t reset);
 
 /* Timing hook: mean milliseconds of `iters` back-to-back launches of one dense GEMM. */
 int32_t bb_bench_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, int32_t N, int32_t K,
@@ -72,8 +76,6 @@ int32_t bb_bench_conv1(int32_t device, int32_t B, int32_t C, int32_t iters, floa
 
 /* Debug hook: clock64 stamps [2 roles][64 k-slices][4 points] of the last traced tcgen05 launch. */
 int32_t bb_debug_tc_trace(int64_t* out);
-/* the same for the experimental kernel variants (BB_TC_CFG 3..6, tc_gemm_variants.cu) */
-int32_t bb_debug_tc_trace_variants(int64_t* out);
 
 /* ------------------------------------------------------------------------------------------
  * Replay buffer: SimpleReplayBuffer<O, A> (border-core/src/generic_replay_buffer/base.rs:86-426)
