@@ -230,11 +230,11 @@ void Agent::load_params(const char* dir) {
             }
         }
         if (!f) throw Error("read failed: " + path);
-        BB_CUDA(cudaMemcpy(m->p, hp.data(), m->n * 4, cudaMemcpyHostToDevice));
+        h2d_sync(m->p, hp.data(), m->n * 4, ctx.stream);
         m->refresh_lo(ctx);
         if (m->has_opt && has_opt) {
-            BB_CUDA(cudaMemcpy(m->m, hm.data(), m->n * 4, cudaMemcpyHostToDevice));
-            BB_CUDA(cudaMemcpy(m->v, hv.data(), m->n * 4, cudaMemcpyHostToDevice));
+            h2d_sync(m->m, hm.data(), m->n * 4, ctx.stream);
+            h2d_sync(m->v, hv.data(), m->n * 4, ctx.stream);
             m->step = step;
         }
     }
@@ -456,7 +456,7 @@ int32_t bb_agent_set_param(bb_agent* a, const char* model, const char* name, con
     std::vector<float> tmp(pi->numel);
     bb::param_to_internal(*pi, host_in, tmp.data());
     BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
-    BB_CUDA(cudaMemcpy(m->p + pi->offset, tmp.data(), pi->numel * 4, cudaMemcpyHostToDevice));
+    bb::h2d_sync(m->p + pi->offset, tmp.data(), pi->numel * 4, ag.ctx.stream);
     bb::make_lo(ag.ctx, m->p + pi->offset, m->p_lo() + pi->offset, pi->numel);
     BB_API_END
 }
@@ -516,7 +516,7 @@ int32_t bb_agent_sync_model(bb_agent* a, const float* host_in, size_t n) {
         off += pi.numel;
     }
     BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
-    BB_CUDA(cudaMemcpy(m->p, h.data(), m->n * 4, cudaMemcpyHostToDevice));
+    bb::h2d_sync(m->p, h.data(), m->n * 4, ag.ctx.stream);
     m->refresh_lo(ag.ctx);
     BB_API_END
 }

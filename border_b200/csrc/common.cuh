@@ -130,6 +130,14 @@ int* device_error_flag();
 void check_device_error(const char* where);  // throws bb::Error when the flag is set
 
 cudaStream_t device_stream(int device);  // one non-blocking stream per (host thread, device)
+// Host -> device copy that later work on `s` (a NON-BLOCKING stream) is guaranteed to see.  A plain cudaMemcpy from
+// pageable memory returns once the data sits in the driver's staging buffer: the DMA itself is ordered on the legacy
+// default stream, which non-blocking streams do not wait for -- a kernel launched right after (the lo-plane refresh of
+// set_param) read the OLD parameter values.  Copy in stream order and wait for the stream.
+inline void h2d_sync(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    BB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    BB_CUDA(cudaStreamSynchronize(s));
+}
 void stream_wait(cudaStream_t waiter, cudaStream_t signaler);
 
 inline int num_sms(int device) {

@@ -1054,6 +1054,23 @@ const float* Net::forward(const Ctx& c, const float* p, const void* input, long 
         }
         x = w.act[i];
         ldx = (long)l.out_elems_per_sample;
+        if (p_plane && env_int("BB_DEBUG_CHECK_LO", 0)) {  // debugging aid: is the lo plane every producer must write really there?
+            const size_t n = (size_t)B * l.out_elems_per_sample;
+            std::vector<float> hx(n), hl(n);
+            BB_CUDA(cudaStreamSynchronize(c.stream));
+            BB_CUDA(cudaMemcpy(hx.data(), w.act[i], n * 4, cudaMemcpyDeviceToHost));
+            BB_CUDA(cudaMemcpy(hl.data(), w.act[i] + w.plane[i], n * 4, cudaMemcpyDeviceToHost));
+            size_t bad = 0, first = 0;
+            for (size_t j = 0; j < n; ++j) {
+                uint32_t u; memcpy(&u, &hx[j], 4); u &= 0xffffe000u;
+                float hi; memcpy(&hi, &u, 4);
+                if (hl[j] != hx[j] - hi) { if (!bad) first = j; ++bad; }
+            }
+            double sum = 0, sq = 0;
+            for (size_t j = 0; j < n; ++j) { sum += hx[j]; sq += (double)hx[j] * hx[j]; }
+            fprintf(stderr, "[check_lo] %s (stream %p): %zu / %zu lo values wrong (first at %zu: x %.9g lo %.9g)  sum %.12g sumsq %.12g  x[0..2] %.9g %.9g %.9g\n",
+                    c.layer.c_str(), (void*)c.stream, bad, n, first, bad ? hx[first] : 0.f, bad ? hl[first] : 0.f, sum, sq, hx[0], hx[1], hx[2]);
+        }
     }
     return w.act.back();
 }
@@ -1283,3 +1300,82 @@ void param_to_reference(const ParamInfo& pi, const float* internal, float* ref) 
 }
 
 }  // namespace bb
+
+// Test hook: ONE convolution layer (NHWC float input, [OC][KH][KW][C] weights) through the layer primitives, with
+// (use_tma = 1) or without the operands' lo planes, i.e. through the TMA-fed im2col kernels or the SIMT-producer ones.
+//   mode 0: Y[B][OH][OW][OC] = conv(X, W) + bias (no ReLU)      mode 1: dW[OC][KH][KW][C] from (dY, X)
+//   mode 2: dX[B][H][W][C] from (dY, W)
+// The layer is built as the second layer of a two-layer Net so that the production table / workspace code is what runs.
+extern "C" int32_t bb_test_conv(int32_t device, int32_t mode, int32_t use_tma, int32_t B, int32_t C, int32_t H, int32_t W,
+                                int32_t OC, int32_t k, int32_t s, const float* X, const float* Wt, const float* bias,
+                                const float* dY, float* out) {
+    BB_API_BEGIN
+    using namespace bb;
+    DeviceGuard dg(device);
+    Ctx c;
+    c.device = device; c.sms = num_sms(device); c.stream = device_stream(device);
+    c.alloc_scratch(8u << 20);
+    Net net;
+    add_conv(net, "a", C, H, W, C, 1, 1, false);   // placeholder producing the [B][H][W][C] input; never run
+    add_conv(net, "b", C, H, W, OC, k, s, false);
+    net.init_tables(device);
+    NetWorkspace w;
+    net.alloc_workspace(w, B, true);
+    const Layer& l = net.layers[1];
+    ConvGeom g = l.geom;
+    g.B = B; g.rowbase = w.rowbase[1];
+    g.dg_rowbase = w.dg_rowbase[1]; g.dg_crow = w.dg_crow[1]; g.dypad = w.dypad[1]; g.dg_wt = w.dg_wt[1];
+    const size_t nx = (size_t)B * H * W * C, ny = (size_t)B * g.OH * g.OW * OC, nw = (size_t)OC * k * k * C;
+    const size_t nwp = (nw + 3) / 4 * 4;
+    float* dW = dev_alloc<float>(2 * nwp);
+    float* dG = dev_alloc_zero<float>(nwp, c.stream);
+    float* dB = dev_alloc_zero<float>(OC, c.stream);
+    BB_CUDA(cudaMemcpyAsync(w.act[0], X, nx * 4, cudaMemcpyHostToDevice, c.stream));
+    BB_CUDA(cudaMemcpyAsync(dW, Wt, nw * 4, cudaMemcpyHostToDevice, c.stream));
+    if (bias) BB_CUDA(cudaMemcpyAsync(dB, bias, (size_t)OC * 4, cudaMemcpyHostToDevice, c.stream));
+    if (dY) BB_CUDA(cudaMemcpyAsync(w.dact[1], dY, ny * 4, cudaMemcpyHostToDevice, c.stream));
+    if (use_tma) {
+        make_lo(c, w.act[0], w.act[0] + w.plane[0], nx);
+        make_lo(c, dW, dW + nwp, nw);
+        if (dY) make_lo(c, w.dact[1], w.dact[1] + w.plane[1], ny);
+        g.x_plane = w.plane[0]; g.w_plane = (long)nwp; g.y_plane = w.plane[1]; g.dx_plane = w.plane[0];
+        g.dypad_plane = w.dypad_plane[1]; g.wt_plane = w.wt_plane[1];
+    }
+    size_t n_out = 0;
+    const float* src = nullptr;
+    auto run = [&]() {
+        if (mode == 0) {
+            conv_fwd(c, g, w.act[0], dW, bias ? dB : nullptr, w.act[1], false);
+            src = w.act[1]; n_out = ny;
+        } else if (mode == 1) {
+            conv_bwd_weight(c, g, w.dact[1], w.act[0], dG, nullptr);
+            src = dG; n_out = nw;
+        } else if (mode == 2) {
+            conv_bwd_data(c, g, w.dact[1], dW, w.col, w.dact[0], nullptr);
+            src = w.dact[0]; n_out = nx;
+        } else {
+            throw Error("bb_test_conv: mode must be 0, 1 or 2");
+        }
+    };
+    run();
+    if (int iters = env_int("BB_CONV_ITERS", 0)) {   // scratch timing of the layer (stderr)
+        cudaEvent_t e0, e1;
+        BB_CUDA(cudaEventCreate(&e0)); BB_CUDA(cudaEventCreate(&e1));
+        BB_CUDA(cudaEventRecord(e0, c.stream));
+        for (int i = 0; i < iters; ++i) run();
+        BB_CUDA(cudaEventRecord(e1, c.stream));
+        BB_CUDA(cudaStreamSynchronize(c.stream));
+        float ms = 0.f;
+        BB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        fprintf(stderr, "[conv timing] mode %d tma %d B %d C %d HxW %dx%d OC %d k %d s %d: %.1f us\n", mode, use_tma, B, C, H, W, OC, k, s,
+                ms * 1e3f / iters);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    BB_CUDA(cudaMemcpyAsync(out, src, n_out * 4, cudaMemcpyDeviceToHost, c.stream));
+    cudaError_t e = cudaStreamSynchronize(c.stream);
+    w.release(); net.free_tables();
+    cudaFree(dW); cudaFree(dG); cudaFree(dB); c.free_scratch();
+    BB_CUDA(e);
+    check_device_error("bb_test_conv");
+    BB_API_END
+}

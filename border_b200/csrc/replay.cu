@@ -822,7 +822,7 @@ void Replay::fill_synthetic(uint64_t n_rows, uint32_t n_actions, uint64_t seed) 
     BB_CUDA(cudaStreamSynchronize(stream));
     BB_CUDA(cudaMemcpy(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost));
     h.head = head; h.size = size;
-    BB_CUDA(cudaMemcpy(ctl, &h, sizeof(h), cudaMemcpyHostToDevice));
+    h2d_sync(ctl, &h, sizeof(h), stream);  // (a plain cudaMemcpy is not ordered against this non-blocking stream)
 }
 
 }  // namespace bb

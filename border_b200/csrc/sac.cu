@@ -269,7 +269,7 @@ struct Sac : Agent {
         BB_CUDA(cudaStreamSynchronize(ctx.stream));
         cudaFree(d_inject[slot]);
         d_inject[slot] = dev_alloc<float>(n);
-        BB_CUDA(cudaMemcpy(d_inject[slot], host, n * 4, cudaMemcpyHostToDevice));
+        h2d_sync(d_inject[slot], host, n * 4, ctx.stream);
         inject_n[slot] = n;
     }
 

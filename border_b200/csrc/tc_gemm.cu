@@ -144,7 +144,7 @@ extern "C" int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, in
     else if (mode == 3) { gm = G_WGRAD; a.lda = M; a.ldb = N; }
     else throw Error("bb_test_gemm: mode must be 0, 2 or 3");
     if (use_tc == 3) { a.a_plane = (long)na; a.b_plane = (long)nb; }
-    if (use_tc >= 2) a.c_plane = (long)nc;
+    if (use_tc == 3 || (use_tc == 2 && mode != 3)) a.c_plane = (long)nc;   // (weight gradients feed Adam only: the skinny wgrad kernel writes no lo plane)
     if (use_tc == 3) {
         BB_CHECK(tma_gemm(c, gm, a), "bb_test_gemm: the TMA path declined this problem");
     } else if (use_tc == 2) {
@@ -156,7 +156,7 @@ extern "C" int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, in
     }
     BB_CUDA(cudaMemcpyAsync(C_out, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost, c.stream));
     std::vector<float> lo;
-    if (use_tc >= 2) {
+    if (a.c_plane) {
         lo.resize((size_t)M * N);
         BB_CUDA(cudaMemcpyAsync(lo.data(), dC + nc, (size_t)M * N * 4, cudaMemcpyDeviceToHost, c.stream));
     }

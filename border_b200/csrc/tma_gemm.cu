@@ -60,10 +60,10 @@ std::atomic<uint64_t> g_tma_launches{0}, g_tma_rejects{0};
 
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1
 static bool tiled_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                      const uint32_t* box) {
+                      const uint32_t* box, bool mn_major = false) {
     MapKey k;
     memset(&k, 0, sizeof(k));
-    k.p = base; k.v[0] = 100 + rank;
+    k.p = base; k.v[0] = 100 + rank + (mn_major ? 50 : 0);
     for (int i = 0; i < rank; ++i) { k.v[1 + i] = (long)dims[i]; k.v[6 + i] = (long)box[i]; }
     for (int i = 0; i + 1 < rank; ++i) k.v[11 + i] = (long)strides_b[i];
     std::lock_guard<std::mutex> lk(g_map_mu);
@@ -76,9 +76,10 @@ static bool tiled_map(CUtensorMap* out, const void* base, int rank, const uint64
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_b[i];
     CUtensorMap m;
+    // MN-major 32-bit UMMA operands live in the 32-byte-atom flavour of the 128-byte swizzle (see tma_gemm.cuh: desc_mn)
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     map_cache()[k] = m;
     *out = m;
@@ -87,10 +88,10 @@ static bool tiled_map(CUtensorMap* out, const void* base, int rank, const uint64
 
 // NHWC float tensor [N][H][W][C] walked by a KH x KW filter with traversal stride S (no padding): box = 32 channels x
 // `pixels` filter positions.  Bounding box of the filter base: lower corner 0, upper corner -(K-1).
-static bool im2col_map(CUtensorMap* out, const float* base, const TmaConv& cv, int pixels) {
+static bool im2col_map(CUtensorMap* out, const float* base, const TmaConv& cv, int pixels, bool mn_major = false) {
     MapKey k;
     memset(&k, 0, sizeof(k));
-    k.p = base; k.v[0] = 200; k.v[1] = cv.N; k.v[2] = cv.H; k.v[3] = cv.W; k.v[4] = cv.C; k.v[5] = cv.KH; k.v[6] = cv.KW;
+    k.p = base; k.v[0] = mn_major ? 250 : 200; k.v[1] = cv.N; k.v[2] = cv.H; k.v[3] = cv.W; k.v[4] = cv.C; k.v[5] = cv.KH; k.v[6] = cv.KW;
     k.v[7] = cv.S; k.v[8] = pixels;
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = map_cache().find(k);
@@ -104,8 +105,8 @@ static bool im2col_map(CUtensorMap* out, const float* base, const TmaConv& cv, i
     cuuint32_t es[4] = {1, (cuuint32_t)cv.S, (cuuint32_t)cv.S, 1};
     CUtensorMap m;
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gd, gs, lower, upper, 32, (cuuint32_t)pixels, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     // Drivers up to 13.1 mis-encode im2col maps of tensors under 128 KiB (the same correction CUTLASS applies in
     // cute/atom/copy_traits_sm90_im2col.hpp): clear bit 21 of the second descriptor word.
@@ -198,7 +199,8 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     Args g;
     memset(&g, 0, sizeof(g));
     g.ga.flip_w = g.ga.flip_h = -1;
-    const int BN = a.N >= 64 ? 64 : 32;
+    int BN = a.N >= 64 ? 64 : 32;
+    if (env_i("BB_TMA_BN", 0) == 128 && a.N >= 128) BN = 128;   // experiment knob
 
     // ---- A
     if (mode == G_FWD || mode == G_NN) {
@@ -227,7 +229,7 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
             AK = OP_MN_IM2COL;
             const int OH = (cv.H - cv.KH) / cv.S + 1, OW = (cv.W - cv.KW) / cv.S + 1;
             if (a.K != cv.N * OH * OW || a.M != cv.KH * cv.KW * cv.C) return false;
-            if (!im2col_map(&ta, A, cv, 32) || !im2col_map(&tal, A + a.a_plane, cv, 32)) { g_tma_rejects++; return false; }
+            if (!im2col_map(&ta, A, cv, 32, true) || !im2col_map(&tal, A + a.a_plane, cv, 32, true)) { g_tma_rejects++; return false; }
             g.ga.ow = OW; g.ga.ohw = OH * OW; g.ga.stride = cv.S; g.ga.kw = cv.KW; g.ga.cblocks = cv.C / 32;
             g.ga.nblocks = cv.KH * cv.KW * (cv.C / 32);
         } else {
@@ -236,7 +238,7 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
             uint64_t dims[4] = {32, (uint64_t)a.K, (uint64_t)a.M / 32, npl};
             uint64_t st[3] = {(uint64_t)a.lda * 4, 128, (uint64_t)a.a_plane * 4};
             uint32_t box[4] = {32, 32, 4, npl};
-            if (!tiled_map(&ta, A, 4, dims, st, box)) { g_tma_rejects++; return false; }
+            if (!tiled_map(&ta, A, 4, dims, st, box, true)) { g_tma_rejects++; return false; }
         }
     }
     // ---- B
@@ -253,7 +255,7 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
         uint64_t dims[4] = {32, (uint64_t)a.K, (uint64_t)a.N / 32, npl};
         uint64_t st[3] = {(uint64_t)a.ldb * 4, 128, (uint64_t)a.b_plane * 4};
         uint32_t box[4] = {32, 32, (uint32_t)BN / 32, npl};
-        if (!tiled_map(&tb, B, 4, dims, st, box)) { g_tma_rejects++; return false; }
+        if (!tiled_map(&tb, B, 4, dims, st, box, true)) { g_tma_rejects++; return false; }
     }
 
     // ---- tiles and split-K (finished inside the kernel by the last CTA of each tile)
@@ -264,7 +266,9 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     const long want = (long)c.sms * fill_pct / 100;
     int split = 1;
     if (tiles * 2 <= want && nks >= 8) {
-        split = (int)std::min<long>((want + tiles - 1) / tiles, nks / 4);
+        // as many splits as keep every CTA of the launch resident at once (one per SM with the deep ring): a second,
+        // mostly empty wave doubled l1.fwd's time (160 CTAs on 148 SMs)
+        split = (int)std::min<long>(want / tiles, nks / 4);
         const size_t per = (size_t)a.M * a.N;
         const size_t usable = c.ws_floats - 1024;
         if (per * split > usable) split = (int)(usable / per);
@@ -282,11 +286,11 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     dim3 grid(tn, tm, split);
     static const int cfg = env_i("BB_TMA_CFG", 0);
     // debugging aid: BB_TMA_MASK bit i enables operand combination i (dense forward, conv forward / data gradient,
-    // linear data gradient, linear weight gradient, conv weight gradient); the others fall back to tc_gemm.cu
-    const int combo = (AK == OP_K_TILED && BKIND == OP_K_TILED) ? 0 : (AK == OP_K_IM2COL && BKIND == OP_K_TILED) ? 1
+    // linear data gradient, linear weight gradient, conv weight gradient, conv data gradient); the others fall back to tc_gemm.cu
+    const int combo = (AK == OP_K_TILED && BKIND == OP_K_TILED) ? 0 : (AK == OP_K_IM2COL && BKIND == OP_K_TILED) ? (g.ga.flip_w >= 0 ? 5 : 1)
                     : (AK == OP_K_TILED && BKIND == OP_MN_TILED) ? 2 : (AK == OP_MN_TILED && BKIND == OP_MN_TILED) ? 3
-                    : (AK == OP_MN_IM2COL && BKIND == OP_MN_TILED) ? 4 : 5;
-    if (!((env_i("BB_TMA_MASK", 0x1f) >> combo) & 1)) return false;
+                    : (AK == OP_MN_IM2COL && BKIND == OP_MN_TILED) ? 4 : 6;
+    if (!((env_i("BB_TMA_MASK", 0x3f) >> combo) & 1)) return false;
 
 #define BB_TMA_GO(AK_, BK_)                                                                       \
     do {                                                                                          \

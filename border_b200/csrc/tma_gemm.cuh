@@ -121,17 +121,20 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
         : "memory");
 }
 
-// UMMA shared-memory descriptors, SWIZZLE_128B (layout type 2), descriptor version 1.
-//   K-major : rows of 128 B (32 tf32 along k), 8-row groups 1024 B apart (SBO); LBO unused.  k-step (8 tf32) = +32 B.
-//   MN-major: atoms of 8 k-rows x 128 B (32 tf32 along m/n); next 32 m/n = +LBO (4096 B: a [32 k][128 B] block), next 8 k =
-//             +SBO (1024 B).  k-step (8 k-rows) = +1024 B.
+// UMMA shared-memory descriptors, descriptor version 1.
+//   K-major : SWIZZLE_128B (layout type 2; TMA CU_TENSOR_MAP_SWIZZLE_128B): rows of 128 B (32 tf32 along k), 8-row groups
+//             1024 B apart (SBO); LBO unused.  k-step (8 tf32) = +32 B.
+//   MN-major: 32-bit operands have exactly one legal MN-major layout, SWIZZLE_128B_BASE32B (layout type 1; TMA
+//             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: 32-byte chunks permuted inside each 128-byte row by (row & 3); measured on
+//             B200: with the 16-byte-atom swizzle the MMA returns zeros).  Atoms of 4 k-rows x 128 B (32 tf32 along m/n); next
+//             32 m/n = +LBO (4096 B: a [32 k][128 B] block), next 4 k = +SBO (512 B).  k-step (8 k-rows) = +1024 B.
 __device__ __forceinline__ uint64_t desc_k(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
 __device__ __forceinline__ uint64_t desc_mn(uint32_t addr) {
-    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)1 << 61);
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {

@@ -63,6 +63,13 @@ int32_t bb_test_powf(int32_t device, const float* host_x, const float* host_y, f
 int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, int32_t N, int32_t K,
                      const float* A, const float* B, const float* bias, int32_t relu, float* C_out);
 
+/* Test hook: one convolution layer (NHWC float X[B][H][W][C], weights [OC][k][k][C], stride s, no padding) through the layer
+ * primitives of the agents' networks, with (use_tma = 1) or without lo operand planes, i.e. on the TMA-fed im2col tcgen05
+ * kernels or the SIMT-producer ones.  mode 0: out = Y[B][OH][OW][OC] (+bias); 1: out = dW[OC][k][k][C] from (dY, X);
+ * 2: out = dX[B][H][W][C] from (dY, W).  Host pointers. */
+int32_t bb_test_conv(int32_t device, int32_t mode, int32_t use_tma, int32_t B, int32_t C, int32_t H, int32_t W, int32_t OC,
+                     int32_t k, int32_t s, const float* X, const float* Wt, const float* bias, const float* dY, float* out);
+
 /* GEMM launches that took the TMA-fed path / tensor-map constructions the driver refused, since the last reset. */
 int32_t bb_tma_stats(uint64_t* launches, uint64_t* rejects, int32_t reset);
 

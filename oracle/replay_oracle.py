@@ -130,6 +130,10 @@ class StdRng:
     def next_u32(self):
         return lib().bo_stdrng_next_u32(self._s)
 
+    def key_words(self):
+        """The 8 little-endian key words seed_from_u64 produced (first field of bo_stdrng)."""
+        return [int.from_bytes(bytes(self._s[4 * i:4 * i + 4]), "little") for i in range(8)]
+
 
 class FastRand:
     def __init__(self, seed):
