@@ -89,11 +89,13 @@ _P = C.c_void_p
 _SIGS = {
     "bb_last_error": (C.c_char_p, []),
     "bb_abi_version": (C.c_int32, []),
+    "bb_device_error": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32]),
     "bb_device_count": (C.c_int32, [C.POINTER(C.c_int32)]),
     "bb_test_powf": (C.c_int32, [C.c_int32, _P, _P, _P, C.c_size_t]),
     "bb_test_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P,
                                  C.c_int32, _P]),
     "bb_test_conv": (C.c_int32, [C.c_int32] * 10 + [_P] * 5),
+    "bb_tma_trace": (C.c_int32, [_P]),
     "bb_tma_stats": (C.c_int32, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int32]),
     "bb_bench_gemm": (C.c_int32, [C.c_int32] * 7 + [C.POINTER(C.c_float)]),
     "bb_debug_tc_trace": (C.c_int32, [_P]),

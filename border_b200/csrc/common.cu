@@ -70,6 +70,13 @@ int32_t bb_device_count(int32_t* out) {
     *out = n;
     BB_API_END
 }
+int32_t bb_device_error(int32_t* out, int32_t reset) {
+    BB_API_BEGIN
+    volatile int* f = bb::device_error_flag();
+    if (out) *out = *f;
+    if (reset) *f = 0;
+    BB_API_END
+}
 int32_t bb_kernel_launch_count(uint64_t* out, int32_t reset) {
     BB_API_BEGIN
     if (out) *out = bb::g_launch_count.load();

@@ -199,16 +199,16 @@ struct Dqn : Agent {
         const Ctx& tctx = conc ? *ctx.side[0] : ctx;
         if (conc) ctx.fork_to(tctx);
         ctx.phase = "fwd_online";
-        const float* q = net.forward(ctx, qnet.p, bv.obs, ld_in, B, ws_online, qnet.plane());         // :71-74
+        const float* q = net.forward(ctx, qnet.p, bv.obs, ld_in, B, ws_online);         // :71-74
         const float* q_next = nullptr;
         ctx.phase = "fwd_target";
         if (cfg.double_dqn) {                                                              // :93-99
             // online net on next_obs: borrow the target workspace first, keep its Q in d_scratch
-            const float* qn = net.forward(tctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt, qnet.plane());
+            const float* qn = net.forward(tctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt);
             BB_CUDA(cudaMemcpyAsync(d_scratch, qn, (size_t)B * net.out_dim * 4, cudaMemcpyDeviceToDevice, tctx.stream));
             q_next = d_scratch;
         }
-        const float* qt = net.forward(tctx, qnet_tgt.p, bv.next_obs, ld_in, B, ws_tgt, qnet_tgt.plane());  // :100-103
+        const float* qt = net.forward(tctx, qnet_tgt.p, bv.next_obs, ld_in, B, ws_tgt);  // :100-103
         if (conc) ctx.join_from(tctx);
         DqnLossParams lp;
         lp.q = q; lp.q_tgt = qt; lp.q_next = q_next; lp.act = (const long long*)bv.act;
@@ -232,7 +232,7 @@ struct Dqn : Agent {
         ctx.mark("d2h_32B");  // (profiled runs are serial: without its own mark the copy's latency lands on the next kernel)
         ctx.phase = "backward";
         // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
-        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0, qnet.plane());
+        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0);
         if (conc) ctx.join_from(rctx);  // (backward joins the side streams it used; this one may not be among them)
     }
 

@@ -586,7 +586,7 @@ void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float
         a.tables_vec4 = 1;  // OC % 4 == 0 and C % 4 == 0 (dgrad_gather_ok)
         // TMA form: a stride-1 im2col walk of the padded dY with the tap offsets running backwards
         const TmaConv cv{g.B, g.dg_hp(), g.dg_wp(), g.OC, Jh, Jw, 1, 1};
-        if (g.y_plane && g.dypad_plane) { a.a_conv = &cv; a.a_plane = g.dypad_plane; a.b_plane = g.wt_plane; }
+        a.a_conv = &cv; a.a_plane = g.dypad_plane; a.b_plane = g.wt_plane;
         a.c_plane = g.dx_plane;
         if (tma_gemm(c, G_FWD, a)) return;
         if (tc_gemm(c, G_FWD, a)) return;

@@ -6,9 +6,7 @@
 #include <map>
 #include <mutex>
 #include <vector>
-#include "gemm.cuh"
-#include "nn.cuh"
-#include "tma_gemm.cuh"
+#include "tma_gemm_launch.cuh"
 
 namespace bb {
 
@@ -136,43 +134,21 @@ void make_lo(const Ctx& c, const float* x, float* lo, size_t n) {
     c.mark("make_lo");
 }
 
+// ------------------------------------------------------------------------------- debug trace
+static long long* tma_trace_buffer() {
+    static long long* buf = nullptr;
+    if (!buf) {
+        BB_CUDA(cudaMalloc(&buf, 3 * 64 * 4 * sizeof(long long)));
+        BB_CUDA(cudaMemset(buf, 0, 3 * 64 * 4 * sizeof(long long)));
+    }
+    return buf;
+}
+
 // ------------------------------------------------------------------------------- launch
 
 static int env_i(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
-}
-
-template <int BN, int STAGES, int AK, int BKIND, int PASSES, int MINB>
-static void launch_one(const CUtensorMap& ta, const CUtensorMap& tal, const CUtensorMap& tb, const tg::Args& g, dim3 grid, cudaStream_t s) {
-    constexpr int NPL = PASSES == 3 ? 2 : 1;
-    constexpr size_t smem = (size_t)STAGES * NPL * (tg::BM * 128 + BN * 128) + 1024;
-    auto kern = tma_gemm_kernel<BN, STAGES, AK, BKIND, PASSES, MINB>;
-    static std::atomic<uint32_t> configured{0};  // bit per device: the attribute is per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(configured.load() & (1u << dev))) {
-        BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured.fetch_or(1u << dev);
-    }
-    launch_pdl(kern, grid, dim3(tg::NTHREADS), smem, s, ta, tal, tb, g);
-    BB_LAUNCHED();
-}
-
-template <int AK, int BKIND, int PASSES>
-static void launch_cfg(int BN, int cfg, const CUtensorMap& ta, const CUtensorMap& tal, const CUtensorMap& tb, const tg::Args& g, dim3 grid,
-                       cudaStream_t s) {
-    // cfg 0: deep ring, one CTA per SM; cfg 1: two co-resident CTAs with short rings (one's prologue / epilogue overlaps
-    // the other's main loop)
-    if (BN == 32) {
-        if (cfg == 1) launch_one<32, 2, AK, BKIND, PASSES, 2>(ta, tal, tb, g, grid, s);
-        else launch_one<32, 4, AK, BKIND, PASSES, 1>(ta, tal, tb, g, grid, s);
-    } else if (BN == 64) {
-        if (cfg == 1) launch_one<64, 2, AK, BKIND, PASSES, 2>(ta, tal, tb, g, grid, s);
-        else launch_one<64, 4, AK, BKIND, PASSES, 1>(ta, tal, tb, g, grid, s);
-    } else {
-        launch_one<128, 3, AK, BKIND, PASSES, 1>(ta, tal, tb, g, grid, s);
-    }
 }
 
 // false => not handled (the caller falls back to the SIMT-producer tcgen05 kernel or the CUDA-core tiles)
@@ -182,8 +158,6 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     const int passes = env_i("BB_TMA_PASSES", 3) == 1 ? 1 : 3;
     if (mode != G_FWD && mode != G_NN && mode != G_WGRAD) return false;
     if (!c.tickets) return false;
-    if (!a.a_plane || !a.b_plane) return false;   // operands without lo planes
-    if ((a.a_plane & 3) || (a.b_plane & 3)) return false;
     if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return false;
     if (a.c_rowoff && !a.tables_vec4) return false;
     const bool a_gather = a.a_rowbase || a.a_koff;
@@ -191,11 +165,10 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     if (a.b_rowbase || a.b_noff) return false;
     const float* A = reinterpret_cast<const float*>(a.A);
     const float* B = reinterpret_cast<const float*>(a.B);
-    const uint32_t npl = passes == 3 ? 2u : 1u;
 
     int AK, BKIND;
-    CUtensorMap ta, tal, tb;
-    memset(&ta, 0, sizeof(ta)); memset(&tal, 0, sizeof(tal)); memset(&tb, 0, sizeof(tb));
+    CUtensorMap ta, tb;
+    memset(&ta, 0, sizeof(ta)); memset(&tb, 0, sizeof(tb));
     Args g;
     memset(&g, 0, sizeof(g));
     g.ga.flip_w = g.ga.flip_h = -1;
@@ -210,16 +183,16 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
             AK = OP_K_IM2COL;
             const int OH = (cv.H - cv.KH) / cv.S + 1, OW = (cv.W - cv.KW) / cv.S + 1;
             if (a.M != cv.N * OH * OW || a.K != cv.KH * cv.KW * cv.C) return false;
-            if (!im2col_map(&ta, A, cv, 128) || !im2col_map(&tal, A + a.a_plane, cv, 128)) { g_tma_rejects++; return false; }
+            if (!im2col_map(&ta, A, cv, 128)) { g_tma_rejects++; return false; }
             g.ga.ow = OW; g.ga.ohw = OH * OW; g.ga.stride = cv.S; g.ga.kw = cv.KW; g.ga.cblocks = cv.C / 32;
             if (cv.flip) { g.ga.flip_w = cv.KW - 1; g.ga.flip_h = cv.KH - 1; }
         } else {
             if (a.lda & 3) return false;
             AK = OP_K_TILED;
-            uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.M, npl};
-            uint64_t st[2] = {(uint64_t)a.lda * 4, (uint64_t)a.a_plane * 4};
-            uint32_t box[3] = {32, 128, npl};
-            if (!tiled_map(&ta, A, 3, dims, st, box)) { g_tma_rejects++; return false; }
+            uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+            uint64_t st[1] = {(uint64_t)a.lda * 4};
+            uint32_t box[2] = {32, 128};
+            if (!tiled_map(&ta, A, 2, dims, st, box)) { g_tma_rejects++; return false; }
         }
     } else {  // G_WGRAD: A(m, k) m-contiguous
         if (a.a_conv) {
@@ -229,46 +202,48 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
             AK = OP_MN_IM2COL;
             const int OH = (cv.H - cv.KH) / cv.S + 1, OW = (cv.W - cv.KW) / cv.S + 1;
             if (a.K != cv.N * OH * OW || a.M != cv.KH * cv.KW * cv.C) return false;
-            if (!im2col_map(&ta, A, cv, 32, true) || !im2col_map(&tal, A + a.a_plane, cv, 32, true)) { g_tma_rejects++; return false; }
+            if (!im2col_map(&ta, A, cv, 32, true)) { g_tma_rejects++; return false; }
             g.ga.ow = OW; g.ga.ohw = OH * OW; g.ga.stride = cv.S; g.ga.kw = cv.KW; g.ga.cblocks = cv.C / 32;
             g.ga.nblocks = cv.KH * cv.KW * (cv.C / 32);
         } else {
             if ((a.lda & 3) || (a.M & 31)) return false;
             AK = OP_MN_TILED;
-            uint64_t dims[4] = {32, (uint64_t)a.K, (uint64_t)a.M / 32, npl};
-            uint64_t st[3] = {(uint64_t)a.lda * 4, 128, (uint64_t)a.a_plane * 4};
-            uint32_t box[4] = {32, 32, 4, npl};
-            if (!tiled_map(&ta, A, 4, dims, st, box, true)) { g_tma_rejects++; return false; }
+            uint64_t dims[3] = {32, (uint64_t)a.K, (uint64_t)a.M / 32};
+            uint64_t st[2] = {(uint64_t)a.lda * 4, 128};
+            uint32_t box[3] = {32, 32, 4};
+            if (!tiled_map(&ta, A, 3, dims, st, box, true)) { g_tma_rejects++; return false; }
         }
     }
     // ---- B
     if (mode == G_FWD) {
         if (a.ldb & 3) return false;
         BKIND = OP_K_TILED;
-        uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.N, npl};
-        uint64_t st[2] = {(uint64_t)a.ldb * 4, (uint64_t)a.b_plane * 4};
-        uint32_t box[3] = {32, (uint32_t)BN, npl};
-        if (!tiled_map(&tb, B, 3, dims, st, box)) { g_tma_rejects++; return false; }
+        uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+        uint64_t st[1] = {(uint64_t)a.ldb * 4};
+        uint32_t box[2] = {32, (uint32_t)BN};
+        if (!tiled_map(&tb, B, 2, dims, st, box)) { g_tma_rejects++; return false; }
     } else {
         if ((a.ldb & 3) || (a.N & 31)) return false;
         BKIND = OP_MN_TILED;
-        uint64_t dims[4] = {32, (uint64_t)a.K, (uint64_t)a.N / 32, npl};
-        uint64_t st[3] = {(uint64_t)a.ldb * 4, 128, (uint64_t)a.b_plane * 4};
-        uint32_t box[4] = {32, 32, (uint32_t)BN / 32, npl};
-        if (!tiled_map(&tb, B, 4, dims, st, box, true)) { g_tma_rejects++; return false; }
+        uint64_t dims[3] = {32, (uint64_t)a.K, (uint64_t)a.N / 32};
+        uint64_t st[2] = {(uint64_t)a.ldb * 4, 128};
+        uint32_t box[3] = {32, 32, (uint32_t)BN / 32};
+        if (!tiled_map(&tb, B, 3, dims, st, box, true)) { g_tma_rejects++; return false; }
     }
 
     // ---- tiles and split-K (finished inside the kernel by the last CTA of each tile)
     const int tm = (a.M + BM - 1) / BM, tn = (a.N + BN - 1) / BN;
     const long tiles = (long)tm * tn;
     const int nks = (a.K + BK - 1) / BK;
-    static const int fill_pct = env_i("BB_TMA_FILL", 100);
+    // The fp32 operand planes make these kernels L2-bandwidth bound (48 KB per 128x64x32 slice and CTA): beyond about half
+    // the SMs more CTAs add no throughput, only partial tiles for the finishing CTA to fold -- at most 16 splits.
+    static const int fill_pct = env_i("BB_TMA_FILL", 50);
     const long want = (long)c.sms * fill_pct / 100;
     int split = 1;
-    if (tiles * 2 <= want && nks >= 8) {
+    if (tiles * 2 <= want && nks >= 8 && !a.c_rowoff) {
         // as many splits as keep every CTA of the launch resident at once (one per SM with the deep ring): a second,
         // mostly empty wave doubled l1.fwd's time (160 CTAs on 148 SMs)
-        split = (int)std::min<long>(want / tiles, nks / 4);
+        split = (int)std::min<long>(std::min<long>(want / tiles, 16), nks / 4);
         const size_t per = (size_t)a.M * a.N;
         const size_t usable = c.ws_floats - 1024;
         if (per * split > usable) split = (int)(usable / per);
@@ -283,6 +258,7 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     g.bias = a.bias; g.mask = a.mask; g.relu = a.relu; g.trans_out = a.trans_out;
     g.c_rowoff = a.c_rowoff; g.c_coloff = a.c_coloff;
     g.workspace = c.ws; g.counters = c.tickets; g.error = device_error_flag();
+    g.trace = env_i("BB_TMA_TRACE", 0) ? tma_trace_buffer() : nullptr;
     dim3 grid(tn, tm, split);
     static const int cfg = env_i("BB_TMA_CFG", 0);
     // debugging aid: BB_TMA_MASK bit i enables operand combination i (dense forward, conv forward / data gradient,
@@ -292,24 +268,25 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
                     : (AK == OP_MN_IM2COL && BKIND == OP_MN_TILED) ? 4 : 6;
     if (!((env_i("BB_TMA_MASK", 0x3f) >> combo) & 1)) return false;
 
-#define BB_TMA_GO(AK_, BK_)                                                                       \
-    do {                                                                                          \
-        if (passes == 3) launch_cfg<AK_, BK_, 3>(BN, cfg, ta, tal, tb, g, grid, c.stream);        \
-        else launch_cfg<AK_, BK_, 1>(BN, cfg, ta, tal, tb, g, grid, c.stream);                    \
-    } while (0)
-    if (AK == OP_K_TILED && BKIND == OP_K_TILED) BB_TMA_GO(OP_K_TILED, OP_K_TILED);
-    else if (AK == OP_K_IM2COL && BKIND == OP_K_TILED) BB_TMA_GO(OP_K_IM2COL, OP_K_TILED);
-    else if (AK == OP_K_TILED && BKIND == OP_MN_TILED) BB_TMA_GO(OP_K_TILED, OP_MN_TILED);
-    else if (AK == OP_MN_TILED && BKIND == OP_MN_TILED) BB_TMA_GO(OP_MN_TILED, OP_MN_TILED);
-    else if (AK == OP_MN_IM2COL && BKIND == OP_MN_TILED) BB_TMA_GO(OP_MN_IM2COL, OP_MN_TILED);
-    else return false;
-#undef BB_TMA_GO
+    if (passes == 3) {
+        if (!launch_combo<3>(AK, BKIND, BN, cfg, ta, tb, g, grid, c.stream)) return false;
+    } else if (!tma_launch_fast(AK, BKIND, BN, cfg, ta, tb, g, grid, c.stream)) {
+        return false;
+    }
     g_tma_launches++;
     c.mark(BN == 32 ? "tma_gemm128x32" : "tma_gemm128x64");
     return true;
 }
 
 }  // namespace bb
+
+// clock64 stamps of CTA (0,0,0) of the last traced launch (BB_TMA_TRACE=1): [3 roles][64 slices][4]
+extern "C" int32_t bb_tma_trace(int64_t* out) {
+    BB_API_BEGIN
+    BB_CUDA(cudaDeviceSynchronize());
+    BB_CUDA(cudaMemcpy(out, bb::tma_trace_buffer(), 3 * 64 * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    BB_API_END
+}
 
 // launches that took the TMA path / tensor-map constructions the driver rejected (tests assert the path is live)
 extern "C" int32_t bb_tma_stats(uint64_t* launches, uint64_t* rejects, int32_t reset) {

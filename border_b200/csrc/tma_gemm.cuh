@@ -5,23 +5,26 @@
 // networks (cnn/base.rs:23-36 conv2d/linear, mlp/base.rs:13-41 linear) and the backward passes libtorch autograd
 // derives for opt.rs:74-83.  What changed is WHO moves the operands:
 //
-//   * every fp32 tensor a GEMM consumes carries a second "lo" plane next to it,  lo = x - tf32_trunc(x), written by
-//     whoever produces the tensor (GEMM epilogues, the Adam / Polyak kernels for the weights).  The tensor core
-//     ignores the low 13 mantissa bits of a TF32 operand, so the fp32 plane itself IS the "hi" operand:
-//     x*y ~= x.y + lo(x).y + x.lo(y)  with three tcgen05.mma.kind::tf32 products accumulated in fp32 (error ~2^-21,
-//     what keeps the 1e-4 loss parity with the libtorch-CPU oracle).
-//   * ONE thread issues cp.async.bulk.tensor (TMA) loads that land the tiles of both planes in shared memory in the
-//     canonical SWIZZLE_128B UMMA layouts -- tiled boxes for dense operands, im2col boxes (cuTensorMapEncodeIm2col)
-//     for the implicit-GEMM rows of a convolution -- and arms an mbarrier with the byte count.  No SIMT producer, no
-//     st.shared, no generic->async proxy fence.
+//   * ONE thread issues cp.async.bulk.tensor (TMA) loads that land the fp32 operand tiles in shared memory in the
+//     canonical swizzled UMMA layouts -- tiled boxes for dense operands, im2col boxes (cuTensorMapEncodeIm2col) for the
+//     implicit-GEMM rows of a convolution -- and arms an mbarrier with the byte count.  No SIMT global loads, no
+//     address tables.
+//   * 3xTF32 from ONE copy of the data: the tensor core ignores the low 13 mantissa bits of a TF32 operand (measured:
+//     bit-identical to an explicit truncation), so the fp32 tile itself IS the "hi" operand.  While the ring runs, the
+//     four epilogue warps -- idle until the accumulator is complete -- derive the "lo" tiles  lo = x - tf32_trunc(x)
+//     from the landed tile with a purely elementwise shared->shared pass (same swizzled position, so no layout
+//     knowledge), fence to the async proxy and hand the stage to the MMA thread.  x*y ~= x.y + lo(x).y + x.lo(y) with three
+//     tcgen05.mma.kind::tf32 products accumulated in fp32 (error ~2^-21, what keeps the 1e-4 loss parity with the
+//     libtorch-CPU oracle).  (Round-2 measurement: shipping a second lo plane through L2 instead made every layer
+//     L2-bandwidth bound -- 48 KB per 128x64x32 slice and CTA, ~1.3 GB per DQN step.)
 //   * ONE thread issues the MMAs (M = 128, K = 8 per instruction).  K-major operands (k contiguous in memory) and
 //     MN-major operands (m or n contiguous: weight gradients, the linear data gradient) both feed the tensor core
 //     directly: the instruction descriptor's major bits select the layout, nothing is transposed.
 //     "Stacked" 3xTF32: the hi and lo tiles of B are adjacent, so one descriptor spans [B_hi; B_lo] as 2*BN columns:
 //     A x [B_hi; B_lo] gives x.y in TMEM columns [0,BN) and x.lo(y) in [BN,2BN); lo(A) x B_hi accumulates into
 //     [0,BN).  tcgen05.commit hands the stage back to the TMA thread.
-//   * four epilogue warps read the accumulator (tcgen05.ld 32x32b), add the halves, apply bias / ReLU / ReLU-mask,
-//     and store C together with its lo plane (row-major, transposed, or through a separable output map).
+//   * the eight split warps then read the accumulator (tcgen05.ld 32x32b), add the halves, apply bias / ReLU /
+//     ReLU-mask, and store C (row-major, transposed, or through a separable output map).
 //   * split-K without a second launch: every split stores its partial tile, the LAST CTA of a tile (atomic ticket)
 //     adds the partials in split order -- deterministic -- and runs the epilogue.
 //
@@ -36,7 +39,7 @@
 namespace bb {
 namespace tg {
 
-constexpr int BM = 128, BK = 32, NTHREADS = 192;
+constexpr int BM = 128, BK = 32, NTHREADS = 320;   // TMA warp, MMA warp, 2 x 4 split / epilogue warps
 
 enum OpKind {
     OP_K_TILED = 0,    // k contiguous, dense rows:            map (k, row, plane), box (32, rows, planes)
@@ -71,10 +74,18 @@ struct Args {
     float* workspace;      // [split_k][M][N] partial tiles
     unsigned int* counters;  // [tiles] tickets, zero between launches
     int* error;            // device flag: a bounded wait timed out
+    long long* trace;      // debug (BB_TMA_TRACE=1): clock64 stamps of CTA (0,0,0): [role 0..2][slice < 64][4]
     Im2col ga;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one lane of the (converged) warp: the single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) go under it
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.b32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -91,15 +102,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code = 1) {
 #pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it)
         if (mbar_try_wait(bar, parity)) return true;
-    *reinterpret_cast<volatile int*>(err) = 1;  // pinned, mapped host memory (common.cuh: device_error_flag)
+    *reinterpret_cast<volatile int*>(err) = code;  // pinned, mapped host memory (common.cuh: device_error_flag)
     __threadfence_system();
     return false;
 }
 
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
@@ -143,6 +159,20 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* f) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::
+            "r"(taddr),
+        "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]), "f"(f[8]), "f"(f[9]), "f"(f[10]),
+        "f"(f[11]), "f"(f[12]), "f"(f[13]), "f"(f[14]), "f"(f[15])
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -173,19 +203,23 @@ __device__ __forceinline__ void pixel_of(const Im2col& g, int p, int& n, int& h,
 // hi planes are loaded).
 template <int BN, int STAGES, int AK, int BKIND, int PASSES, int MINB>
 __global__ void __launch_bounds__(tg::NTHREADS, MINB)
-tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmB, tg::Args g) {
+tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, tg::Args g) {
     using namespace tg;
     static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
     constexpr bool A_MN = AK == OP_MN_TILED || AK == OP_MN_IM2COL;
     constexpr bool B_MN = BKIND == OP_MN_TILED;
-    constexpr int NPL = PASSES == 3 ? 2 : 1;                        // planes per operand in shared memory
-    constexpr uint32_t A_TILE = BM * 128, B_TILE = BN * 128;        // bytes per plane
-    constexpr uint32_t STAGE_BYTES = NPL * (A_TILE + B_TILE);
+    constexpr uint32_t A_TILE = BM * 128, B_TILE = BN * 128;        // bytes of one fp32 tile
+    // shared-memory stage: [A][B][lo(B)] -- TMA fills A and B, the split warps derive lo(B) next to B (one descriptor
+    // then spans [B; lo(B)]) and put lo(A) into TENSOR memory (32 columns per stage: the MMA takes it from there)
+    constexpr uint32_t STAGE_BYTES = A_TILE + (PASSES == 3 ? 2 : 1) * B_TILE;
+    constexpr uint32_t TX_BYTES = A_TILE + B_TILE;
+    // accumulator columns: [0,BN) x.y + lo(x).y, [BN,2BN) x.lo(y); the epilogue adds the halves
     constexpr uint32_t ACC_COLS = PASSES == 3 ? 2 * BN : BN;
-    constexpr uint32_t TMEM_COLS = ACC_COLS < 32 ? 32 : ACC_COLS;
+    constexpr uint32_t ALO_COL0 = ACC_COLS;                          // first tensor-memory column of the lo(A) stages
+    constexpr uint32_t USED_COLS = ACC_COLS + (PASSES == 3 ? STAGES * 32 : 0);
+    constexpr uint32_t TMEM_COLS = USED_COLS <= 32 ? 32 : USED_COLS <= 64 ? 64 : USED_COLS <= 128 ? 128 : USED_COLS <= 256 ? 256 : 512;
     extern __shared__ uint8_t smem_dyn[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+    __shared__ uint64_t full_bar[STAGES], ready_bar[STAGES], empty_bar[STAGES], accum_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_last;
 
@@ -199,13 +233,13 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&ready_bar[s]), 4);   // one arrive per split warp
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         mbar_init(smem_u32(&accum_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        if (AK == OP_K_IM2COL || AK == OP_MN_IM2COL) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -220,94 +254,184 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     pdl_sync();  // barriers / tensor memory are set up while the previous kernel of the stream drains
 
     if (warp == 0) {
-        // ================================================================ TMA producer (one thread)
-        if (lane == 0) {
-            int pn = 0, ph = 0, pw = 0;                 // OP_K_IM2COL: filter base of the tile's first row
-            if (AK == OP_K_IM2COL) pixel_of(g.ga, m0, pn, ph, pw);
-            int bc[4] = {0, 0, 0, 0};                    // OP_MN_IM2COL: channel / tap offsets of the tile's four 32-row blocks
-            uint16_t bw[4] = {0, 0, 0, 0}, bh[4] = {0, 0, 0, 0};
-            if (AK == OP_MN_IM2COL) {
+        // ================================================================ TMA producer
+        // The WHOLE warp walks the loop so that every coordinate / address is warp-uniform (uniform registers feed UTMALDG
+        // directly); only the instructions themselves sit under elect.sync.  Issued from inside an `if (lane == 0)` branch the
+        // operands live in vector registers and ptxas wraps every UTMALDG / UTCHMMA in an R2UR + ELECT "waterfall" loop:
+        // measured ~108 cycles per tcgen05.mma instead of ~55-64 (tools/tma_probe.cu, probe 4 vs probe 5).
+        int pn = 0, ph = 0, pw = 0;                 // OP_K_IM2COL: filter base of the tile's first row
+        if (AK == OP_K_IM2COL) pixel_of(g.ga, m0, pn, ph, pw);
+        int bc[4] = {0, 0, 0, 0};                    // OP_MN_IM2COL: channel / tap offsets of the tile's four 32-row blocks
+        int bw[4] = {0, 0, 0, 0}, bh[4] = {0, 0, 0, 0};
+        if (AK == OP_MN_IM2COL) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int q = min(m0 / 32 + j, g.ga.nblocks - 1);   // rows past M repeat the last block (never stored)
-                    const int tap = q / g.ga.cblocks;
-                    bc[j] = (q - tap * g.ga.cblocks) * 32;
-                    const int th = tap / g.ga.kw, tw = tap - th * g.ga.kw;
-                    bw[j] = (uint16_t)(g.ga.flip_w >= 0 ? g.ga.flip_w - tw : tw);
-                    bh[j] = (uint16_t)(g.ga.flip_h >= 0 ? g.ga.flip_h - th : th);
-                }
-            }
-            bool alive = true;
-            for (int i = 0; i < nks && alive; ++i) {
-                const int s = i % STAGES;
-                const uint32_t phs = (uint32_t)(i / STAGES) & 1u;
-                if (!mbar_wait(smem_u32(&empty_bar[s]), phs ^ 1u, g.error)) { alive = false; break; }
-                const uint32_t bar = smem_u32(&full_bar[s]);
-                mbar_expect_tx(bar, STAGE_BYTES);
-                const int ks = ks0 + i;
-                const uint32_t a_hi = tiles + s * STAGE_BYTES, b_hi = a_hi + NPL * A_TILE;
-                if (AK == OP_K_TILED) {
-                    tma_load_3d(a_hi, &tmA, bar, ks * BK, m0, 0);
-                } else if (AK == OP_MN_TILED) {
-                    tma_load_4d(a_hi, &tmA, bar, 0, ks * BK, m0 / 32, 0);
-                } else if (AK == OP_K_IM2COL) {
-                    const int tap = ks / g.ga.cblocks;
-                    const int c = (ks - tap * g.ga.cblocks) * 32;
-                    const int th = tap / g.ga.kw, tw = tap - th * g.ga.kw;
-                    const uint16_t ow_ = (uint16_t)(g.ga.flip_w >= 0 ? g.ga.flip_w - tw : tw);
-                    const uint16_t oh_ = (uint16_t)(g.ga.flip_h >= 0 ? g.ga.flip_h - th : th);
-                    tma_load_im2col(a_hi, &tmA, bar, c, pw, ph, pn, ow_, oh_);
-                    if (PASSES == 3) tma_load_im2col(a_hi + A_TILE, &tmA_lo, bar, c, pw, ph, pn, ow_, oh_);
-                } else {  // OP_MN_IM2COL: contraction over pixels, 32 per k-slice
-                    int n_, h_, w_;
-                    pixel_of(g.ga, ks * BK, n_, h_, w_);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        tma_load_im2col(a_hi + j * 4096, &tmA, bar, bc[j], w_, h_, n_, bw[j], bh[j]);
-                        if (PASSES == 3) tma_load_im2col(a_hi + A_TILE + j * 4096, &tmA_lo, bar, bc[j], w_, h_, n_, bw[j], bh[j]);
-                    }
-                }
-                if (BKIND == OP_K_TILED) tma_load_3d(b_hi, &tmB, bar, ks * BK, n0, 0);
-                else tma_load_4d(b_hi, &tmB, bar, 0, ks * BK, n0 / 32, 0);
+            for (int j = 0; j < 4; ++j) {
+                const int q = min(m0 / 32 + j, g.ga.nblocks - 1);   // rows past M repeat the last block (never stored)
+                const int tap = q / g.ga.cblocks;
+                bc[j] = (q - tap * g.ga.cblocks) * 32;
+                const int th = tap / g.ga.kw, tw = tap - th * g.ga.kw;
+                bw[j] = g.ga.flip_w >= 0 ? g.ga.flip_w - tw : tw;
+                bh[j] = g.ga.flip_h >= 0 ? g.ga.flip_h - th : th;
             }
         }
+        bool alive = true;
+        for (int i = 0; i < nks && alive; ++i) {
+            const int s = i % STAGES;
+            const uint32_t phs = (uint32_t)(i / STAGES) & 1u;
+            const bool tr0 = g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i < 64 && lane == 0;
+            if (tr0) g.trace[(0 * 64 + i) * 4 + 0] = clock64();
+            if (!mbar_wait(smem_u32(&empty_bar[s]), phs ^ 1u, g.error, 11)) { alive = false; break; }
+            if (tr0) g.trace[(0 * 64 + i) * 4 + 1] = clock64();
+            const uint32_t bar = smem_u32(&full_bar[s]);
+            const int ks = ks0 + i;
+            const uint32_t a_hi = tiles + s * STAGE_BYTES, b_hi = a_hi + A_TILE;
+            int c = 0, ow_ = 0, oh_ = 0, n_ = 0, h_ = 0, w_ = 0;
+            if (AK == OP_K_IM2COL) {
+                const int tap = ks / g.ga.cblocks;
+                c = (ks - tap * g.ga.cblocks) * 32;
+                const int th = tap / g.ga.kw, tw = tap - th * g.ga.kw;
+                ow_ = g.ga.flip_w >= 0 ? g.ga.flip_w - tw : tw;
+                oh_ = g.ga.flip_h >= 0 ? g.ga.flip_h - th : th;
+            } else if (AK == OP_MN_IM2COL) {   // contraction over pixels, 32 per k-slice
+                pixel_of(g.ga, ks * BK, n_, h_, w_);
+            }
+            if (elect_one()) {
+                mbar_expect_tx(bar, TX_BYTES);
+                if (AK == OP_K_TILED) {
+                    tma_load_2d(a_hi, &tmA, bar, ks * BK, m0);
+                } else if (AK == OP_MN_TILED) {
+                    tma_load_3d(a_hi, &tmA, bar, 0, ks * BK, m0 / 32);
+                } else if (AK == OP_K_IM2COL) {
+                    tma_load_im2col(a_hi, &tmA, bar, c, pw, ph, pn, (uint16_t)ow_, (uint16_t)oh_);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tma_load_im2col(a_hi + j * 4096, &tmA, bar, bc[j], w_, h_, n_, (uint16_t)bw[j], (uint16_t)bh[j]);
+                }
+                if (BKIND == OP_K_TILED) tma_load_2d(b_hi, &tmB, bar, ks * BK, n0);
+                else tma_load_3d(b_hi, &tmB, bar, 0, ks * BK, n0 / 32);
+            }
+            __syncwarp();
+            if (tr0) g.trace[(0 * 64 + i) * 4 + 2] = clock64();
+        }
+        // Producer tail: every tcgen05.commit of the ring must have ARRIVED before this CTA may exit.  The accumulator
+        // barrier the epilogue waits on is a different barrier: its arrival can be observed while the last stages' "empty"
+        // arrivals are still in flight, and they would then land in the shared memory of the NEXT CTA scheduled on this SM
+        // (same barrier addresses), flipping its phases -- measured as sporadic timeouts / wrong results whenever a grid had
+        // more CTAs than fit at once.
+        for (int i = max(0, nks - STAGES); i < nks && alive; ++i)
+            alive = mbar_wait(smem_u32(&empty_bar[i % STAGES]), (uint32_t)(i / STAGES) & 1u, g.error, 15);
     } else if (warp == 1) {
-        // ================================================================ MMA issuer (one thread)
-        if (lane == 0) {
-            // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), major bits 15 / 16 (1 = MN-major),
-            // N >> 3 at bit 17, M >> 4 at bit 24
-            constexpr uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                                            ((uint32_t)(BM >> 4) << 24);
-            constexpr uint32_t idesc1 = idesc_base | ((uint32_t)(BN >> 3) << 17);
-            constexpr uint32_t idesc2 = idesc_base | ((uint32_t)((2 * BN) >> 3) << 17);
-            constexpr uint64_t a_adv = A_MN ? (1024 >> 4) : 2, b_adv = B_MN ? (1024 >> 4) : 2;
-            bool alive = true;
-            for (int i = 0; i < nks && alive; ++i) {
-                const int s = i % STAGES;
-                const uint32_t phs = (uint32_t)(i / STAGES) & 1u;
-                if (!mbar_wait(smem_u32(&full_bar[s]), phs, g.error)) { alive = false; break; }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = tiles + s * STAGE_BYTES, b_hi = a_hi + NPL * A_TILE;
-                const uint64_t da_hi = A_MN ? desc_mn(a_hi) : desc_k(a_hi);
-                const uint64_t da_lo = A_MN ? desc_mn(a_hi + A_TILE) : desc_k(a_hi + A_TILE);
-                const uint64_t db = B_MN ? desc_mn(b_hi) : desc_k(b_hi);
+        // ================================================================ MMA issuer (warp-uniform loop, one elected lane issues)
+        // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), major bits 15 / 16 (1 = MN-major),
+        // N >> 3 at bit 17, M >> 4 at bit 24
+        constexpr uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                        ((uint32_t)(BM >> 4) << 24);
+        constexpr uint32_t idesc1 = idesc_base | ((uint32_t)(BN >> 3) << 17);
+        constexpr uint32_t idesc2 = idesc_base | ((uint32_t)((2 * BN) >> 3) << 17);
+        // lo(A) comes from tensor memory (lane = row, column = k): no A-major bit
+        constexpr uint32_t idesc_lo = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BM >> 4) << 24) |
+                                      ((uint32_t)(BN >> 3) << 17);
+        constexpr uint64_t a_adv = A_MN ? (1024 >> 4) : 2, b_adv = B_MN ? (1024 >> 4) : 2;
+        bool alive = true;
+        for (int i = 0; i < nks && alive; ++i) {
+            const int s = i % STAGES;
+            const uint32_t phs = (uint32_t)(i / STAGES) & 1u;
+            const bool tr1 = g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i < 64 && lane == 0;
+            if (tr1) g.trace[(1 * 64 + i) * 4 + 0] = clock64();
+            // 3 passes: the stage is ready once the split warps have derived its lo operands; 1 pass: as soon as the TMA data landed
+            if (!mbar_wait(smem_u32(PASSES == 3 ? &ready_bar[s] : &full_bar[s]), phs, g.error, 12)) { alive = false; break; }
+            if (tr1) g.trace[(1 * 64 + i) * 4 + 1] = clock64();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = tiles + s * STAGE_BYTES, b_hi = a_hi + A_TILE;
+            const uint64_t da_hi = A_MN ? desc_mn(a_hi) : desc_k(a_hi);
+            const uint64_t db = B_MN ? desc_mn(b_hi) : desc_k(b_hi);
+            const uint32_t a_lo = tmem_base + ALO_COL0 + (uint32_t)s * 32u;   // lo(A): 128 lanes x 32 columns of this stage
+            const uint32_t ebar = smem_u32(&empty_bar[s]);
+            if (elect_one()) {
 #pragma unroll
                 for (int k4 = 0; k4 < BK / 8; ++k4) {
                     const uint32_t acc = (i | k4) ? 1u : 0u;
                     if (PASSES == 3) {
-                        mma_tf32(tmem_base, da_hi + a_adv * k4, db + b_adv * k4, idesc2, acc);
-                        mma_tf32(tmem_base, da_lo + a_adv * k4, db + b_adv * k4, idesc1, 1u);
+                        mma_tf32(tmem_base, da_hi + a_adv * k4, db + b_adv * k4, idesc2, acc);            // x . [y; lo(y)]
+                        mma_tf32_ts(tmem_base, a_lo + (uint32_t)k4 * 8u, db + b_adv * k4, idesc_lo, 1u);   // lo(x) . y
                     } else {
                         mma_tf32(tmem_base, da_hi + a_adv * k4, db + b_adv * k4, idesc1, acc);
                     }
                 }
-                mma_commit(smem_u32(&empty_bar[s]));  // frees the stage once the MMAs above have read it
+                mma_commit(ebar);  // frees the stage once the MMAs above have read it
             }
-            if (nks > 0) mma_commit(smem_u32(&accum_bar));
+            __syncwarp();
+            if (tr1) g.trace[(1 * 64 + i) * 4 + 2] = clock64();
         }
+        if (nks > 0 && elect_one()) mma_commit(smem_u32(&accum_bar));
+        __syncwarp();
     } else {
-        // ================================================================ epilogue (4 warps, one accumulator row per thread)
-        const int q = warp & 3;                      // the TMEM lane quarter this warp may read
+        // ================================================================ split warps, then epilogue (2 groups of 4 warps)
+        // Measured (clock64 trace, tools/tma_trace.py): one group of four warps needs ~850 cycles per k-slice for the lo pass
+        // (loads, 48 subtractions, stores, tcgen05.wait::st + proxy fence + arrive) while the 8 MMAs of a slice issue in
+        // ~440: two groups take alternate slices.
+        const int q = warp & 3;                      // the TMEM lane quarter this warp may touch
+        const int grp = (warp - 2) >> 2;             // split group 0 / 1; in the epilogue: which half of the tile's columns
+        if (PASSES == 3) {
+            // lo operands of every landed stage.  lo(B): an elementwise pass over the B tile (16 bytes per thread and trip,
+            // consecutive lanes on consecutive addresses: conflict-free), same offset in the tile after it.  lo(A): thread =
+            // tile row = tensor-memory lane; it reads its 32 k-values of the swizzled tile and stores their lo parts into the
+            // stage's 32 tensor-memory columns.
+            const int te = (tid - 64) & 127;
+            const uint32_t row = (uint32_t)(q * 32 + lane);
+            bool alive_s = true;
+            for (int i = 0; i < nks && alive_s; ++i) {
+                const int s = i % STAGES;
+                const uint32_t phs = (uint32_t)(i / STAGES) & 1u;
+                const bool tr2 = g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i < 64 && tid == 64;
+                if (tr2) g.trace[(2 * 64 + i) * 4 + 0] = clock64();
+                // BOTH groups observe every phase of every "full" barrier, although a group only works on alternate slices: a
+                // parity wait can tell a phase from its neighbours only, and with an odd ring depth a group that skipped the
+                // other group's phase of a stage would take the completion of slice i - 2*STAGES for that of slice i (measured:
+                // sporadic stale tiles / timeouts as soon as CTAs queued behind each other)
+                if (!mbar_wait(smem_u32(&full_bar[s]), phs, g.error, 13)) { alive_s = false; break; }
+                if ((i & 1) != grp) continue;
+                if (tr2) g.trace[(2 * 64 + i) * 4 + 1] = clock64();
+                const uint32_t a_hi = tiles + s * STAGE_BYTES, b_hi = a_hi + A_TILE;
+                constexpr int B4 = B_TILE / 16 / 128;   // 16-byte groups of B per thread
+                float4 vb[B4];
+                float fa[32];
+#pragma unroll
+                for (int j = 0; j < B4; ++j)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vb[j].x), "=f"(vb[j].y), "=f"(vb[j].z), "=f"(vb[j].w) : "r"(b_hi + (uint32_t)(te + 128 * j) * 16u));
+                if (!A_MN) {
+                    // K-major SWIZZLE_128B: 16-byte chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(fa[4 * c]), "=f"(fa[4 * c + 1]), "=f"(fa[4 * c + 2]), "=f"(fa[4 * c + 3])
+                                     : "r"(a_hi + row * 128u + ((((uint32_t)c) ^ (row & 7u)) << 4)));
+                } else {
+                    // MN-major, 32-byte-atom swizzle: element (m, k) of 32-row block b = m / 32 sits at
+                    // b*4096 + k*128 + ((((m % 32) / 8) ^ (k & 3)) * 32) + (m % 8) * 4
+                    const uint32_t base = a_hi + (row >> 5) * 4096u + (row & 7u) * 4u, ch = (row & 31u) >> 3;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(fa[k]) : "r"(base + (uint32_t)k * 128u + ((ch ^ ((uint32_t)k & 3u)) << 5)));
+                }
+#pragma unroll
+                for (int j = 0; j < B4; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b_hi + B_TILE + (uint32_t)(te + 128 * j) * 16u), "f"(tf32_lo(vb[j].x)),
+                                 "f"(tf32_lo(vb[j].y)), "f"(tf32_lo(vb[j].z)), "f"(tf32_lo(vb[j].w))
+                                 : "memory");
+#pragma unroll
+                for (int k = 0; k < 32; ++k) fa[k] = tf32_lo(fa[k]);
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ALO_COL0 + (uint32_t)s * 32u;
+                tmem_st16(ta, fa);
+                tmem_st16(ta + 16, fa + 16);
+                if (tr2) g.trace[(2 * 64 + i) * 4 + 2] = clock64();
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores of lo(B) -> the tensor core's async proxy
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
+                if (tr2) g.trace[(2 * 64 + i) * 4 + 3] = clock64();
+            }
+        }
         const int m = m0 + q * 32 + lane;
         const bool row_ok = m < g.M;
         const bool split = g.split_k > 1;
@@ -356,12 +480,15 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         };
 
         bool alive = true;
-        if (nks > 0) alive = mbar_wait(smem_u32(&accum_bar), 0, g.error);
+        if (nks > 0) alive = mbar_wait(smem_u32(&accum_bar), 0, g.error, 14);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* part = split ? g.workspace + ((size_t)blockIdx.z * g.M + (row_ok ? m : 0)) * g.N : nullptr;
+        float* part_t = split ? g.workspace + (size_t)blockIdx.z * g.M * g.N + (row_ok ? m : 0) : nullptr;   // transposed output
         const bool pvec = (g.N & 3) == 0;
+        constexpr int HALF = BN / 2;
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int cc = 0; cc < HALF; cc += 16) {
+            const int c0 = grp * HALF + cc;
             uint32_t r[16];
             if (nks > 0 && alive) {
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -385,53 +512,110 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (!split) {
                 emit(c0, v);
             } else if (row_ok) {
+                // partial tile in C's logical layout: [m][n] (ld N), or [n][m] (ld M) for a transposed output, where consecutive
+                // lanes (rows m) then write consecutive addresses
+                if (g.trans_out) {
 #pragma unroll
-                for (int j4 = 0; j4 < 16; j4 += 4) {
-                    const int n = n0 + c0 + j4;
-                    if (n >= g.N) break;
-                    if (pvec) *reinterpret_cast<float4*>(part + n) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
-                    else
-                        for (int j = 0; j < 4 && n + j < g.N; ++j) part[n + j] = v[j4 + j];
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + c0 + j;
+                        if (n < g.N) part_t[(size_t)n * g.M] = v[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; j4 += 4) {
+                        const int n = n0 + c0 + j4;
+                        if (n >= g.N) break;
+                        if (pvec) *reinterpret_cast<float4*>(part + n) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+                        else
+                            for (int j = 0; j < 4 && n + j < g.N; ++j) part[n + j] = v[j4 + j];
+                    }
                 }
             }
         }
         if (split) {
-            // the last CTA of this tile to arrive folds the partials in split order (deterministic) and runs the epilogue
+            // The last CTA of this tile to arrive (atomic ticket) folds the partials in split order -- deterministic -- and runs
+            // the epilogue.  The fold is a coalesced pass over the tile with 16 independent 16-byte loads in flight per thread
+            // (4 positions x 4 splits): a thread-per-row walk took 300k cycles for 36 splits.
             __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
             if (tid == 64) {
                 const unsigned int t = atomicAdd(&g.counters[tile], 1u);
                 s_last = (t == (unsigned int)g.split_k - 1u) ? 1 : 0;
                 if (s_last) g.counters[tile] = 0u;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (s_last) {
                 __threadfence();
+                const bool tr = g.trans_out != 0;
+                const int ldp = tr ? g.M : g.N;                       // leading dimension of a partial
+                const int R0 = tr ? n0 : m0, C0 = tr ? m0 : n0;       // tile origin in the partial's (row, column) space
+                const int RT = tr ? BN : BM, CT = tr ? BM : BN;
+                const int Rmax = tr ? g.N : g.M, Cmax = tr ? g.M : g.N;
+                const int G = CT / 4;                                 // 16-byte groups per tile row
                 const size_t zs = (size_t)g.M * g.N;
-                const float* p0 = g.workspace + (size_t)(row_ok ? m : 0) * g.N;
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 16) {
-                    if (n0 + c0 >= g.N) break;
-                    float v[16];
+                const bool v4 = (ldp & 3) == 0;
+                const bool ov4 = (g.ldc & 3) == 0 && (g.c_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0;
+                const int te = tid - 64;
+                for (int base = 0; base < RT * G; base += 256 * 4) {
+                    float4 acc[4];
+                    const float* src[4];
+                    int rr[4], cc[4], nv[4];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                    if (row_ok) {
-                        for (int z = 0; z < g.split_k; ++z) {
-                            const float* pz = p0 + (size_t)z * zs + n0 + c0;
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = base + te + 256 * i;
+                        rr[i] = R0 + idx / G;
+                        cc[i] = C0 + (idx % G) * 4;
+                        nv[i] = (idx < RT * G && rr[i] < Rmax) ? min(4, Cmax - cc[i]) : 0;   // valid elements of the group
+                        src[i] = g.workspace + (size_t)rr[i] * ldp + cc[i];
+                        acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    for (int z0 = 0; z0 < g.split_k; z0 += 4) {
+                        float4 t[4][4];
 #pragma unroll
-                            for (int j4 = 0; j4 < 16; j4 += 4) {
-                                if (n0 + c0 + j4 >= g.N) break;
-                                if (pvec) {
-                                    const float4 x = __ldcg(reinterpret_cast<const float4*>(pz + j4));
-                                    v[j4] += x.x; v[j4 + 1] += x.y; v[j4 + 2] += x.z; v[j4 + 3] += x.w;
-                                } else {
-                                    for (int j = 0; j < 4 && n0 + c0 + j4 + j < g.N; ++j) v[j4 + j] += __ldcg(pz + j4 + j);
+                        for (int dz = 0; dz < 4; ++dz)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                t[dz][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (z0 + dz < g.split_k && nv[i] > 0) {
+                                    const float* pz = src[i] + (size_t)(z0 + dz) * zs;
+                                    if (v4 && nv[i] == 4) t[dz][i] = __ldcg(reinterpret_cast<const float4*>(pz));
+                                    else {
+                                        t[dz][i].x = __ldcg(pz);
+                                        if (nv[i] > 1) t[dz][i].y = __ldcg(pz + 1);
+                                        if (nv[i] > 2) t[dz][i].z = __ldcg(pz + 2);
+                                        if (nv[i] > 3) t[dz][i].w = __ldcg(pz + 3);
+                                    }
                                 }
+                            }
+#pragma unroll
+                        for (int dz = 0; dz < 4; ++dz)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) { acc[i].x += t[dz][i].x; acc[i].y += t[dz][i].y; acc[i].z += t[dz][i].z; acc[i].w += t[dz][i].w; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (nv[i] <= 0) continue;
+                        // element j of the group is (m, n) = tr ? (cc + j, rr) : (rr, cc + j); stored at C[m*ldc + n] / C[n*ldc + m]
+                        float x[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+                        const size_t o = (size_t)rr[i] * g.ldc + cc[i];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (j >= nv[i]) break;
+                            if (g.bias) x[j] += g.bias[tr ? rr[i] : cc[i] + j];
+                            if (g.relu) x[j] = fmaxf(x[j], 0.f);
+                            if (g.mask) x[j] = g.mask[o + j] > 0.f ? x[j] : 0.f;
+                        }
+                        if (ov4 && nv[i] == 4) {
+                            *reinterpret_cast<float4*>(g.C + o) = make_float4(x[0], x[1], x[2], x[3]);
+                            if (g.c_plane) *reinterpret_cast<float4*>(g.C + g.c_plane + o) = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
+                        } else {
+                            for (int j = 0; j < nv[i]; ++j) {
+                                g.C[o + j] = x[j];
+                                if (g.c_plane) g.C[g.c_plane + o + j] = tf32_lo(x[j]);
                             }
                         }
                     }
-                    emit(c0, v);
                 }
             }
         }

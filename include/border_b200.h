@@ -53,6 +53,9 @@ enum { BB_IQN_CONST10 = 0, BB_IQN_UNIFORM8 = 1, BB_IQN_UNIFORM10 = 2, BB_IQN_UNI
 const char* bb_last_error(void);
 int32_t bb_abi_version(void);
 int32_t bb_device_count(int32_t* out);
+/* Sticky device-side failure flag (0 = none): a bounded wait inside a kernel timed out (tcgen05 / TMA pipelines: 11 producer,
+ * 12 MMA issuer, 13 split warps, 14 epilogue; peer barrier: 21).  Every agent entry point checks it and fails loudly. */
+int32_t bb_device_error(int32_t* out, int32_t reset);
 /* glibc powf restated on the device (sum_tree.rs:76,96,134,139 use f32::powf); test hook. */
 int32_t bb_test_powf(int32_t device, const float* host_x, const float* host_y, float* host_out, size_t n);
 
@@ -69,6 +72,10 @@ int32_t bb_test_gemm(int32_t device, int32_t mode, int32_t use_tc, int32_t M, in
  * 2: out = dX[B][H][W][C] from (dY, W).  Host pointers. */
 int32_t bb_test_conv(int32_t device, int32_t mode, int32_t use_tma, int32_t B, int32_t C, int32_t H, int32_t W, int32_t OC,
                      int32_t k, int32_t s, const float* X, const float* Wt, const float* bias, const float* dY, float* out);
+
+/* Debug: clock64 stamps of CTA (0,0,0) of the last TMA GEMM launched with BB_TMA_TRACE=1: [3 roles: TMA producer, MMA issuer,
+ * split warp][64 k-slices][4 stamps]. */
+int32_t bb_tma_trace(int64_t* out);
 
 /* GEMM launches that took the TMA-fed path / tensor-map constructions the driver refused, since the last reset. */
 int32_t bb_tma_stats(uint64_t* launches, uint64_t* rejects, int32_t reset);

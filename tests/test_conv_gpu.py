@@ -37,7 +37,8 @@ GEOMS = [(32, 32, 20, 20, 64, 4, 2), (256, 32, 20, 20, 64, 4, 2), (32, 64, 9, 9,
 
 @pytest.mark.parametrize("use_tma", [1, 0])
 @pytest.mark.parametrize("geom", GEOMS)
-def test_conv_layer_matches_float64(geom, use_tma):
+def test_conv_layer_matches_float64(geom, use_tma, monkeypatch):
+    monkeypatch.setenv("BB_TMA", str(use_tma))   # 0: the SIMT-producer tcgen05 kernels (tc_gemm.cuh)
     B, Cc, H, W, OC, k, s = geom
     rng = np.random.default_rng(B + Cc + H)
     x = rng.standard_normal((B, H, W, Cc)).astype(np.float32)

@@ -33,3 +33,5 @@ obs = np.zeros((1, 4, 84, 84), np.uint8)
 t0 = time.time()
 for _ in range(500): agent.sample(obs)
 print("policy sample: %.1f us" % ((time.time() - t0) / 500 * 1e6))
+import ctypes as C
+e = C.c_int32(); L.check(L.lib().bb_device_error(C.byref(e), 0)); print("device error flag:", e.value)

@@ -119,6 +119,99 @@ __global__ void __launch_bounds__(128) mma_probe_kernel(const float* a_img, cons
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
 }
 
+// ---- probe 4: tcgen05.mma issue/execute throughput: R back-to-back MMAs on fixed shared-memory tiles, one CTA
+__global__ void __launch_bounds__(128) mma_rate_kernel(int N, int kind_bf16, int a_tmem, int reps, long long* cycles, int* err) {
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t tiles = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    float* sa = reinterpret_cast<float*>(smem_dyn + (tiles - smem_u32(smem_dyn)));
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) sa[i] = 0.f;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    if (threadIdx.x == 0) {
+        const uint32_t fmt = kind_bf16 ? 1u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (((uint32_t)N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t da = desc_k(tiles), db = desc_k(tiles + 16384);
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            const uint64_t adv = (uint64_t)((r & 3) * 2);
+            if (a_tmem) {
+                if (kind_bf16)
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem), "r"(tmem + 128u + (r & 3) * 8u), "l"(db + adv), "r"(idesc), "r"(1u) : "memory");
+                else
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem), "r"(tmem + 128u + (r & 3) * 8u), "l"(db + adv), "r"(idesc), "r"(1u) : "memory");
+            } else {
+                if (kind_bf16)
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem), "l"(da + adv), "l"(db + adv), "r"(idesc), "r"(1u) : "memory");
+                else
+                    mma_tf32(tmem, da + adv, db + adv, idesc, 1u);
+            }
+        }
+        long long t1 = clock64();
+        mma_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0, err);
+        long long t2 = clock64();
+        cycles[0] = t1 - t0;
+        cycles[1] = t2 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+// ---- probe 5: TWO warps of one CTA issuing tcgen05.mma concurrently into disjoint accumulator columns
+__global__ void __launch_bounds__(128) mma_rate2_kernel(int N, int issuers, int reps, long long* cycles, int* err) {
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t tiles = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    float* sa = reinterpret_cast<float*>(smem_dyn + (tiles - smem_u32(smem_dyn)));
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) sa[i] = 0.f;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bar[0]), 1);
+        mbar_init(smem_u32(&bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && w < issuers) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t da = desc_k(tiles), db = desc_k(tiles + 16384);
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            const uint64_t adv = (uint64_t)((r & 3) * 2);
+            mma_tf32(tmem + (uint32_t)w * 128u, da + adv, db + adv, idesc, 1u);
+        }
+        mma_commit(smem_u32(&bar[w]));
+        mbar_wait(smem_u32(&bar[w]), 0, err);
+        long long t2 = clock64();
+        cycles[w] = t2 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
 int main() {
     EncodeTiledFn enc_t = (EncodeTiledFn)drv("cuTensorMapEncodeTiled");
     EncodeIm2colFn enc_i = (EncodeIm2colFn)drv("cuTensorMapEncodeIm2col");
@@ -267,6 +360,65 @@ int main() {
             for (int i = 0; i < 128 * 64; ++i) { if (o[i] != ref[i]) ++bad; if (o[i] == 0.f) ++zeros; }
             printf("probe3 %-45s mismatches %5d / 8192  (zeros %d)  o[0..3] = %.0f %.0f %.0f %.0f  ref = %.0f %.0f %.0f %.0f\n", c.name, bad, zeros, o[0],
                    o[1], o[2], o[3], ref[0], ref[1], ref[2], ref[3]);
+        }
+    }
+    // ---------------- probe 4: MMA rate
+    {
+        CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        long long* dc;
+        CK(cudaMalloc(&dc, 16));
+        const int reps = 2048;
+        for (int bf = 0; bf < 2; ++bf)
+            for (int at = 0; at < 2; ++at)
+                for (int N : {64, 128, 256}) {
+                    for (int warm = 0; warm < 2; ++warm) {
+                        mma_rate_kernel<<<1, 128, 56 * 1024>>>(N, bf, at, reps, dc, err);
+                        CK(cudaDeviceSynchronize());
+                    }
+                    long long hc[2];
+                    CK(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+                    const double macs = 128.0 * N * (bf ? 16 : 8);
+                    printf("probe4 %s A-%s N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA -> %.0f MAC/cycle\n", bf ? "bf16" : "tf32", at ? "tmem" : "smem", N,
+                           (double)hc[0] / reps, (double)hc[1] / reps, macs / ((double)hc[1] / reps));
+                }
+        // one vs two CTAs per SM (wall time by events): is the ~108-cycle floor per issuing thread or per SM?
+        {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            for (int N : {64, 128}) {   // (N <= 128: accumulator + A columns fit 256 tensor-memory columns, two CTAs per SM)
+                for (int ctas : {148, 296, 444}) {
+                    mma_rate_kernel<<<ctas, 128, 56 * 1024>>>(N, 0, 0, reps, dc, err);
+                    CK(cudaDeviceSynchronize());
+                    cudaEventRecord(e0);
+                    mma_rate_kernel<<<ctas, 128, 56 * 1024>>>(N, 0, 0, reps, dc, err);
+                    cudaEventRecord(e1);
+                    CK(cudaDeviceSynchronize());
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    long long hc[2];
+                    CK(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+                    printf("probe4 tf32 N=%3d, %d CTAs: wall %.1f us, CTA 0: %.1f cyc/MMA\n", N, ctas, ms * 1e3, (double)hc[1] / reps);
+                }
+            }
+        }
+        CK(cudaFuncSetAttribute(mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        for (int N : {64, 128})
+            for (int iss : {1, 2}) {
+                for (int warm = 0; warm < 2; ++warm) {
+                    mma_rate2_kernel<<<1, 128, 56 * 1024>>>(N, iss, reps, dc, err);
+                    CK(cudaDeviceSynchronize());
+                }
+                long long hc[2];
+                CK(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+                printf("probe5 tf32 N=%3d, %d issuing warps in ONE CTA: %.1f / %.1f cyc per MMA per issuer\n", N, iss, (double)hc[0] / reps, (double)hc[iss - 1] / reps);
+            }
+        // many CTAs at once (one per SM): does the rate hold chip-wide (power / clocks)?
+        for (int N : {128, 256}) {
+            mma_rate_kernel<<<148, 128, 56 * 1024>>>(N, 0, 0, reps, dc, err);
+            CK(cudaDeviceSynchronize());
+            long long hc[2];
+            CK(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+            printf("probe4 tf32 A-smem N=%3d x148 CTAs: complete %.1f cyc/MMA\n", N, (double)hc[1] / reps);
         }
     }
     int herr = 0;
