@@ -172,8 +172,14 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     Args g;
     memset(&g, 0, sizeof(g));
     g.ga.flip_w = g.ga.flip_h = -1;
+    // One tcgen05.mma costs the issuing thread ~55-64 cycles whatever its width up to N = 128 (tools/tma_probe.cu), so wide
+    // layers take 128-column tiles: x.[y; lo(y)] becomes ONE N = 256 instruction.  (BB_TMA_BN=64 forces the narrow tile.)
+    // Only for grids of several waves, though: on the DQN shapes (a few hundred 128x64 tiles) the narrow tile measured faster
+    // (l1.fwd 24.8 vs 28.8 us, c2.dgrad 37.7 vs 40.9), on 8192^2 x 1024 the wide one (659 vs 719 us).
     int BN = a.N >= 64 ? 64 : 32;
-    if (env_i("BB_TMA_BN", 0) == 128 && a.N >= 128) BN = 128;   // experiment knob
+    if (a.N >= 128 && a.N % 128 == 0 && env_i("BB_TMA_BN", 128) == 128 &&
+        (long)((a.M + BM - 1) / BM) * ((a.N + 63) / 64) > 4L * c.sms)
+        BN = 128;
 
     // ---- A
     if (mode == G_FWD || mode == G_NN) {

@@ -111,6 +111,13 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
     return false;
 }
 
+// For the warp-uniform loops of the TMA / MMA warps ALL lanes poll.  (Letting one lane poll and broadcasting the result
+// makes the loop body divergent for ptxas again: the TMA / MMA operands fall back to vector registers and every UTCHMMA is
+// wrapped in an R2UR + ELECT loop -- measured 1030 instead of 480 cycles for the 8 MMAs of a k-slice.)
+__device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, int* err, int code) {
+    return mbar_wait(bar, parity, err, code);
+}
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                  "l"(map), "r"(bar), "r"(c0), "r"(c1)
@@ -252,6 +259,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     pdl_sync();  // barriers / tensor memory are set up while the previous kernel of the stream drains
+    if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) g.trace[(1 * 64 + 63) * 4 + 0] = clock64();
 
     if (warp == 0) {
         // ================================================================ TMA producer
@@ -280,7 +288,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t phs = (uint32_t)(i / STAGES) & 1u;
             const bool tr0 = g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i < 64 && lane == 0;
             if (tr0) g.trace[(0 * 64 + i) * 4 + 0] = clock64();
-            if (!mbar_wait(smem_u32(&empty_bar[s]), phs ^ 1u, g.error, 11)) { alive = false; break; }
+            if (!mbar_wait_warp(smem_u32(&empty_bar[s]), phs ^ 1u, g.error, 11)) { alive = false; break; }
             if (tr0) g.trace[(0 * 64 + i) * 4 + 1] = clock64();
             const uint32_t bar = smem_u32(&full_bar[s]);
             const int ks = ks0 + i;
@@ -319,7 +327,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // (same barrier addresses), flipping its phases -- measured as sporadic timeouts / wrong results whenever a grid had
         // more CTAs than fit at once.
         for (int i = max(0, nks - STAGES); i < nks && alive; ++i)
-            alive = mbar_wait(smem_u32(&empty_bar[i % STAGES]), (uint32_t)(i / STAGES) & 1u, g.error, 15);
+            alive = mbar_wait_warp(smem_u32(&empty_bar[i % STAGES]), (uint32_t)(i / STAGES) & 1u, g.error, 15);
     } else if (warp == 1) {
         // ================================================================ MMA issuer (warp-uniform loop, one elected lane issues)
         // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), major bits 15 / 16 (1 = MN-major),
@@ -339,7 +347,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const bool tr1 = g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i < 64 && lane == 0;
             if (tr1) g.trace[(1 * 64 + i) * 4 + 0] = clock64();
             // 3 passes: the stage is ready once the split warps have derived its lo operands; 1 pass: as soon as the TMA data landed
-            if (!mbar_wait(smem_u32(PASSES == 3 ? &ready_bar[s] : &full_bar[s]), phs, g.error, 12)) { alive = false; break; }
+            if (!mbar_wait_warp(smem_u32(PASSES == 3 ? &ready_bar[s] : &full_bar[s]), phs, g.error, 12)) { alive = false; break; }
             if (tr1) g.trace[(1 * 64 + i) * 4 + 1] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = tiles + s * STAGE_BYTES, b_hi = a_hi + A_TILE;
@@ -389,7 +397,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // parity wait can tell a phase from its neighbours only, and with an odd ring depth a group that skipped the
                 // other group's phase of a stage would take the completion of slice i - 2*STAGES for that of slice i (measured:
                 // sporadic stale tiles / timeouts as soon as CTAs queued behind each other)
-                if (!mbar_wait(smem_u32(&full_bar[s]), phs, g.error, 13)) { alive_s = false; break; }
+                if (!mbar_wait_warp(smem_u32(&full_bar[s]), phs, g.error, 13)) { alive_s = false; break; }
                 if ((i & 1) != grp) continue;
                 if (tr2) g.trace[(2 * 64 + i) * 4 + 1] = clock64();
                 const uint32_t a_hi = tiles + s * STAGE_BYTES, b_hi = a_hi + A_TILE;
@@ -432,59 +440,62 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (tr2) g.trace[(2 * 64 + i) * 4 + 3] = clock64();
             }
         }
-        const int m = m0 + q * 32 + lane;
-        const bool row_ok = m < g.M;
+        // ================================================================ epilogue (8 warps)
+        // Phase A: accumulator (tcgen05.ld, halves added) -> a staging tile in the now idle ring memory; thread = row, group =
+        // column half.  Phase B: a coalesced pass over the staged tile (16 bytes per thread and trip, consecutive lanes on
+        // consecutive addresses of C) applies bias / ReLU / ReLU-mask and stores C -- or the split-K partial.  (Storing straight
+        // from the row-per-thread registers cost 8000 cycles per 128x64 tile: every lane wrote its own 256-byte-strided row.)
+        // The storage space is (rr, cc) with cc contiguous: (m, n), or (n, m) for a transposed output.
         const bool split = g.split_k > 1;
+        const bool tr = g.trans_out != 0;
         const bool mapped = g.c_rowoff != nullptr;
-        const size_t rowo = row_ok ? (mapped ? (size_t)g.c_rowoff[m] : (g.trans_out ? (size_t)m : (size_t)m * g.ldc)) : 0;
-        // 16-byte vector stores / loads along n: plain row-major output with aligned rows, or a 4-contiguous output map
-        const bool vec = !g.trans_out && (g.N & 3) == 0 && (mapped || (g.ldc & 3) == 0) && (g.c_plane & 3) == 0 &&
-                         ((reinterpret_cast<uintptr_t>(g.C) | reinterpret_cast<uintptr_t>(g.mask) | reinterpret_cast<uintptr_t>(g.bias)) & 15) == 0;
+        const int te = tid - 64;                                 // 0..255
+        constexpr int LDN = BN + 4, LDT = BM + 4;                // padded row lengths of the staging tile (floats)
+        const uint32_t stg = tiles;
+        const int RT = tr ? BN : BM, CT = tr ? BM : BN;          // tile extent in storage space
+        const int R0 = tr ? n0 : m0, C0 = tr ? m0 : n0;
+        const int Rmax = tr ? g.N : g.M, Cmax = tr ? g.M : g.N;
+        const int G = CT / 4;                                    // 16-byte groups per staged row
+        const int ldp = tr ? g.M : g.N;                          // leading dimension of a split-K partial
+        const bool ov4 = (mapped || (g.ldc & 3) == 0) && (g.c_plane & 3) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(g.C) | reinterpret_cast<uintptr_t>(g.mask)) & 15) == 0;
 
-        // final values of 16 consecutive columns of this thread's row -> C (+ lo plane)
-        auto emit = [&](int col, float* v) {
-            if (!row_ok) return;
+        // final values of storage-space group (rr, cc .. cc+nv-1) -> C (+ lo plane)
+        auto store_final = [&](int rr, int cc, float4 a, int nv) {
+            float x[4] = {a.x, a.y, a.z, a.w};
+            const size_t o = mapped ? (size_t)g.c_rowoff[rr] + (size_t)g.c_coloff[cc] : (size_t)rr * g.ldc + cc;
 #pragma unroll
-            for (int j4 = 0; j4 < 16; j4 += 4) {
-                const int n = n0 + col + j4;
-                if (n >= g.N) break;
-                const size_t colo = mapped ? (size_t)g.c_coloff[n] : (g.trans_out ? (size_t)n * g.ldc : (size_t)n);
-                if (vec) {
-                    float4 x = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
-                    if (g.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-                        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-                    }
-                    if (g.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                    if (g.mask) {
-                        const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + rowo + colo));
-                        x.x = k.x > 0.f ? x.x : 0.f; x.y = k.y > 0.f ? x.y : 0.f; x.z = k.z > 0.f ? x.z : 0.f; x.w = k.w > 0.f ? x.w : 0.f;
-                    }
-                    *reinterpret_cast<float4*>(g.C + rowo + colo) = x;
-                    if (g.c_plane)
-                        *reinterpret_cast<float4*>(g.C + g.c_plane + rowo + colo) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (n + j >= g.N) break;
-                        float x = v[j4 + j];
-                        const size_t o = rowo + (mapped ? (size_t)g.c_coloff[n + j] : (g.trans_out ? (size_t)(n + j) * g.ldc : (size_t)(n + j)));
-                        if (g.bias) x += g.bias[n + j];
-                        if (g.relu) x = fmaxf(x, 0.f);
-                        if (g.mask) x = g.mask[o] > 0.f ? x : 0.f;
-                        g.C[o] = x;
-                        if (g.c_plane) g.C[g.c_plane + o] = tf32_lo(x);
-                    }
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nv) break;
+                if (g.bias) x[j] += g.bias[tr ? rr : cc + j];
+                if (g.relu) x[j] = fmaxf(x[j], 0.f);
+            }
+            if (ov4 && nv == 4) {
+                if (g.mask) {
+                    const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + o));
+                    x[0] = k.x > 0.f ? x[0] : 0.f; x[1] = k.y > 0.f ? x[1] : 0.f; x[2] = k.z > 0.f ? x[2] : 0.f; x[3] = k.w > 0.f ? x[3] : 0.f;
+                }
+                *reinterpret_cast<float4*>(g.C + o) = make_float4(x[0], x[1], x[2], x[3]);
+                if (g.c_plane) *reinterpret_cast<float4*>(g.C + g.c_plane + o) = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
+            } else {
+                for (int j = 0; j < nv; ++j) {
+                    const size_t oj = mapped ? (size_t)g.c_rowoff[rr] + (size_t)g.c_coloff[cc + j] : o + j;
+                    float y = x[j];
+                    if (g.mask) y = g.mask[oj] > 0.f ? y : 0.f;
+                    g.C[oj] = y;
+                    if (g.c_plane) g.C[g.c_plane + oj] = tf32_lo(y);
                 }
             }
         };
 
         bool alive = true;
-        if (nks > 0) alive = mbar_wait(smem_u32(&accum_bar), 0, g.error, 14);
+        const bool tr3 = g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 64;
+        if (tr3) g.trace[(2 * 64 + 63) * 4 + 0] = clock64();
+        if (nks > 0) alive = mbar_wait_warp(smem_u32(&accum_bar), 0, g.error, 14);
+        if (tr3) g.trace[(2 * 64 + 63) * 4 + 1] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* part = split ? g.workspace + ((size_t)blockIdx.z * g.M + (row_ok ? m : 0)) * g.N : nullptr;
-        float* part_t = split ? g.workspace + (size_t)blockIdx.z * g.M * g.N + (row_ok ? m : 0) : nullptr;   // transposed output
-        const bool pvec = (g.N & 3) == 0;
+        // ---- phase A
+        const uint32_t row = (uint32_t)(q * 32 + lane);
         constexpr int HALF = BN / 2;
 #pragma unroll
         for (int cc = 0; cc < HALF; cc += 16) {
@@ -506,36 +517,46 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 16; ++j) r[j] = 0u;
             }
-            float v[16];
+            if (!tr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                for (int j4 = 0; j4 < 16; j4 += 4)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (row * LDN + (uint32_t)(c0 + j4)) * 4u), "r"(r[j4]), "r"(r[j4 + 1]),
+                                 "r"(r[j4 + 2]), "r"(r[j4 + 3])
+                                 : "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + ((uint32_t)(c0 + j) * LDT + row) * 4u), "r"(r[j]) : "memory");
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // ---- phase B
+        float* part = split ? g.workspace + (size_t)blockIdx.z * g.M * g.N : nullptr;
+        const bool pv4 = (ldp & 3) == 0;
+        const uint32_t ldst = tr ? LDT : LDN;
+        for (int idx = te; idx < RT * G; idx += 256) {
+            const int rl = idx / G, cl = (idx - rl * G) * 4;
+            const int rr = R0 + rl, cc = C0 + cl;
+            if (rr >= Rmax || cc >= Cmax) continue;
+            const int nv = min(4, Cmax - cc);
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(stg + ((uint32_t)rl * ldst + (uint32_t)cl) * 4u));
             if (!split) {
-                emit(c0, v);
-            } else if (row_ok) {
-                // partial tile in C's logical layout: [m][n] (ld N), or [n][m] (ld M) for a transposed output, where consecutive
-                // lanes (rows m) then write consecutive addresses
-                if (g.trans_out) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + c0 + j;
-                        if (n < g.N) part_t[(size_t)n * g.M] = v[j];
-                    }
-                } else {
-#pragma unroll
-                    for (int j4 = 0; j4 < 16; j4 += 4) {
-                        const int n = n0 + c0 + j4;
-                        if (n >= g.N) break;
-                        if (pvec) *reinterpret_cast<float4*>(part + n) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
-                        else
-                            for (int j = 0; j < 4 && n + j < g.N; ++j) part[n + j] = v[j4 + j];
-                    }
+                store_final(rr, cc, x, nv);
+            } else {
+                float* pz = part + (size_t)rr * ldp + cc;
+                if (pv4 && nv == 4) *reinterpret_cast<float4*>(pz) = x;
+                else {
+                    pz[0] = x.x;
+                    if (nv > 1) pz[1] = x.y;
+                    if (nv > 2) pz[2] = x.z;
+                    if (nv > 3) pz[3] = x.w;
                 }
             }
         }
         if (split) {
             // The last CTA of this tile to arrive (atomic ticket) folds the partials in split order -- deterministic -- and runs
-            // the epilogue.  The fold is a coalesced pass over the tile with 16 independent 16-byte loads in flight per thread
-            // (4 positions x 4 splits): a thread-per-row walk took 300k cycles for 36 splits.
+            // the final epilogue: a coalesced pass with 16 independent 16-byte loads in flight per thread (4 positions x 4 splits).
             __threadfence();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
@@ -547,16 +568,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (s_last) {
                 __threadfence();
-                const bool tr = g.trans_out != 0;
-                const int ldp = tr ? g.M : g.N;                       // leading dimension of a partial
-                const int R0 = tr ? n0 : m0, C0 = tr ? m0 : n0;       // tile origin in the partial's (row, column) space
-                const int RT = tr ? BN : BM, CT = tr ? BM : BN;
-                const int Rmax = tr ? g.N : g.M, Cmax = tr ? g.M : g.N;
-                const int G = CT / 4;                                 // 16-byte groups per tile row
                 const size_t zs = (size_t)g.M * g.N;
-                const bool v4 = (ldp & 3) == 0;
-                const bool ov4 = (g.ldc & 3) == 0 && (g.c_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0;
-                const int te = tid - 64;
                 for (int base = 0; base < RT * G; base += 256 * 4) {
                     float4 acc[4];
                     const float* src[4];
@@ -579,7 +591,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 t[dz][i] = make_float4(0.f, 0.f, 0.f, 0.f);
                                 if (z0 + dz < g.split_k && nv[i] > 0) {
                                     const float* pz = src[i] + (size_t)(z0 + dz) * zs;
-                                    if (v4 && nv[i] == 4) t[dz][i] = __ldcg(reinterpret_cast<const float4*>(pz));
+                                    if (pv4 && nv[i] == 4) t[dz][i] = __ldcg(reinterpret_cast<const float4*>(pz));
                                     else {
                                         t[dz][i].x = __ldcg(pz);
                                         if (nv[i] > 1) t[dz][i].y = __ldcg(pz + 1);
@@ -594,35 +606,17 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             for (int i = 0; i < 4; ++i) { acc[i].x += t[dz][i].x; acc[i].y += t[dz][i].y; acc[i].z += t[dz][i].z; acc[i].w += t[dz][i].w; }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (nv[i] <= 0) continue;
-                        // element j of the group is (m, n) = tr ? (cc + j, rr) : (rr, cc + j); stored at C[m*ldc + n] / C[n*ldc + m]
-                        float x[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
-                        const size_t o = (size_t)rr[i] * g.ldc + cc[i];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (j >= nv[i]) break;
-                            if (g.bias) x[j] += g.bias[tr ? rr[i] : cc[i] + j];
-                            if (g.relu) x[j] = fmaxf(x[j], 0.f);
-                            if (g.mask) x[j] = g.mask[o + j] > 0.f ? x[j] : 0.f;
-                        }
-                        if (ov4 && nv[i] == 4) {
-                            *reinterpret_cast<float4*>(g.C + o) = make_float4(x[0], x[1], x[2], x[3]);
-                            if (g.c_plane) *reinterpret_cast<float4*>(g.C + g.c_plane + o) = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
-                        } else {
-                            for (int j = 0; j < nv[i]; ++j) {
-                                g.C[o + j] = x[j];
-                                if (g.c_plane) g.C[g.c_plane + o + j] = tf32_lo(x[j]);
-                            }
-                        }
-                    }
+                    for (int i = 0; i < 4; ++i)
+                        if (nv[i] > 0) store_final(rr[i], cc[i], acc[i], nv[i]);
                 }
             }
         }
     }
 
+    if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 64) g.trace[(2 * 64 + 63) * 4 + 2] = clock64();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 64) g.trace[(2 * 64 + 63) * 4 + 3] = clock64();
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }

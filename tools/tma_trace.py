@@ -17,3 +17,5 @@ for i in range(min(n, 24)):
     r = lambda a: (a - t0) if a else -1
     print("%3d | %6d %6d %6d | %6d %6d %6d | %6d %6d %6d %6d" % (i, r(t[0, i, 0]), r(t[0, i, 1]), r(t[0, i, 2]), r(t[1, i, 0]), r(t[1, i, 1]), r(t[1, i, 2]),
                                                              r(t[2, i, 0]), r(t[2, i, 1]), r(t[2, i, 2]), r(t[2, i, 3])))
+print("kernel body start %d | epilogue: wait accum %d, accum ready %d, stores done %d, after final sync %d" % (t[1, 63, 0] - t0, t[2, 63, 0] - t0, t[2, 63, 1] - t0, t[2, 63, 2] - t0, t[2, 63, 3] - t0))
+print("ms per GEMM (2 iterations, traced): %.4f" % ms.value)
