@@ -43,6 +43,10 @@ struct Args {
     float* Y;              // [M][32] NHWC
     long y_plane;          // != 0: also store lo(Y) = Y - tf32_trunc(Y) at Y + y_plane (operand plane of the next layer's TMA loads)
     const int* rowbase;    // [M]
+    // != null: image b of the batch is row ix[b] of X (the replay ring itself, base.rs:388-395 gather fused into the loader:
+    // no materialised batch); OHW = output positions per image
+    const unsigned long long* ix;
+    int OHW;
     int M, C, HW, W, relu;
     int n_tiles;
     int dbg;   // bench bisect: 1 no MMA, 2 no global loads, 4 no TMEM stores
@@ -133,6 +137,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv1_fwd_kernel(Args g) {
             const int m = t * 128 + row;
             if (m < g.M && !(g.dbg & 2)) {
                 const uint8_t* pc = g.X + (size_t)__ldg(g.rowbase + m) + (size_t)c * g.HW;
+                if (g.ix) {
+                    const int b = m / g.OHW;
+                    pc += ((long long)__ldg(g.ix + b) - (long long)b) * ((long long)g.C * g.HW);
+                }
 #pragma unroll
                 for (int kh = 0; kh < 8; ++kh) {
                     const uint32_t* pr = reinterpret_cast<const uint32_t*>(pc + kh * g.W);
@@ -271,6 +279,7 @@ struct Args {
     const float* dY;    // [B*OH*OW][32]
     float* part;        // [ctas][32][K] partial dW (already scaled by 1/255)
     int n_stages;       // B * OH / 2
+    const unsigned long long* ix;   // != null: image b is row ix[b] of X (see c1::Args)
     int C, HW, W, OHW /* OH*OW */, OW, OH2 /* OH/2 */;
     int dbg;
 };
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1_wgrad_kernel(Args g) {
         bool alive = true;
         auto load = [&](int st, uint32_t* w) {
             const int b = st / g.OH2, oh0 = (st % g.OH2) * 2;
-            const uint8_t* p0 = g.X + (size_t)b * g.C * g.HW + plane + (size_t)(oh0 * 4) * g.W;
+            const uint8_t* p0 = g.X + (size_t)(g.ix ? __ldg(g.ix + b) : (unsigned long long)b) * g.C * g.HW + plane + (size_t)(oh0 * 4) * g.W;
             const uint32_t* r0 = reinterpret_cast<const uint32_t*>(p0);
             const uint32_t* r1 = reinterpret_cast<const uint32_t*>(p0 + 4 * g.W);
 #pragma unroll
@@ -446,6 +455,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1_wgrad_kernel(Args g) {
 __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                       int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask, long c_plane);
 
+// Can BOTH dedicated kernels take this first layer?  Then the replay batch need not be materialised: they read the ring rows
+// through the sampled index list (ConvGeom::in_ix).
+bool conv1_direct_ok(const ConvGeom& g) {
+    const bool on = (getenv("BB_CONV1_TC") ? atoi(getenv("BB_CONV1_TC")) : 1) && (getenv("BB_TC") ? atoi(getenv("BB_TC")) : 1);
+    return on && g.u8_chw && g.KH == 8 && g.KW == 8 && g.S == 4 && g.OC == 32 && (g.C == 2 || g.C == 4) && (g.W & 3) == 0 &&
+           (g.OH & 1) == 0 && g.OW == 20 && g.M() >= 1024;
+}
+
 // dW[32][64C] of the AtariCnn first layer; false => geometry not handled (generic path).
 bool conv1_wgrad_tc(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW) {
     static const int on = getenv("BB_CONV1_TC") ? atoi(getenv("BB_CONV1_TC")) : 1;
@@ -453,7 +470,7 @@ bool conv1_wgrad_tc(const Ctx& c, const ConvGeom& g, const float* dY, const void
         g.OW != 20 || g.M() < 1024)
         return false;
     c1w::Args a;
-    a.X = (const uint8_t*)X; a.dY = dY; a.part = c.ws; a.n_stages = g.B * g.OH / 2; a.C = g.C; a.HW = g.H * g.W; a.W = g.W;
+    a.X = (const uint8_t*)X; a.dY = dY; a.part = c.ws; a.n_stages = g.B * g.OH / 2; a.ix = g.in_ix; a.C = g.C; a.HW = g.H * g.W; a.W = g.W;
     a.OHW = g.OH * g.OW; a.OW = g.OW; a.OH2 = g.OH / 2;
     static const int dbg = getenv("BB_CONV1_DEBUG") ? atoi(getenv("BB_CONV1_DEBUG")) : 0;
     a.dbg = dbg;
@@ -484,7 +501,7 @@ bool conv1_fwd_tc(const Ctx& c, const ConvGeom& g, const void* X, const float* W
     if (!on || !g.u8_chw || g.KH != 8 || g.KW != 8 || g.S != 4 || g.OC != 32 || g.C < 1 || g.C > 8 || (g.W & 3) || g.M() < 1024)
         return false;
     c1::Args a;
-    a.X = (const uint8_t*)X; a.Wt = W; a.bias = b; a.Y = Y; a.y_plane = g.y_plane; a.rowbase = g.rowbase; a.M = g.M(); a.C = g.C;
+    a.X = (const uint8_t*)X; a.Wt = W; a.bias = b; a.Y = Y; a.y_plane = g.y_plane; a.rowbase = g.rowbase; a.ix = g.in_ix; a.OHW = g.OH * g.OW; a.M = g.M(); a.C = g.C;
     a.HW = g.H * g.W; a.W = g.W; a.relu = relu ? 1 : 0; a.n_tiles = (a.M + 127) / 128;
     static const int dbg = getenv("BB_CONV1_DEBUG") ? atoi(getenv("BB_CONV1_DEBUG")) : 0;
     a.dbg = dbg;

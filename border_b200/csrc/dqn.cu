@@ -188,8 +188,13 @@ struct Dqn : Agent {
     // forwards, loss / TD kernel, backward.  Every kernel argument here is launch-invariant for a fixed
     // (replay, batch size, stream), so the sequence can be captured once and replayed as a CUDA graph.
     void enqueue_update(Replay& rb, int B, bool launch_sample, bb_batch_view& bv, bool capturing) {
+        // buffer.batch(self.batch_size), dqn/base.rs:62.  With the dedicated AtariCnn first-layer kernels the gather of
+        // base.rs:388-395 is fused into their loaders: only the indices and the small columns are produced here.
+        const bool direct = net.direct_input_ok(B) && !(getenv("BB_GATHER_DIRECT") && atoi(getenv("BB_GATHER_DIRECT")) == 0);
+        const unsigned long long* in_ix = nullptr;
         if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
-        rb.sample(B, &bv, launch_sample);  // buffer.batch(self.batch_size), dqn/base.rs:62
+        rb.sample(B, &bv, launch_sample, !direct);
+        if (direct) in_ix = (const unsigned long long*)bv.ix_sample;
         if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
         ctx.phase = "replay"; ctx.layer = "batch";
         ctx.mark("sample_gather");
@@ -199,16 +204,16 @@ struct Dqn : Agent {
         const Ctx& tctx = conc ? *ctx.side[0] : ctx;
         if (conc) ctx.fork_to(tctx);
         ctx.phase = "fwd_online";
-        const float* q = net.forward(ctx, qnet.p, bv.obs, ld_in, B, ws_online);         // :71-74
+        const float* q = net.forward(ctx, qnet.p, bv.obs, ld_in, B, ws_online, 0, in_ix);         // :71-74
         const float* q_next = nullptr;
         ctx.phase = "fwd_target";
         if (cfg.double_dqn) {                                                              // :93-99
             // online net on next_obs: borrow the target workspace first, keep its Q in d_scratch
-            const float* qn = net.forward(tctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt);
+            const float* qn = net.forward(tctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt, 0, in_ix);
             BB_CUDA(cudaMemcpyAsync(d_scratch, qn, (size_t)B * net.out_dim * 4, cudaMemcpyDeviceToDevice, tctx.stream));
             q_next = d_scratch;
         }
-        const float* qt = net.forward(tctx, qnet_tgt.p, bv.next_obs, ld_in, B, ws_tgt);  // :100-103
+        const float* qt = net.forward(tctx, qnet_tgt.p, bv.next_obs, ld_in, B, ws_tgt, 0, in_ix);  // :100-103
         if (conc) ctx.join_from(tctx);
         DqnLossParams lp;
         lp.q = q; lp.q_tgt = qt; lp.q_next = q_next; lp.act = (const long long*)bv.act;
@@ -232,7 +237,7 @@ struct Dqn : Agent {
         ctx.mark("d2h_32B");  // (profiled runs are serial: without its own mark the copy's latency lands on the next kernel)
         ctx.phase = "backward";
         // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
-        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0);
+        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0, 0, in_ix);
         if (conc) ctx.join_from(rctx);  // (backward joins the side streams it used; this one may not be among them)
     }
 

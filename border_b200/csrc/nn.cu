@@ -452,6 +452,7 @@ static TmaConv tma_conv_of(const ConvGeom& g) { return TmaConv{g.B, g.H, g.W, g.
 
 void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu) {
     if (g.u8_chw && env_int("BB_TC", 1) && conv1_fwd_tc(c, g, X, W, b, Y, relu)) return;
+    BB_CHECK(!g.in_ix, "indexed input reached the generic convolution path");
     GemmArgs a = zero_args();
     const TmaConv cv = tma_conv_of(g);
     if (!g.u8_chw) { a.a_conv = &cv; a.a_plane = g.x_plane; a.b_plane = g.w_plane; }
@@ -468,6 +469,7 @@ void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const voi
         if (db) colsum(c, dY, db, g.M(), g.OC);
         return;
     }
+    BB_CHECK(!g.in_ix, "indexed input reached the generic convolution path");
     // (float inputs only: for the u8 conv1 frames the transposed 4-byte gathers are slower than the
     // CUDA-core kernel -- 115 us vs 67 us at B=256)
     if (!g.u8_chw && env_int("BB_TC", 1) && env_int("BB_TC_WGRAD_T", 1)) {
@@ -1034,8 +1036,17 @@ std::string Net::layer_name(size_t i) const {
     return "layer" + std::to_string(i);
 }
 
-const float* Net::forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w, long p_plane) const {
+bool Net::direct_input_ok(int B) const {
+    if (layers.empty() || layers[0].type != 1) return false;
+    ConvGeom g = layers[0].geom;
+    g.B = B;
+    return conv1_direct_ok(g);
+}
+
+const float* Net::forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w, long p_plane,
+                          const unsigned long long* in_ix) const {
     BB_CHECK(B <= w.max_batch, "batch larger than the workspace");
+    BB_CHECK(!in_ix || direct_input_ok(B), "indexed input needs the dedicated first-layer kernels");
     const void* x = input;
     long ldx = ld_in;
     for (size_t i = 0; i < layers.size(); ++i) {
@@ -1047,6 +1058,7 @@ const float* Net::forward(const Ctx& c, const float* p, const void* input, long 
             ConvGeom g = l.geom;
             g.B = B; g.rowbase = w.rowbase[i];
             g.x_plane = x_plane; g.w_plane = p_plane; g.y_plane = y_plane;
+            g.in_ix = i == 0 ? in_ix : nullptr;
             conv_fwd(c, g, x, p + l.w_off, p + l.b_off, w.act[i], l.relu);
         } else {
             linear_fwd(c, (const float*)x, ldx, p + l.w_off, p + l.b_off, w.act[i], B, l.out_dim, l.in_dim, l.relu, x_plane,
@@ -1172,7 +1184,7 @@ __global__ void relu_mask_kernel(float* __restrict__ d, const float* __restrict_
 }
 
 void Net::backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
-                   float* d_input, long ld_din, long p_plane) const {
+                   float* d_input, long ld_din, long p_plane, const unsigned long long* in_ix) const {
     BB_CHECK(w.with_grad, "workspace was allocated without gradient buffers");
     int L = (int)layers.size();
     // d(output) arrives in w.dact[L-1] as the gradient wrt the post-activation output
@@ -1217,6 +1229,7 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
             cg.dg_rowbase = w.dg_rowbase[i]; cg.dg_crow = w.dg_crow[i]; cg.dypad = w.dypad[i]; cg.dg_wt = w.dg_wt[i];
             cg.x_plane = x_plane; cg.y_plane = dy_plane; cg.w_plane = p_plane; cg.dx_plane = dx_plane;
             cg.dypad_plane = p_plane ? w.dypad_plane[i] : 0; cg.wt_plane = p_plane ? w.wt_plane[i] : 0;
+            cg.in_ix = i == 0 ? in_ix : nullptr;
             if (g) {
                 c.layer = layer_name(i) + ".wgrad";
                 if (bc) colsum(*bc, w.dact[i], g + l.b_off, cg.M(), cg.OC);

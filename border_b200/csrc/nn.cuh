@@ -88,6 +88,8 @@ struct ConvGeom {
     float* dg_wt = nullptr;           // [S*S*C][(KH/S)*(KW/S)*OC] per workspace: the weights re-laid k-contiguous per step
     // lo planes (element offsets; 0 = none): input X, output Y / its gradient dY, weights, input gradient dX, dypad, dg_wt
     long x_plane = 0, y_plane = 0, w_plane = 0, dx_plane = 0, dypad_plane = 0, wt_plane = 0;
+    // u8 first layer only: image b of the batch is row in_ix[b] of X (the replay ring; conv1_tc.cu reads it through the list)
+    const unsigned long long* in_ix = nullptr;
     int M() const { return B * OH * OW; }
     int K() const { return C * KH * KW; }
     bool dgrad_gather_ok() const {
@@ -99,6 +101,7 @@ struct ConvGeom {
 // conv1_tc.cu: dedicated tcgen05 kernel for the AtariCnn first layer; false => geometry not handled
 bool conv1_fwd_tc(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu);
 bool conv1_wgrad_tc(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW);
+bool conv1_direct_ok(const ConvGeom& g);   // both of the above take the layer: the batch need not be materialised
 void conv_fwd(const Ctx& c, const ConvGeom& g, const void* X, const float* W, const float* b, float* Y, bool relu);
 void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const void* X, float* dW, float* db);
 // dX[B][H][W][C] = col2im(dY W) * (mask > 0); `col` is [M][K] scratch
@@ -181,7 +184,10 @@ class Net {
     // forward: input [B][in] (u8 CHW frames or float rows); returns ws.act.back()
     // p_plane != 0: the parameter vector carries a valid lo plane at p + p_plane; the layers then write the lo planes of
     // their outputs and the TMA-fed tensor-core GEMMs are used wherever both operands have one.
-    const float* forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w, long p_plane = 0) const;
+    // in_ix != null (u8 AtariCnn input only, see direct_input_ok): `input` is the replay ring and image b is its row in_ix[b]
+    const float* forward(const Ctx& c, const float* p, const void* input, long ld_in, int B, NetWorkspace& w, long p_plane = 0,
+                         const unsigned long long* in_ix = nullptr) const;
+    bool direct_input_ok(int B) const;   // the first layer can read ring rows through an index list at this batch size
     // Policy::sample-sized batches (B <= 8): the whole forward as ONE cooperative kernel, a warp per output element
     // and a grid-wide barrier between layers (the per-layer GEMM launches are pure latency at B = 1).  Returns null
     // when the net / batch does not qualify (caller falls back to forward()).
@@ -192,7 +198,7 @@ class Net {
     // With c.concurrent() the weight gradients of all layers but the first run on the side contexts
     // while the data-gradient chain continues on c.stream; everything is joined before returning.
     void backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
-                  float* d_input, long ld_din, long p_plane = 0) const;
+                  float* d_input, long ld_din, long p_plane = 0, const unsigned long long* in_ix = nullptr) const;
     void free_tables();
     std::string layer_name(size_t i) const;
 };

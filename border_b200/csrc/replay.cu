@@ -191,6 +191,7 @@ struct SampleParams {
     unsigned long long n_opts_final, fr_seed;
     const float* inject_u;
     int powf_fused;
+    int skip_obs;   // draw the indices and gather the small columns only: the consumer reads obs / next_obs rows of the ring itself
 };
 
 // One CTA per (row chunk, batch row).  Thread 0 draws the row's index (ChaCha12 word or sum-tree
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(256) replay_sample_gather_kernel(SampleParams 
     __syncthreads();
     const unsigned long long ix = s_ix;
     const uint32_t off = c * p.chunk_bytes;
-    if (off < p.obs_row_bytes) {
+    if (!p.skip_obs && off < p.obs_row_bytes) {
         uint32_t n = min(p.chunk_bytes, p.obs_row_bytes - off);
         block_copy2(p.b_obs + (size_t)b * p.obs_row_bytes + off, p.obs + ix * p.obs_row_bytes + off,
                     p.b_next_obs + (size_t)b * p.obs_row_bytes + off, p.next_obs + ix * p.obs_row_bytes + off, n, p.vec);
@@ -749,7 +750,7 @@ void Replay::push(const void* o, const void* a, const void* no, const float* r, 
     if (per) n_samples = std::min<uint64_t>(n_samples + n, cfg.capacity);
 }
 
-void Replay::sample(size_t B, bb_batch_view* out, bool launch) {
+void Replay::sample(size_t B, bb_batch_view* out, bool launch, bool gather_obs) {
     DeviceGuard g(device);
     BB_CHECK(B >= 1 && B <= 65535, "batch size out of range");
     BB_CHECK(size > 0, "cannot sample from an empty replay buffer");
@@ -763,8 +764,9 @@ void Replay::sample(size_t B, bb_batch_view* out, bool launch) {
     sp.per = per; sp.normalize = cfg.normalize; sp.tree = tree; sp.min_tree = min_tree;
     sp.beta_0 = cfg.beta_0; sp.beta_final = cfg.beta_final; sp.n_opts_final = cfg.n_opts_final;
     sp.fr_seed = cfg.fastrand_seed; sp.inject_u = inject_u; sp.powf_fused = powf_fused;
+    sp.skip_obs = gather_obs ? 0 : 1;
     if (launch) {
-        launch_pdl_if(pdl_replay_enabled(), replay_sample_gather_kernel, dim3(n_chunks, (unsigned)B), dim3(256), 0, stream, sp, (uint32_t)B);
+        launch_pdl_if(pdl_replay_enabled(), replay_sample_gather_kernel, dim3(gather_obs ? n_chunks : 1, (unsigned)B), dim3(256), 0, stream, sp, (uint32_t)B);
         BB_LAUNCHED();
     }
     if (!per) rng_pos += B;
@@ -772,7 +774,8 @@ void Replay::sample(size_t B, bb_batch_view* out, bool launch) {
     else { fr_draws += B; inject_pending = 0; }
     last_batch = B;
     if (out) {
-        out->batch_size = B; out->obs = b_obs; out->act = b_act; out->next_obs = b_next_obs; out->reward = b_reward;
+        // (index-only sampling: obs / next_obs are the ring columns themselves, to be read through ix_sample)
+        out->batch_size = B; out->obs = gather_obs ? b_obs : obs; out->act = b_act; out->next_obs = gather_obs ? b_next_obs : next_obs; out->reward = b_reward;
         out->is_terminated = b_term; out->is_truncated = b_trunc; out->ix_sample = (const uint64_t*)b_ix;
         out->weight = per ? b_weight : nullptr;
     }

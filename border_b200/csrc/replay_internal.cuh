@@ -78,7 +78,9 @@ struct Replay {
               size_t n, bool on_device);
     // launch = false only advances the host mirror and fills `out` (the launch itself is replayed by a
     // CUDA graph that captured an identical call: every kernel argument of sample() is launch-invariant)
-    void sample(size_t B, bb_batch_view* out, bool launch = true);
+    // gather_obs = false: indices + small columns only; out->obs / next_obs are then the RING columns, to be read through
+    // out->ix_sample (the DQN update's first-layer kernels do: no 14.5 MB batch is written and re-read)
+    void sample(size_t B, bb_batch_view* out, bool launch = true, bool gather_obs = true);
     void update_priority_dev(const unsigned long long* ixs, const float* td, size_t n);
     void update_priority_host(const uint64_t* ixs, const float* td, size_t n);
     void fill_synthetic(uint64_t n_rows, uint32_t n_actions, uint64_t seed);
