@@ -29,7 +29,15 @@ $(LIB): $(OBJS)
 $(HOSTLIB): border_b200/host/host_capi.cpp border_b200/host/border_host.hpp include/border_host.h include/border_b200.h $(LIB)
 	g++ -std=c++17 -O2 -fPIC -shared -Wall -Iinclude border_b200/host/host_capi.cpp -o $@ -Lborder_b200 -lborder_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
 
-oracle: oracle/_build/libreplay_oracle.so
+oracle: oracle/_build/libreplay_oracle.so oracle/_build/varstore_oracle
+
+# libtorch C++ leg of the oracle (TEST INFRASTRUCTURE): tch's VarStore save / load calls and the real torch::optim::Adam
+TORCH_DIR := $(shell python -c "import torch, os; print(os.path.dirname(torch.__file__))" 2>/dev/null)
+TORCH_ABI := $(shell python -c "import torch; print(int(torch._C._GLIBCXX_USE_CXX11_ABI))" 2>/dev/null)
+oracle/_build/varstore_oracle: oracle/varstore_oracle.cpp
+	@mkdir -p oracle/_build
+	g++ -std=c++17 -O1 -D_GLIBCXX_USE_CXX11_ABI=$(TORCH_ABI) -I$(TORCH_DIR)/include -I$(TORCH_DIR)/include/torch/csrc/api/include \
+	    $< -o $@ -L$(TORCH_DIR)/lib -ltorch -ltorch_cpu -lc10 -Wl,-rpath,$(TORCH_DIR)/lib
 
 oracle/_build/libreplay_oracle.so: oracle/replay_oracle.c
 	@mkdir -p oracle/_build

@@ -120,13 +120,48 @@ def cpu_dqn_runner(capacity=4096, seed=42):
     return lambda: agent.opt_(sample)
 
 
-def time_cpu(steps, warmup):
+def time_cpu(steps, warmup, threads=None):
+    import torch
     step = cpu_dqn_runner()
+    if threads:
+        torch.set_num_threads(threads)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
+    dt = time.perf_counter() - t0
+    torch.set_num_threads(os.cpu_count() or 1)
+    return steps / dt, dt
+
+
+def time_cpu_env(steps, warmup):
+    """env-steps/s of the reference's CPU path restated: Policy::sample (B=1 NatureCNN forward + argmax,
+    dqn/base.rs:211-241) + SimpleStepProcessor::process + ExperienceBufferBase::push (base.rs:295-316) with a zero-cost
+    synthetic env, as Sampler::sample_and_push (trainer/sampler.rs:99-144) does."""
+    import numpy as np
+    import torch
+    from oracle import agent_oracle as ao
+    from oracle import replay_oracle as ro
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = ao.atari_cnn_params(4, N_ACT, torch.Generator().manual_seed(0))
+    orc = ro.ReplayOracle(4096, 42, (4, 84, 84), np.uint8, (1,), np.int64)
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, (17,) + OBS_SHAPE, dtype=np.uint8)
+    r, t, tr = np.ones(1, np.float32), np.zeros(1, np.int8), np.zeros(1, np.int8)
+
+    def step(i):
+        obs, nxt = frames[i % 16:i % 16 + 1], frames[i % 16 + 1:i % 16 + 2]
+        with torch.no_grad():
+            q = ao.atari_cnn_forward(params, torch.from_numpy(obs).reshape(1, 4, 1, 84, 84))
+        act = np.array([[int(q.argmax(-1))]], np.int64)
+        orc.push(obs, act, nxt, r, t, tr)
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
     dt = time.perf_counter() - t0
     return steps / dt, dt
 
@@ -199,22 +234,29 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, repeats=1):
+        """CUDA-event time of `steps` calls (max over ranks); with repeats > 1 the region is timed that many times and the
+        MEDIAN is returned (20 steps are ~6 ms: one scheduler hiccup must not decide the number)."""
         for _ in range(warmup):
             fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        out = []
+        for _ in range(repeats):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            out.append(ms)
+        out.sort()
+        timed.last_samples = out
+        return out[len(out) // 2]
 
     lib = L.lib()
     n0 = __import__("ctypes").c_uint64()
@@ -228,11 +270,12 @@ def run_b200(args):
         agent.opt(rb)
     torch.cuda.synchronize()
     lib.bb_kernel_launch_count(None, 1)
-    ms = timed(lambda: agent.opt(rb), args.steps, args.warmup)
+    ms = timed(lambda: agent.opt(rb), args.steps, args.warmup, repeats=args.repeats)
+    ms_samples = list(timed.last_samples)
     lib.bb_kernel_launch_count(__import__("ctypes").byref(n0), 0)
-    launches_total = n0.value  # includes warm-up launches
+    launches_total = n0.value  # includes warm-up launches and every repeat
     clk = clocks.stop()
-    launches = int(round(launches_total * args.steps / float(args.steps + args.warmup)))
+    launches = int(round(launches_total * args.steps / float(args.steps * args.repeats + args.warmup)))
     value = world * args.steps / (ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers: the Trainer's inner loop in C++ (libborder_host.so,
@@ -252,21 +295,26 @@ def run_b200(args):
     def e2e_run(k):
         return hl.e2e_steps(agent, rb, h_obs, h_act, h_next, h_rew, h_term, h_trunc, k)
 
-    e2e_steps = max(10, args.steps // 2)
-    e2e_run(max(3, args.warmup // 2))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t_host0 = time.perf_counter()
-    e2e_run(e2e_steps)
-    t_host1 = time.perf_counter()
-    e1.record()
-    barrier()
-    ms_e2e = max(e0.elapsed_time(e1), 1e3 * (t_host1 - t_host0))  # the loop is synchronous: device span == host span
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    e2e_steps = max(args.steps, 50)
+    e2e_run(max(3, args.warmup))
+    e2e_samples = []
+    for _ in range(args.repeats):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t_host0 = time.perf_counter()
+        e2e_run(e2e_steps)
+        t_host1 = time.perf_counter()
+        e1.record()
+        barrier()
+        m = max(e0.elapsed_time(e1), 1e3 * (t_host1 - t_host0))  # the loop is synchronous: device span == host span
+        if world > 1:
+            t = torch.tensor([m], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            m = float(t.item())
+        e2e_samples.append(m)
+    e2e_samples.sort()
+    ms_e2e = e2e_samples[len(e2e_samples) // 2]
     e2e_value = world * e2e_steps / (ms_e2e * 1e-3)
     h2d = 2 * ROW + 8 + 4 + 1 + 1 + 2  # packed staging block of one transition (padded to 16 B)
     h2d = (h2d + 15) // 16 * 16
@@ -288,11 +336,11 @@ def run_b200(args):
         for k, v in run:
             agg[k] = agg.get(k, 0.0) + v / len(prof_runs)
     step_ms_prof = sum(agg.values())
-    # dominant kernel = tc_gemm_kernel (tc_gemm.cuh), 12 launches per step (c2/c3/l1 x {forward of both nets, data
+    # dominant kernel = tma_gemm_kernel (tma_gemm.cuh), 12 launches per step (c2/c3/l1 x {forward of both nets, data
     # gradient, weight gradient}): achieved = their algorithmic FLOPs / their device time, per launch = the averages.
     # The slowest and fastest single launches are reported beside it.  (At N>1 the profiled Adam also absorbs the ranks'
     # skew in its peer barrier, which is waiting, not work.)
-    tcs = {k: v for k, v in agg.items() if k.endswith(":tc_gemm128x64") or k.endswith(":tc_gemm128x32") or k.endswith(":tc_gemm128x128")}
+    tcs = {k: v for k, v in agg.items() if k.split(":")[-1].startswith(("tma_gemm", "tc_gemm"))}
     if tcs:
         per = {k: roofline_for(k, v, step_ms_prof, pk) for k, v in tcs.items()}
         flop = sum(r["algorithmic_flop"] for r in per.values())
@@ -301,7 +349,7 @@ def run_b200(args):
         worst = min(per.values(), key=lambda r: r["achieved"])
         best = max(per.values(), key=lambda r: r["achieved"])
         traffic = [r["traffic"] for r in per.values()]
-        roof = {"kernel": "tc_gemm_kernel<128xBNx32, 3xTF32> (%d launches per step)" % len(tcs), "bound": "tensor",
+        roof = {"kernel": "tma_gemm_kernel<128xBNx32, 3xTF32, TMA-fed> (%d launches per step)" % len(tcs), "bound": "tensor",
                 "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
                 "traffic": (sum(traffic) / len(traffic)) if all(t is not None for t in traffic) else None,
                 "ms_per_launch": ms_sum / len(tcs), "launches_per_step": len(tcs), "share_of_step": ms_sum / step_ms_prof,
@@ -331,14 +379,22 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt = time_cpu(args.cpu_steps, 2)
+        v1, dt1 = time_cpu(max(10, args.cpu_steps // 8), 1, threads=1)   # the async example pins tch::set_num_threads(1)
+        ve, dte = time_cpu_env(max(200, args.cpu_steps), 5)
         cpu = {"value": v, "unit": "grad-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "%d full B=256 NatureCNN update steps on the host CPU (torch fp32, all threads), %.1f s"
-                         % (args.cpu_steps, dt)}
+                         % (args.cpu_steps, dt),
+               "one_thread": {"value": v1, "unit": "grad-steps/s", "cores": 1,
+                              "sample": "%d steps with torch.set_num_threads(1) (dqn_atari_async_tch/src/main.rs:108), %.1f s" % (max(10, args.cpu_steps // 8), dt1)},
+               "env_steps": {"value": ve, "unit": "env-steps/s", "cores": os.cpu_count() or 1,
+                             "sample": "%d x (B=1 NatureCNN Policy::sample + replay push, zero-cost env), %.1f s" % (max(200, args.cpu_steps), dte)}}
 
     if rank == 0:
         out = {"metric": "grad-steps/sec", "value": value, "unit": "grad-steps/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "timing": {"repeats": args.repeats, "statistic": "median", "ms_per_step_samples": [round(x / args.steps, 5) for x in ms_samples],
+                          "e2e_steps": e2e_steps, "e2e_ms_per_step_samples": [round(x / e2e_steps, 5) for x in e2e_samples]},
                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "replay_capacity": cap, "replay_bytes": cap * (2 * ROW + 14),
                           "n_actions": N_ACT, "optimizer": "Adam lr 1e-4", "critic_loss": "Mse",
                           "l2_policy": "inputs larger than L2 (random rows of a %.1f GB ring)" % (cap * 2 * ROW / 1e9),
@@ -449,11 +505,20 @@ def other_workloads(dev, stream, timed, pk):
     return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture of the same
-# step (profiles/r01_tc_gemm_ncu_full.txt, profiles/r01_misc_ncu_full.txt; cold-cache replays)
-NCU_TRAFFIC = {"c2.fwd": 13400000, "c3.fwd": 5580000, "l1.fwd": 9700000, "l1.wgrad": 3810000, "l1.dgrad": 10200000,
-               "c3.wgrad": 8670000, "c3.dgrad": 13600000, "c2.wgrad": 18600000, "c2.dgrad": 21400000 + 11500,
-               "c1.wgrad": 20400000, "c1.fwd": 7693056}
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the tracked ncu summary of THIS round's kernels
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` capture of one step); entries
+    are used only when the kernel name recorded there is the one this build launches -- otherwise traffic is null rather
+    than a stale literal."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d if d.get("kernel", "").startswith("tma_gemm_kernel") else {}
+    except Exception:
+        return {}
+
+
+NCU_TRAFFIC = _ncu_traffic().get("per_layer", {})
 
 
 def roofline_for(label, ms, step_ms, pk):
@@ -468,7 +533,7 @@ def roofline_for(label, ms, step_ms, pk):
         return {"kernel": label, "bound": "tensor", "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": tf / pk["tf_sust"], "traffic": NCU_TRAFFIC.get(layer), "ms_per_launch": ms, "share_of_step": ms / step_ms,
                 "algorithmic_flop": flop, "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside the step)",
-                "note": ("tcgen05 kind::tf32, 3xTF32 for fp32 parity (hi*hi and hi*lo in one N=2*BN MMA, lo*hi in a second): "
+                "note": ("TMA-fed tcgen05 kind::tf32, 3xTF32 for fp32 parity (x.[y;lo(y)] in one N=2*BN MMA from shared memory, lo(x).y from tensor memory): "
                          "algorithmic FLOPs are counted once, so the tensor pipe does 3x this; peak is the dense bf16 figure "
                          "(TF32 peak is half)")
                 if on_tc else "fp32 CUDA-core implicit GEMM; peak is the dense bf16 tensor figure"}
@@ -485,6 +550,7 @@ def main():
     ap.add_argument("--capacity", type=int, default=1 << 20)
     ap.add_argument("--sync", default="allreduce", choices=["allreduce", "replicas"])
     ap.add_argument("--cpu-steps", type=int, default=400)
+    ap.add_argument("--repeats", type=int, default=5, help="time the K-step region this many times, report the median")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the SAC / IQN / PER / large-batch gather side measurements")
     args = ap.parse_args()

@@ -108,6 +108,7 @@ _SIGS = {
     "bb_replay_len": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "bb_replay_sample": (C.c_int32, [_P, C.c_size_t, C.POINTER(bb_batch_view)]),
     "bb_replay_batch_to_host": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bb_replay_last_batch": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "bb_replay_update_priority": (C.c_int32, [_P, _P, _P, C.c_size_t, C.c_int32]),
     "bb_replay_inject_uniforms": (C.c_int32, [_P, _P, C.c_size_t]),
     "bb_replay_dump_sum_tree": (C.c_int32, [_P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -121,6 +122,7 @@ _SIGS = {
     "bb_iqn_create": (C.c_int32, [C.POINTER(bb_iqn_cfg), C.POINTER(_P)]),
     "bb_agent_destroy": (C.c_int32, [_P]),
     "bb_agent_set_stream": (C.c_int32, [_P, _P]),
+    "bb_agent_set_precision": (C.c_int32, [_P, C.c_int32]),
     "bb_agent_set_train": (C.c_int32, [_P, C.c_int32]),
     "bb_agent_is_train": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
     "bb_agent_sample": (C.c_int32, [_P, _P, C.c_size_t, _P]),
@@ -134,6 +136,7 @@ _SIGS = {
                                         C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "bb_agent_get_param": (C.c_int32, [_P, C.c_char_p, C.c_char_p, _P, C.c_size_t]),
     "bb_agent_set_param": (C.c_int32, [_P, C.c_char_p, C.c_char_p, _P, C.c_size_t]),
+    "bb_agent_reset_opt_state": (C.c_int32, [_P]),
     "bb_agent_get_opt_state": (C.c_int32, [_P, C.c_char_p, C.c_char_p, _P, _P, C.c_size_t, C.POINTER(C.c_uint64)]),
     "bb_agent_model_info_size": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "bb_agent_model_info": (C.c_int32, [_P, _P, C.c_size_t, C.POINTER(C.c_uint64)]),

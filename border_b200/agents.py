@@ -7,6 +7,7 @@ Agent surface: border-core/src/base/agent.rs:24-136, policy.rs:49-63; SyncModel:
 border-async-trainer/src/sync_model.rs:2-13.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Tuple
 
@@ -298,12 +299,41 @@ class Agent:
         return out.value
 
     # Agent::save_params / load_params
+    def set_precision(self, fast):
+        """fast=False (default): 3xTF32, fp32 parity; fast=True: single-pass TF32 contractions (see border_b200.h)."""
+        L.check(L.lib().bb_agent_set_precision(self._h, 1 if fast else 0))
+
     def save_params(self, path):
+        """Agent::save_params (dqn/base.rs:348-362, sac/base.rs:313-345): one tch `VarStore` archive `<model>.pt.tch` per
+        model -- the file names and tensor names a reference-side `load_params` expects (checkpoint.py) -- and returns their
+        paths like the trait does.  The Adam moments / step counts the reference does not save go to this library's
+        side-car files `<model>.pt.tch.b200` in the same directory (true resume)."""
+        from . import checkpoint
+        os.makedirs(str(path), exist_ok=True)  # fs::create_dir_all
         L.check(L.lib().bb_agent_save_params(self._h, str(path).encode()))
-        return [str(path) + "/" + m + ".pt.tch.b200" for m in self._models]
+        out = []
+        for m in self._models:
+            f = os.path.join(str(path), m + ".pt.tch")
+            checkpoint.write_varstore(f, self.named_parameters(m))
+            out.append(f)
+        return out
 
     def load_params(self, path):
-        L.check(L.lib().bb_agent_load_params(self._h, str(path).encode()))
+        """Agent::load_params: reads `<model>.pt.tch` archives written by the reference (tch VarStore::save) or by
+        save_params.  When this library's side-car is present the optimizer state is restored from it first; otherwise
+        the Adam moments and step of the live models are reset (a reference checkpoint carries none)."""
+        from . import checkpoint
+        side = all(os.path.exists(os.path.join(str(path), m + ".pt.tch.b200")) for m in self._models)
+        if side:
+            L.check(L.lib().bb_agent_load_params(self._h, str(path).encode()))
+        for m in self._models:
+            f = os.path.join(str(path), m + ".pt.tch")
+            if os.path.exists(f):
+                self.set_parameters(m, checkpoint.read_varstore(f))
+            elif not side:
+                raise FileNotFoundError(f)
+        if not side:
+            L.check(L.lib().bb_agent_reset_opt_state(self._h))
 
     # named tensors in the reference layout
     def named_parameters(self, model):

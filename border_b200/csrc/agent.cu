@@ -101,7 +101,7 @@ void Agent::grad_buffer(void** p, uint64_t* n) { *p = nullptr; *n = 0; }
 __global__ void peer_barrier_kernel(unsigned int* mine, unsigned int* const* peers_unused, unsigned int* p0,
                                     unsigned int* p1, unsigned int* p2, unsigned int* p3, unsigned int* p4,
                                     unsigned int* p5, unsigned int* p6, unsigned int* p7, int rank, int world,
-                                    unsigned int epoch) {
+                                    unsigned int epoch, int* err, long long timeout_cycles) {
     (void)peers_unused;
     unsigned int* peers[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
     int t = threadIdx.x;
@@ -113,16 +113,30 @@ __global__ void peer_barrier_kernel(unsigned int* mine, unsigned int* const* pee
         volatile unsigned int* src = mine + t;
         long long t0 = clock64();
         while ((int)(*src - epoch) < 0) {
-            if (clock64() - t0 > 4000000000LL) break;  // ~2 s: give up instead of hanging
+            if (clock64() - t0 > timeout_cycles) {
+                // a peer never arrived: the gradients this rank is about to read are not complete.  Raise the sticky
+                // failure flag (every following opt() throws) instead of falling through to the optimizer silently.
+                *reinterpret_cast<volatile int*>(err) = 21;
+                __threadfence_system();
+                break;
+            }
         }
     }
+}
+
+// BB_PEER_TIMEOUT_S (default 30): how long a rank may lag (checkpointing, evaluation, graph capture on a peer) before the
+// barrier gives up and raises the failure flag
+static long long peer_timeout_cycles() {
+    static const long long c = (long long)(getenv("BB_PEER_TIMEOUT_S") ? atof(getenv("BB_PEER_TIMEOUT_S")) : 30.0) * 1900000000LL;
+    return c;
 }
 
 static void peer_barrier(Agent* a) {
     a->sync_epoch += 1;
     peer_barrier_kernel<<<1, 32, 0, a->ctx.stream>>>(a->my_flags, nullptr, a->peer_flag[0], a->peer_flag[1],
                                                     a->peer_flag[2], a->peer_flag[3], a->peer_flag[4], a->peer_flag[5],
-                                                    a->peer_flag[6], a->peer_flag[7], a->rank, a->world, a->sync_epoch);
+                                                    a->peer_flag[6], a->peer_flag[7], a->rank, a->world, a->sync_epoch,
+                                                    device_error_flag(), peer_timeout_cycles());
     BB_LAUNCHED();
 }
 void Agent::grad_sync_begin() {
@@ -158,7 +172,15 @@ void Agent::synced_adam(Model& m) {
 void Agent::save_params(const char* dir) {
     DeviceGuard g(device);
     BB_CUDA(cudaStreamSynchronize(ctx.stream));
-    if (mkdir(dir, 0777) != 0 && errno != EEXIST) throw Error(std::string("cannot create directory ") + dir);
+    check_device_error("save_params");   // never checkpoint a model a timed-out kernel may have corrupted
+    {   // fs::create_dir_all(&path) (dqn/base.rs:350): every missing component
+        std::string d(dir);
+        for (size_t i = 1; i <= d.size(); ++i)
+            if (i == d.size() || d[i] == '/') {
+                std::string part = d.substr(0, i);
+                if (mkdir(part.c_str(), 0777) != 0 && errno != EEXIST) throw Error("cannot create directory " + part);
+            }
+    }
     for (Model* m : models) {
         std::string path = std::string(dir) + "/" + m->name + ".pt.tch.b200";
         std::ofstream f(path, std::ios::binary);
@@ -205,6 +227,7 @@ void Agent::load_params(const char* dir) {
         uint64_t step;
         f >> magic >> ver >> nt >> has_opt >> step;
         if (magic != "BORDER_B200_VARSTORE" || nt != m->params.size()) throw Error("bad checkpoint " + path);
+        if (ver != 1) throw Error("unsupported checkpoint version in " + path);
         for (auto& pi : m->params) {
             std::string nm;
             size_t nd;
@@ -236,6 +259,12 @@ void Agent::load_params(const char* dir) {
             h2d_sync(m->m, hm.data(), m->n * 4, ctx.stream);
             h2d_sync(m->v, hv.data(), m->n * 4, ctx.stream);
             m->step = step;
+        } else if (m->has_opt) {
+            // the file carries no optimizer state: start Adam afresh rather than keep the live model's stale moments
+            BB_CUDA(cudaMemsetAsync(m->m, 0, m->n * 4, ctx.stream));
+            BB_CUDA(cudaMemsetAsync(m->v, 0, m->n * 4, ctx.stream));
+            BB_CUDA(cudaStreamSynchronize(ctx.stream));
+            m->step = 0;
         }
     }
 }
@@ -327,6 +356,16 @@ int32_t bb_agent_set_stream(bb_agent* a, void* s) {
     ag.ctx.stream = s ? (cudaStream_t)s : bb::device_stream(ag.device);
     BB_API_END
 }
+int32_t bb_agent_set_precision(bb_agent* a, int32_t fast) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
+    const int passes = fast ? 1 : 3;
+    ag.ctx.passes = passes;
+    for (int i = 0; i < 2; ++i) ag.side_ctx[i].passes = passes;
+    ag.precision_changed();   // captured CUDA graphs hold the kernels of the old mode
+    BB_API_END
+}
 int32_t bb_agent_set_train(bb_agent* a, int32_t train) {
     BB_API_BEGIN
     A(a).train = train != 0;
@@ -341,12 +380,16 @@ int32_t bb_agent_is_train(const bb_agent* a, int32_t* out) {
 int32_t bb_agent_sample(bb_agent* a, const void* obs, size_t n, void* act_out) {
     BB_API_BEGIN
     BB_CHECK(obs && act_out, "null argument");
+    bb::check_device_error("bb_agent_sample");
     A(a).sample(obs, n, act_out);
     BB_API_END
 }
 int32_t bb_agent_opt(bb_agent* a, bb_replay* rb, bb_record* record) {
     BB_API_BEGIN
     BB_CHECK(rb, "null replay handle");
+    // a device-side bounded wait that timed out in an EARLIER call (tcgen05 / TMA pipeline, peer barrier) left garbage in
+    // the model: refuse to train on (the flag is pinned mapped memory: a plain host read, no sync)
+    bb::check_device_error("bb_agent_opt");
     A(a).opt(rb->impl, record);
     BB_API_END
 }
@@ -458,6 +501,19 @@ int32_t bb_agent_set_param(bb_agent* a, const char* model, const char* name, con
     BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
     bb::h2d_sync(m->p + pi->offset, tmp.data(), pi->numel * 4, ag.ctx.stream);
     bb::make_lo(ag.ctx, m->p + pi->offset, m->p_lo() + pi->offset, pi->numel);
+    BB_API_END
+}
+int32_t bb_agent_reset_opt_state(bb_agent* a) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    bb::DeviceGuard g(ag.device);
+    for (bb::Model* m : ag.models)
+        if (m->has_opt) {
+            BB_CUDA(cudaMemsetAsync(m->m, 0, m->n * 4, ag.ctx.stream));
+            BB_CUDA(cudaMemsetAsync(m->v, 0, m->n * 4, ag.ctx.stream));
+            m->step = 0;
+        }
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
     BB_API_END
 }
 int32_t bb_agent_get_opt_state(bb_agent* a, const char* model, const char* name, float* host_m, float* host_v, size_t n,

@@ -105,6 +105,7 @@ struct Agent {
     virtual void sample(const void* obs, size_t n, void* act_out) = 0;
     virtual Model* sync_model_src() = 0;  // which VarStore SyncModel ships (DQN qnet, SAC pi)
     virtual void inject_noise(int slot, const float* host, size_t n);
+    virtual void precision_changed() {}   // drop captured graphs (they hold the GEMM kernels of the previous precision mode)
     virtual void grad_buffer(void** p, uint64_t* n);
     void save_params(const char* dir);
     void load_params(const char* dir);

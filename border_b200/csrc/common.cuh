@@ -124,6 +124,19 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     launch_pdl_if(pdl_enabled(), kern, grid, block, smem, s, std::forward<Args>(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, DEVICE): the attribute is per device, so a
+// process-wide "configured" flag left every GPU but the first one a handle touched with the 48 KB default.
+#define BB_ENSURE_SMEM(kern, bytes)                                                                        \
+    do {                                                                                                   \
+        static std::atomic<uint32_t> _done{0};                                                             \
+        int _dev = 0;                                                                                      \
+        cudaGetDevice(&_dev);                                                                              \
+        if (!(_done.load(std::memory_order_acquire) & (1u << (_dev & 31)))) {                              \
+            BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _done.fetch_or(1u << (_dev & 31), std::memory_order_release);                                  \
+        }                                                                                                  \
+    } while (0)
+
 // Sticky device-side failure flag (a bounded mbarrier / peer-barrier wait timed out): ONE int in pinned, mapped host
 // memory, so kernels store to it directly and every host entry point can test it without a copy or a sync.
 int* device_error_flag();

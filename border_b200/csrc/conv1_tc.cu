@@ -24,6 +24,7 @@
 //
 // TMEM: [0,32) [32,64) accumulators, then S stages x 64 columns (one channel = 64 k-values).
 #include <stdlib.h>
+#include <atomic>
 #include <algorithm>
 #include <vector>
 #include "nn.cuh"
@@ -31,6 +32,7 @@
 
 namespace bb {
 static __device__ int g_tc_error_c1 = 0;
+static __device__ int* g_err_flag_c1 = nullptr;   // the library's pinned, mapped failure flag (common.cuh), set per device at first launch
 
 namespace c1 {
 using namespace tc;
@@ -57,6 +59,7 @@ __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity) {
     for (uint32_t it = 0; it < (1u << 22); ++it)
         if (mbar_try_wait(bar, parity)) return true;
     atomicExch(&g_tc_error_c1, 1);
+    if (g_err_flag_c1) { *reinterpret_cast<volatile int*>(g_err_flag_c1) = 16; __threadfence_system(); }
     return false;
 }
 
@@ -455,6 +458,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1_wgrad_kernel(Args g) {
 __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                       int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask, long c_plane);
 
+static void publish_error_flag_c1() {
+    static std::atomic<uint32_t> done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done.load() & (1u << (dev & 31))) return;
+    int* f = device_error_flag();
+    BB_CUDA(cudaMemcpyToSymbol(g_err_flag_c1, &f, sizeof(f)));
+    done.fetch_or(1u << (dev & 31));
+}
+
 // Can BOTH dedicated kernels take this first layer?  Then the replay batch need not be materialised: they read the ring rows
 // through the sampled index list (ConvGeom::in_ix).
 bool conv1_direct_ok(const ConvGeom& g) {
@@ -478,11 +491,8 @@ bool conv1_wgrad_tc(const Ctx& c, const ConvGeom& g, const float* dY, const void
     const int ctas = std::min(a.n_stages, c.sms);
     if ((size_t)ctas * 32 * K > c.ws_floats - 1024) return false;
     const size_t smem = (size_t)c1w::S * c1w::B_STAGE + 1024;
-    static bool configured = false;
-    if (!configured) {
-        BB_CUDA(cudaFuncSetAttribute(c1w::conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    BB_ENSURE_SMEM(c1w::conv1_wgrad_kernel, smem);
+    publish_error_flag_c1();
     launch_pdl(c1w::conv1_wgrad_kernel, dim3(ctas), dim3(c1w::NTHREADS), smem, c.stream, a);
     BB_LAUNCHED();
     c.mark("tc_conv1_wgrad");
@@ -506,11 +516,8 @@ bool conv1_fwd_tc(const Ctx& c, const ConvGeom& g, const void* X, const float* W
     static const int dbg = getenv("BB_CONV1_DEBUG") ? atoi(getenv("BB_CONV1_DEBUG")) : 0;
     a.dbg = dbg;
     const size_t smem = (size_t)g.C * 2 * 2 * 4096 + 1024;   // 2 slices per channel, hi + lo
-    static bool configured = false;
-    if (!configured) {
-        BB_CUDA(cudaFuncSetAttribute(c1::conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2 * 4096 + 1024));
-        configured = true;
-    }
+    BB_ENSURE_SMEM(c1::conv1_fwd_kernel, 8 * 2 * 2 * 4096 + 1024);
+    publish_error_flag_c1();
     const int ctas = std::min(a.n_tiles, 2 * c.sms);
     launch_pdl(c1::conv1_fwd_kernel, dim3(ctas), dim3(c1::NTHREADS), smem, c.stream, a);
     BB_LAUNCHED();

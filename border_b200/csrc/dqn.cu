@@ -174,6 +174,10 @@ struct Dqn : Agent {
         if (h_q) cudaFreeHost(h_q);
     }
     Model* sync_model_src() override { return &qnet; }
+    void precision_changed() override {
+        if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        if (sgexec) { cudaGraphExecDestroy(sgexec); sgexec = nullptr; }
+    }
     void grad_buffer(void** p, uint64_t* n) override { *p = qnet.g; *n = qnet.n; }
 
     void ensure_ws(int B) {

@@ -34,6 +34,9 @@ struct Ctx {
     size_t n_tickets = 0;
     void alloc_scratch(size_t floats);  // ws + tickets (zeroed on `stream`)
     void free_scratch();
+    // tensor-core precision of the TMA-fed GEMMs launched through this context: 3 = 3xTF32 (fp32 parity, the default),
+    // 1 = one TF32 product per fp32 product (the `fast` mode, bb_agent_set_precision)
+    int passes = 3;
     Profiler* prof = nullptr;
     mutable std::string phase, layer;
     void mark(const char* kernel) const;  // no-op unless prof is set

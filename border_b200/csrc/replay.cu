@@ -660,11 +660,7 @@ void Replay::launch_per_update(const unsigned long long* ixs, const float* td, s
         uint32_t threads = (m + 31) / 32 * 32;
         const int dmax = 63 - __builtin_clzll(2 * cfg.capacity - 1);  // depth of the last heap node
         size_t smem = (size_t)m * (8 * 3 + 4 * 2) + 2 * ((size_t)m * (6 + 1 + 1 + 1 + (size_t)dmax + 1) + 1);
-        static bool configured = false;
-        if (!configured) {
-            BB_CUDA(cudaFuncSetAttribute(per_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            configured = true;
-        }
+        BB_ENSURE_SMEM(per_update_kernel, 160 * 1024);
         per_update_kernel<<<1, threads, smem, stream>>>(pp, ixs ? ixs + j0 : nullptr, td ? td + j0 : nullptr, m, mode,
                                                         (uint32_t)j0, bump && last);
         BB_LAUNCHED();
@@ -903,6 +899,12 @@ int32_t bb_replay_batch_to_host(bb_replay* rb, void* obs, void* act, void* next_
         BB_CUDA(cudaMemcpyAsync(weight, r.b_weight, B * 4, cudaMemcpyDeviceToHost, s));
     }
     BB_CUDA(cudaStreamSynchronize(s));
+    BB_API_END
+}
+int32_t bb_replay_last_batch(bb_replay* rb, uint64_t* out) {
+    BB_API_BEGIN
+    BB_CHECK(rb && out, "null argument");
+    *out = rb->impl.last_batch;
     BB_API_END
 }
 int32_t bb_replay_update_priority(bb_replay* rb, const uint64_t* ixs, const float* td, size_t n, int32_t on_device) {

@@ -14,11 +14,7 @@ static void tc_launch(GemmMode mode, const GemmArgs& a, dim3 grid, cudaStream_t 
 #define BB_TC_LAUNCH(AK, BK_, AU, BU, FAST_)                                                                    \
     do {                                                                                                        \
         auto kern = tc_gemm_kernel<BN, STAGES, PF, MINB, AK, BK_, AU, BU, FAST_>;                               \
-        static bool configured = false;                                                                         \
-        if (!configured) {                                                                                      \
-            BB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-            configured = true;                                                                                  \
-        }                                                                                                       \
+        BB_ENSURE_SMEM(kern, smem);                                                                             \
         launch_pdl(kern, grid, dim3(tc::NTHREADS), smem, s, a);                                                 \
     } while (0)
     switch (mode) {
@@ -38,7 +34,18 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
 __global__ void splitk_reduce8_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                       int splits, const float* __restrict__ bias, int relu, const float* __restrict__ mask, long c_plane);
 
+static void publish_error_flag_tc() {
+    static std::atomic<uint32_t> done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done.load() & (1u << (dev & 31))) return;
+    int* f = device_error_flag();
+    BB_CUDA(cudaMemcpyToSymbol(g_tc_err_flag, &f, sizeof(f)));
+    done.fetch_or(1u << (dev & 31));
+}
+
 bool tc_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
+    publish_error_flag_tc();
     // target CTAs of a split-K launch, % of SMs.  A/B on the DQN step (us): 40: 361.5, 50: 357.2, 60: 350.2, 75: 349.1,
     // 100: 354.7, 150: 368.4 -- the split launches share the GPU with the other streams' kernels
     static const int fill_pct = getenv("BB_TC_FILL") ? atoi(getenv("BB_TC_FILL")) : 75;

@@ -27,6 +27,9 @@
 namespace bb {
 
 static __device__ int g_tc_error = 0;  // per translation unit (tc_gemm.cu reads its own copy)
+// the library's pinned, mapped failure flag (common.cuh: device_error_flag), published per device at first launch: a
+// timed-out pipeline is seen by every agent entry point, not only by the test hooks
+static __device__ int* g_tc_err_flag = nullptr;
 // debug trace (BB_TC_DEBUG bit 16): clock64 stamps of CTA (0,0,0)'s producer thread 0 and MMA thread
 static __device__ long long g_tc_trace[2][64][8];  // per translation unit
 
@@ -57,6 +60,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t it = 0; it < (1u << 22); ++it)
         if (mbar_try_wait(bar, parity)) return true;
     atomicExch(&g_tc_error, 1);
+    if (g_tc_err_flag) { *reinterpret_cast<volatile int*>(g_tc_err_flag) = 17; __threadfence_system(); }
     return false;
 }
 

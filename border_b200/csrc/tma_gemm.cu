@@ -155,7 +155,7 @@ static int env_i(const char* name, int dflt) {
 bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     using namespace tg;
     if (!env_i("BB_TMA", 1)) return false;
-    const int passes = env_i("BB_TMA_PASSES", 3) == 1 ? 1 : 3;
+    const int passes = env_i("BB_TMA_PASSES", c.passes) == 1 ? 1 : 3;
     if (mode != G_FWD && mode != G_NN && mode != G_WGRAD) return false;
     if (!c.tickets) return false;
     if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return false;

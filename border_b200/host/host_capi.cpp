@@ -137,6 +137,35 @@ int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg
     BBH_END
 }
 
+// Test hook: n_steps x Sampler::sample_and_push with a scripted policy (action of step i = i) and a recording buffer; row i of
+// `out` = {obs episode, obs pattern word, next_obs episode, next_obs pattern word, act, reward as int, is_terminated,
+// is_truncated} of the i-th pushed transition (u8 observations: bytes 0-7 hold the episode, bytes 8-15 the (episode, t) word).
+int32_t bbh_sampler_trace(const bbh_env_cfg* env_cfg, uint64_t seed, uint64_t n_steps, int64_t* out) {
+    BBH_BEGIN
+    if (!env_cfg || !out) throw Error("null argument");
+    if (env_cfg->obs_kind != BB_U8 || env_cfg->obs_elems < 16) throw Error("bbh_sampler_trace needs u8 observations of >= 16 bytes");
+    struct ScriptedPolicy : Policy {
+        int64_t i = 0;
+        Bytes sample(const Bytes&) override { Bytes a(8); memcpy(a.data(), &i, 8); ++i; return a; }
+    } policy;
+    struct Recorder : ExperienceBufferBase {
+        std::vector<Transition> rows;
+        void push(Transition&& t) override { rows.push_back(std::move(t)); }
+        size_t len() const override { return rows.size(); }
+    } rec;
+    Sampler sampler(std::make_unique<SyntheticEnv>(*env_cfg, seed), SimpleStepProcessor());
+    for (uint64_t k = 0; k < n_steps; ++k) sampler.sample_and_push(policy, rec);
+    for (size_t k = 0; k < rec.rows.size(); ++k) {
+        const Transition& t = rec.rows[k];
+        int64_t* o = out + 8 * k;
+        memcpy(&o[0], t.obs.data(), 8); memcpy(&o[1], t.obs.data() + 8, 8);
+        memcpy(&o[2], t.next_obs.data(), 8); memcpy(&o[3], t.next_obs.data() + 8, 8);
+        memcpy(&o[4], t.act.data(), 8);
+        o[5] = (int64_t)t.reward; o[6] = t.is_terminated; o[7] = t.is_truncated;
+    }
+    BBH_END
+}
+
 int32_t bbh_e2e_steps(bb_agent* agent, bb_replay* replay, const void* obs, const void* act, const void* next_obs,
                       const float* reward, const int8_t* is_terminated, const int8_t* is_truncated,
                       uint64_t obs_row_bytes, uint64_t act_row_bytes, uint64_t n_slots, uint64_t n_steps,

@@ -48,6 +48,8 @@ def host_lib():
                                       C.POINTER(bbh_trainer_cfg), C.POINTER(bbh_train_stat)]
         l.bbh_e2e_steps.restype = C.c_int32
         l.bbh_e2e_steps.argtypes = [C.c_void_p] * 8 + [C.c_uint64] * 4 + [C.POINTER(C.c_float)]
+        l.bbh_sampler_trace.restype = C.c_int32
+        l.bbh_sampler_trace.argtypes = [C.POINTER(bbh_env_cfg), C.c_uint64, C.c_uint64, C.c_void_p]
         l.bbh_env_steps.restype = C.c_int32
         l.bbh_env_steps.argtypes = [C.c_void_p] * 7 + [C.c_uint64] * 3 + [C.POINTER(C.c_int64)]
         _hl = l
@@ -110,3 +112,13 @@ def env_steps(agent, buffer, obs, next_obs, reward, is_terminated, is_truncated,
     _check(host_lib().bbh_env_steps(agent.handle, buffer.handle, *[a.ctypes.data for a in arrs], arrs[0].nbytes // n, n,
                                     n_steps, C.byref(act)))
     return act.value
+
+
+def sampler_trace(obs_elems, episode_len, truncate_len, seed, n_steps):
+    """The transitions Sampler + SimpleStepProcessor (C++ mirror) emit over the synthetic u8 environment with a scripted
+    policy: an int64 array [n_steps][8] (see include/border_host.h: bbh_sampler_trace)."""
+    import numpy as np
+    cfg = bbh_env_cfg(L.BB_U8, obs_elems, episode_len, truncate_len)
+    out = np.zeros((n_steps, 8), np.int64)
+    _check(host_lib().bbh_sampler_trace(C.byref(cfg), seed, n_steps, out.ctypes.data))
+    return out

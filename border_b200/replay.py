@@ -195,6 +195,14 @@ class SimpleReplayBuffer:
                                                 _p(trunc), _p(ix), _p(w)))
         return GenericTransitionBatch(obs, act, next_obs, reward, term, trunc, ix, w)
 
+    def last_indices(self):
+        """ix_sample of the last sampled batch (also when an agent's opt() drew it on the device)."""
+        n = C.c_uint64()
+        L.check(L.lib().bb_replay_last_batch(self.handle, C.byref(n)))
+        ix = np.empty(n.value, np.uint64)
+        L.check(L.lib().bb_replay_batch_to_host(self.handle, None, None, None, None, None, None, _p(ix), None))
+        return ix
+
     def update_priority(self, ixs, td_errs):  # base.rs:413-426
         if self.config.per_config is None:
             return

@@ -148,6 +148,10 @@ int32_t bb_replay_sample(bb_replay* rb, size_t batch_size, bb_batch_view* out);
 int32_t bb_replay_batch_to_host(bb_replay* rb, void* obs, void* act, void* next_obs, float* reward,
                                 int8_t* is_terminated, int8_t* is_truncated, uint64_t* ix_sample,
                                 float* weight);
+/* Rows in the batch the last sample call produced (by bb_replay_sample or inside bb_agent_opt); their indices can then be read
+ * with bb_replay_batch_to_host(ix only): `ix_sample` of TransitionBatch::unpack (batch.rs:66-81). */
+int32_t bb_replay_last_batch(bb_replay* rb, uint64_t* out);
+
 /* ReplayBufferBase::update_priority (base.rs:413-426).  Pointers are host unless on_device. */
 int32_t bb_replay_update_priority(bb_replay* rb, const uint64_t* ixs, const float* td_errs, size_t n,
                                   int32_t on_device);
@@ -264,7 +268,12 @@ int32_t bb_sac_create(const bb_sac_cfg* cfg, bb_agent** out);   /* sac/base.rs *
 int32_t bb_iqn_create(const bb_iqn_cfg* cfg, bb_agent** out);   /* iqn/base.rs */
 int32_t bb_agent_destroy(bb_agent* a);
 int32_t bb_agent_set_stream(bb_agent* a, void* cuda_stream);
-int32_t bb_agent_set_train(bb_agent* a, int32_t train);         /* Agent::train / eval */
+int32_t bb_agent_set_train(bb_agent* a, int32_t train);
+/* Tensor-core precision of the agent's large contractions: fast = 0 (default) 3xTF32 with fp32 accumulation -- fp32 parity
+ * with the reference's CPU path (1e-4 on losses); fast = 1 one TF32 product per fp32 product (10-bit mantissa operands,
+ * fp32 accumulation), ~2-3e-4 relative on the DQN loss (tests/test_fast_mode_gpu.py) for less tensor-core and
+ * shared-memory work.  Not part of the reference's surface: an opt-in of this implementation. */
+int32_t bb_agent_set_precision(bb_agent* a, int32_t fast);         /* Agent::train / eval */
 int32_t bb_agent_is_train(const bb_agent* a, int32_t* out);
 /* Policy::sample for `n` observations (host pointers; n = 1 in Sampler::sample_and_push).
  * act_out: int64[n] for DQN/IQN, float[n*act_dim] for SAC. */
@@ -286,6 +295,10 @@ int32_t bb_agent_param_info(bb_agent* a, const char* model, uint64_t index, char
                             size_t name_cap, int64_t* shape_out /* [4] */, int32_t* ndim_out);
 int32_t bb_agent_get_param(bb_agent* a, const char* model, const char* name, float* host_out, size_t n);
 int32_t bb_agent_set_param(bb_agent* a, const char* model, const char* name, const float* host_in, size_t n);
+/* Zeroes the Adam moments and step counters of every model (loading a reference checkpoint, which carries no optimizer
+ * state: tch VarStore archives hold the variables only, dqn/base.rs:348-362). */
+int32_t bb_agent_reset_opt_state(bb_agent* a);
+
 /* Adam moments of the same tensor (what the reference never saves; for parity tests / resume). */
 int32_t bb_agent_get_opt_state(bb_agent* a, const char* model, const char* name, float* host_m,
                                float* host_v, size_t n, uint64_t* step);

@@ -50,6 +50,12 @@ int32_t bbh_train(int32_t algo, const void* agent_cfg, const bb_replay_cfg* repl
 int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg,
                         const bbh_env_cfg* env_cfg, const bbh_trainer_cfg* trainer_cfg, bbh_train_stat* out);
 
+/* Test hook (no device work): n_steps x Sampler::sample_and_push (trainer/sampler.rs:99-144 + SimpleStepProcessor::process,
+ * step_proc.rs:103-137) with a scripted policy (action of step i = i) and a recording buffer over the synthetic u8 environment;
+ * row i of out[n_steps][8] = {obs episode, obs word, next_obs episode, next_obs word, act, reward, is_terminated, is_truncated}
+ * of the i-th pushed transition. */
+int32_t bbh_sampler_trace(const bbh_env_cfg* env_cfg, uint64_t seed, uint64_t n_steps, int64_t* out);
+
 /* Measurement aid: `n_steps` iterations of the Trainer's inner loop on EXISTING handles, all through
  * the C ABI with host buffers: bb_replay_push(one host transition) + bb_agent_opt(record) -- the
  * loss is read back to the host every step (trainer.rs:206-228 with opt_interval 1).  The n_slots

@@ -369,3 +369,82 @@ class IqnOracle:
             self.soft_update_counter = 0
             track(self.iqn_tgt, self.iqn, self.tau)
         return loss
+
+
+# ------------------------------------------------------------------------------------ explorers
+
+class FastRandPy:
+    """fastrand 1.x wyrand (the global RNG the reference's explorers draw from: dqn/explorer.rs:71,82, dqn/base.rs:231-233),
+    restated in pure Python integers: s += 0xA0761D6478BD642F; t = s * (s ^ 0xE7037ED1A0B428DB) (128 bit); out = lo ^ hi.
+    f64() = from_bits(0x3FF0.. | (u64 >> 12)) - 1; f32() likewise on the low 32 bits; u32(..n) / u64(..n) = Lemire's
+    multiply-high with rejection.  Seeded explicitly here (the reference never seeds it: no run-to-run vector exists)."""
+    M64 = (1 << 64) - 1
+
+    def __init__(self, seed):
+        self.s = seed & self.M64
+
+    def u64(self):
+        self.s = (self.s + 0xA0761D6478BD642F) & self.M64
+        t = self.s * (self.s ^ 0xE7037ED1A0B428DB)
+        return (t & self.M64) ^ (t >> 64)
+
+    def u32(self):
+        return self.u64() & 0xFFFFFFFF
+
+    def f64(self):
+        import struct
+        return struct.unpack("<d", struct.pack("<Q", 0x3FF0000000000000 | (self.u64() >> 12)))[0] - 1.0
+
+    def f32(self):
+        import struct
+        import numpy as np
+        return float(np.float32(struct.unpack("<f", struct.pack("<I", 0x3F800000 | (self.u32() >> 9)))[0]) - np.float32(1.0))
+
+    def _below(self, n, bits):
+        mask = (1 << bits) - 1
+        draw = self.u32 if bits == 32 else self.u64
+        x = draw()
+        m = x * n
+        hi, lo = m >> bits, m & mask
+        if lo < n:
+            t = ((1 << bits) - n) % n
+            while lo < t:
+                x = draw()
+                m = x * n
+                hi, lo = m >> bits, m & mask
+        return hi
+
+    def u32_below(self, n):
+        return self._below(n, 32)
+
+    def u64_below(self, n):
+        return self._below(n, 64)
+
+
+class EpsilonGreedyOracle:
+    """dqn/explorer.rs:33-90 (`EpsilonGreedy::action`) and the eval branch of `Dqn::sample` (dqn/base.rs:229-236)."""
+
+    def __init__(self, fr, eps_start=1.0, eps_final=0.02, final_step=100_000):
+        self.fr, self.n_opts = fr, 0
+        self.eps_start, self.eps_final, self.final_step = eps_start, eps_final, final_step
+
+    def action(self, q):
+        """q: [n_procs, n_actions] tensor of action values."""
+        d = (self.eps_start - self.eps_final) / float(self.final_step)
+        eps = max(self.eps_start - d * float(self.n_opts), self.eps_final)
+        r = self.fr.f64()
+        is_random = r < eps
+        self.n_opts += 1
+        best = [int(x) for x in q.argmax(-1)]
+        if is_random:
+            return [self.fr.u32_below(q.shape[1]) for _ in range(q.shape[0])]
+        return best
+
+    def eval_action(self, q):
+        out = []
+        for i in range(q.shape[0]):
+            if self.fr.f32() < 0.01:
+                out.append(self.fr.u64_below(q.shape[1]))
+            else:
+                out.append(int(q[i].argmax(-1)))
+        return out

@@ -52,7 +52,8 @@ def _check_params(agent, oracle, lr, model="qnet", ref=None, tol_lr=2e-2, n_step
         assert (d > tol_lr * lr + 1e-7).mean() <= 2e-3 * n_steps, (k, (d > tol_lr * lr).mean(), d.max())
 
 
-def _run(kind, B, critic_loss, double_dqn, per, clip, steps=3, lr=1e-3, soft_update_interval=2, tau=0.5):
+def _run(kind, B, critic_loss, double_dqn, per, clip, steps=3, lr=1e-3, soft_update_interval=2, tau=0.5, opt=None,
+         teacher_forced=False, check_indices=False):
     rng = np.random.default_rng(7)
     gen = torch.Generator().manual_seed(0)
     if kind == "cnn":
@@ -70,7 +71,12 @@ def _run(kind, B, critic_loss, double_dqn, per, clip, steps=3, lr=1e-3, soft_upd
     dev = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=cap, seed=42, per_config=PerConfig(**perd) if per else None))
     orc = ro.ReplayOracle(cap, 42, obs_shape, obs_dtype, (1,), np.int64, per=perd)
     _fill(dev, orc, rng, 280, obs_shape, obs_dtype, n_act)
-    cfg = DqnConfig(model_config=DqnModelConfig(q_config=qcfg, opt_config=OptimizerConfig(lr=lr)),
+    opt_cfg = opt if opt is not None else OptimizerConfig(lr=lr)
+    lr = opt_cfg.lr
+    opt_kwargs = None
+    if opt_cfg.kind == "AdamW":
+        opt_kwargs = dict(beta1=opt_cfg.beta1, beta2=opt_cfg.beta2, eps=opt_cfg.eps, wd=opt_cfg.wd, adamw=True)
+    cfg = DqnConfig(model_config=DqnModelConfig(q_config=qcfg, opt_config=opt_cfg),
                     soft_update_interval=soft_update_interval, n_updates_per_opt=1, batch_size=B, discount_factor=0.99,
                     tau=tau, train=True, explorer=EpsilonGreedy(), double_dqn=double_dqn,
                     clip_td_err=(0.05, 1.5) if clip else None, device=0, critic_loss=critic_loss, record_verbose_level=2)
@@ -78,18 +84,29 @@ def _run(kind, B, critic_loss, double_dqn, per, clip, steps=3, lr=1e-3, soft_upd
     agent.set_parameters("qnet", {k: v.numpy() for k, v in params.items()})
     agent.set_parameters("qnet_tgt", {k: v.numpy() for k, v in params.items()})
     oracle = ao.DqnOracle(params, fwd, lr, B, 0.99, tau, soft_update_interval, 1, double_dqn,
-                          (0.05, 1.5) if clip else None, critic_loss)
+                          (0.05, 1.5) if clip else None, critic_loss, opt_kwargs=opt_kwargs)
     for step in range(steps):
         u = rng.random(B, dtype=np.float32) if per else None
         if per:
             dev.inject_uniforms(u)
         rec = agent.opt_with_record(dev)
-        loss_o = oracle.opt_(lambda: _torch_batch(orc.batch(B, u)), orc.update_priority)
+        seen = {}
+
+        def sample():
+            seen["b"] = orc.batch(B, u)
+            return _torch_batch(seen["b"])
+
+        loss_o = oracle.opt_(sample, orc.update_priority)
         assert abs(rec["loss"] - loss_o) <= LOSS_RTOL * abs(loss_o) + 1e-7, (step, rec["loss"], loss_o)
+        if check_indices:  # the device drew the same rows as the oracle (uniform: bit-exact stream; PER: same tree walk)
+            assert np.array_equal(dev.last_indices(), np.asarray(seen["b"]["ix_sample"], dtype=np.uint64)), step
         assert abs(rec["pred_mean"] - float(oracle.last["pred"].mean())) < 1e-4
         assert abs(rec["tgt_mean"] - float(oracle.last["tgt"].mean())) < 1e-4
-        _check_params(agent, oracle, lr, n_steps=step + 1)
-        _check_params(agent, oracle, lr, "qnet_tgt", oracle.qnet_tgt, n_steps=step + 1)
+        _check_params(agent, oracle, lr, n_steps=1 if teacher_forced else step + 1)
+        _check_params(agent, oracle, lr, "qnet_tgt", oracle.qnet_tgt, n_steps=1 if teacher_forced else step + 1)
+        if teacher_forced:  # G8: re-synchronise the weights, so every step is compared from identical state
+            agent.set_parameters("qnet", {k: v.detach().numpy() for k, v in oracle.qnet.items()})
+            agent.set_parameters("qnet_tgt", {k: v.detach().numpy() for k, v in oracle.qnet_tgt.items()})
         if per:  # priorities inherit the network tolerance (SURVEY hard parts): compare loosely
             t_dev = dev.dump_sum_tree()[0]
             t_orc = orc.sum_tree()[0]
@@ -206,3 +223,20 @@ def test_graph_replay_of_the_update_is_bit_identical_to_eager_launches(monkeypat
         assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
         assert np.array_equal(outs[0][2][k], outs[1][2][k]), k
     assert outs[0][3] == outs[1][3]
+
+
+def test_dqn_adamw_parity():
+    """OptimizerConfig::AdamW (opt.rs:38-54): decoupled weight decay, all hyper-parameters given."""
+    _run("mlp", 32, "Mse", False, per=False, clip=False, steps=5,
+         opt=OptimizerConfig(kind="AdamW", lr=1e-3, beta1=0.8, beta2=0.99, wd=0.05, eps=1e-6))
+
+
+def test_dqn_mlp_100_step_teacher_forced_trajectory():
+    """100 updates, weights re-synchronised from the oracle after every step, loss within 1e-4 at each."""
+    _run("mlp", 64, "SmoothL1", True, per=False, clip=False, steps=100, teacher_forced=True, check_indices=True)
+
+
+def test_dqn_per_atari_cnn_20_steps():
+    """DQN + PER on the NatureCNN over 20 updates: losses within 1e-4 at every step, the sampled rows identical at every
+    step (the sum-tree walks agree although priorities carry the network tolerance), tree within 2e-3."""
+    _run("cnn", 16, "SmoothL1", False, per=True, clip=True, steps=20, lr=1e-4, teacher_forced=True, check_indices=True)

@@ -13,7 +13,7 @@ from oracle import agent_oracle as ao
 from oracle import replay_oracle as ro
 
 
-def _setup(kind, B, n_act, lr, sample="Uniform8"):
+def _setup(kind, B, n_act, lr, sample="Uniform8", per=None, cap=200, n=180):
     rng = np.random.default_rng(11)
     gen = torch.Generator().manual_seed(3)
     # feature extractor = AtariCnn.skip_linear, merge net = Mlp(3136 -> 512 -> A): the shapes of
@@ -28,10 +28,9 @@ def _setup(kind, B, n_act, lr, sample="Uniform8"):
     m_params = ao.mlp_params(F, m_units, n_act, gen)
     params = ao.iqn_params(f_params, F, E, m_params, gen)
     m_fn = lambda p, m: ao.mlp_forward(p, m, len(m_units) + 1)
-    cap = 200
-    dev = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=cap, seed=9))
-    orc = ro.ReplayOracle(cap, 9, obs_shape, obs_dtype, (1,), np.int64)
-    n = 180
+    from border_b200.replay import PerConfig
+    dev = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=cap, seed=9, per_config=PerConfig(**per) if per else None))
+    orc = ro.ReplayOracle(cap, 9, obs_shape, obs_dtype, (1,), np.int64, per=per)
     obs = rng.integers(0, 256, (n,) + obs_shape, dtype=np.uint8)
     nxt = rng.integers(0, 256, (n,) + obs_shape, dtype=np.uint8)
     tr = GenericTransitionBatch(obs, rng.integers(0, n_act, (n, 1)).astype(np.int64), nxt,
@@ -77,6 +76,26 @@ def test_iqn_atari_update_parity(sample, N):
         assert abs(rec["loss_critic"] - ref) <= 1e-4 * abs(ref) + 1e-7, (step, rec["loss_critic"], ref)
         _close(agent, "iqn", oracle.iqn, lr)
         _close(agent, "iqn_tgt", oracle.iqn_tgt, lr)
+
+
+def test_iqn_baseline_shape_b256_n64_on_a_prioritized_ring():
+    """BASELINE configs[3] as the bench runs it: B = 256, N = N' = 64, prioritized replay (sampling + IS weights; the
+    reference's IQN never updates priorities): rows drawn identical to the oracle's, loss within 1e-4."""
+    B, N, lr = 256, 64, 1e-4
+    per = dict(alpha=0.6, beta_0=0.4, beta_final=1.0, n_opts_final=500000, normalize="All")
+    rng, dev, orc, agent, oracle, *_ = _setup("cnn", B, 4, lr, "Uniform64", per=per, cap=512, n=400)
+    t1 = rng.random((B, N), dtype=np.float32)
+    t2 = rng.random((B, N), dtype=np.float32)
+    u = rng.random(B, dtype=np.float32)
+    agent.inject_noise(0, t1)
+    agent.inject_noise(1, t2)
+    dev.inject_uniforms(u)
+    rec = agent.opt_with_record(dev)
+    b = orc.batch(B, u)
+    assert np.array_equal(dev.last_indices(), np.asarray(b["ix_sample"], dtype=np.uint64))
+    ref = oracle.opt_(_tb(b), torch.from_numpy(t1), torch.from_numpy(t2))
+    assert abs(rec["loss_critic"] - ref) <= 1e-4 * abs(ref) + 1e-7, (rec["loss_critic"], ref)
+    _close(agent, "iqn", oracle.iqn, lr)
 
 
 def test_iqn_const_modes_policy_and_errors():
