@@ -389,6 +389,37 @@ def run_b200(args):
                "env_steps": {"value": ve, "unit": "env-steps/s", "cores": os.cpu_count() or 1,
                              "sample": "%d x (B=1 NatureCNN Policy::sample + replay push, zero-cost env), %.1f s" % (max(200, args.cpu_steps), dte)}}
 
+    # ---- multi-GPU parity evidence: after every update above (different replay rows on every rank) all ranks must hold
+    # bit-identical parameters -- compare a SHA-256 of the online network across ranks
+    ranks_bit_identical, param_digest = None, None
+    if world > 1 and sync_mode != "none":
+        import hashlib
+        hsh = hashlib.sha256()
+        for k, v in sorted(agent.named_parameters("qnet").items()):
+            hsh.update(np.ascontiguousarray(v).tobytes())
+        param_digest = hsh.hexdigest()
+        d = torch.tensor(list(hsh.digest()), dtype=torch.uint8, device="cuda")
+        ds = [torch.empty_like(d) for _ in range(world)]
+        dist.all_gather(ds, d)
+        ranks_bit_identical = all(bool(torch.equal(x, ds[0])) for x in ds)
+
+    exchange_trace = None
+    if world > 1 and sync_mode != "none":
+        # device-side stamps of the gradient exchange over a few updates (ns relative to the previous update's Adam start)
+        import ctypes as _C
+        rows, prev = [], None
+        for _ in range(6):
+            agent.opt(rb)
+            buf = (_C.c_uint32 * 32)()
+            L.check(lib.bb_agent_exchange_trace(agent.handle, buf))
+            t = list(buf)
+            rel = lambda a_, b_: int((a_ - b_) & 0xFFFFFFFF) if a_ and b_ else None
+            rows.append({"step_ns": rel(t[16], prev) if prev else None, "fc_start_to_adam_ns": rel(t[16], t[8]),
+                         "fc_wait_ns": rel(t[9], t[8]), "fc_reduce_ns": rel(t[10], t[9]), "conv_start_to_adam_ns": rel(t[16], t[12]),
+                         "conv_wait_ns": rel(t[13], t[12]), "conv_reduce_ns": rel(t[14], t[13]), "fc_fence_ns": rel(t[10], t[11]), "conv_fence_ns": rel(t[14], t[15]), "adam_wait_ns": rel(t[17], t[16])})
+            prev = t[16]
+        exchange_trace = rows[1:]
+
     if rank == 0:
         out = {"metric": "grad-steps/sec", "value": value, "unit": "grad-steps/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -409,6 +440,11 @@ def run_b200(args):
                "roofline": roof, "roofline_replay": roof_replay,
                "step_flop": STEP_FLOP, "step_tflops": STEP_FLOP / (ms / args.steps * 1e-3) / 1e12,
                "kernel_breakdown_ms": {k: round(v, 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:12]}}
+        if ranks_bit_identical is not None:
+            out["ranks_bit_identical"] = ranks_bit_identical
+            out["exchange_trace_rank0"] = exchange_trace
+            out["param_sha256_rank0"] = param_digest
+            out["updates_before_checksum"] = int(agent.n_opts()) if hasattr(agent, "n_opts") else None
         if extra:
             out["other_workloads"] = extra
         if cpu:

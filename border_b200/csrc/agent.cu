@@ -16,7 +16,7 @@ void Model::alloc(bool with_opt) {
     has_opt = with_opt;
     p = dev_alloc_zero<float>(2 * n);  // parameters + their lo plane
     if (with_opt) {
-        g = dev_alloc_zero<float>(n);
+        g = dev_alloc_zero<float>(n + 16 * g_ll_cap);
         m = dev_alloc_zero<float>(n);
         v = dev_alloc_zero<float>(n);
     }
@@ -73,9 +73,16 @@ void Agent::init_base(int dev) {
         BB_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
         if (!serial) ctx.side[i] = &s;
     }
+    comm_ctx.device = dev; comm_ctx.sms = ctx.sms;
+    BB_CUDA(cudaStreamCreateWithFlags(&comm_ctx.stream, cudaStreamNonBlocking));
+    BB_CUDA(cudaEventCreateWithFlags(&comm_ctx.ev, cudaEventDisableTiming));
+    xchg_ctr = dev_alloc_zero<unsigned int>(32, ctx.stream);
     BB_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 Agent::~Agent() {
+    if (comm_ctx.stream) { cudaStreamSynchronize(comm_ctx.stream); cudaStreamDestroy(comm_ctx.stream); }
+    if (comm_ctx.ev) cudaEventDestroy(comm_ctx.ev);
+    cudaFree(xchg_ctr);
     for (int i = 0; i < 2; ++i) {
         if (side_ctx[i].stream) { cudaStreamSynchronize(side_ctx[i].stream); cudaStreamDestroy(side_ctx[i].stream); }
         side_ctx[i].free_scratch();
@@ -145,22 +152,68 @@ void Agent::grad_sync_begin() {
 void Agent::grad_sync_end() {
     if (world > 1) peer_barrier(this);
 }
-void Agent::synced_adam(Model& m) {
+Exchange Agent::exchange() const {
+    Exchange x{};
+    for (int r = 0; r < 8; ++r) { x.grads[r] = r < world ? peer_grad[r] : nullptr; x.flags[r] = r < world ? peer_flag[r] : nullptr; }
+    x.ctr = xchg_ctr; x.rank = rank; x.world = world; x.err = device_error_flag(); x.timeout_cycles = peer_timeout_cycles();
+    return x;   // (ll_off / ll_cap: set by synced_adam from the model)
+}
+
+// Called from inside Net::backward once the weight gradients of the region's layers are enqueued (main stream + both side
+// streams): the comm stream waits for all three and runs the region-0 exchange while the convolution backward continues.
+void Agent::begin_early_exchange(Model& m, size_t split) {
+    if (world <= 1) return;
+    for (const Ctx* s : {(const Ctx*)&ctx, ctx.side[0], ctx.side[1]}) {
+        if (!s) continue;
+        BB_CUDA(cudaEventRecord(s->ev, s->stream));
+        BB_CUDA(cudaStreamWaitEvent(comm_ctx.stream, s->ev, 0));
+    }
+    comm_ctx.prof = ctx.prof; comm_ctx.phase = "optimizer";
+    static const int early_blocks = getenv("BB_XCHG_EARLY_BLOCKS") ? atoi(getenv("BB_XCHG_EARLY_BLOCKS")) : 24;
+    grad_exchange(comm_ctx, exchange(), split, m.n, 0, early_blocks);
+}
+void Agent::join_early_exchange() {
+    if (world <= 1) return;
+    BB_CUDA(cudaEventRecord(comm_ctx.ev, comm_ctx.stream));
+    BB_CUDA(cudaStreamWaitEvent(ctx.stream, comm_ctx.ev, 0));
+}
+
+// Optimizer step of a data-parallel replica.  world 1: plain Adam.  Otherwise the mean gradient is formed by
+// grad_exchange_kernel (each rank reduces 1/world of a region and stores it to every rank over NVLink; the rendezvous is
+// folded into the kernels) and Adam waits in its prologue for every rank's slice: with `early` the big region [split, n) was
+// already exchanged under the backward pass (begin_early_exchange) and only [0, split) is exchanged here.
+// BB_GRAD_SYNC=legacy keeps the round-1 sequence (barrier launch, reduce-scatter or all-read Adam, barrier launch).
+void Agent::synced_adam(Model& m, bool early, size_t split) {
     if (world <= 1) {
         adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1, m.p_lo());
         return;
     }
     const char* e = getenv("BB_GRAD_SYNC");
-    const bool sharded = e ? strcmp(e, "sharded") == 0 : world >= 4;
-    peer_barrier(this);  // every rank's gradient is complete
-    if (sharded) {
-        grad_reduce_scatter(ctx, peer_grad, m.n, rank, world);
-        peer_barrier(this);  // every slice of the mean has landed in this rank's buffer (and nobody still reads the old one)
-        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1, m.p_lo());
-    } else {
-        adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, peer_grad, world, m.p_lo());
-        peer_barrier(this);  // everyone done reading before anyone overwrites
+    if (e && (!strcmp(e, "legacy") || !strcmp(e, "sharded") || !strcmp(e, "fused"))) {
+        BB_CHECK(!early, "the legacy gradient exchange has no early region");
+        const bool sharded = !strcmp(e, "legacy") ? world >= 4 : !strcmp(e, "sharded");
+        peer_barrier(this);  // every rank's gradient is complete
+        if (sharded) {
+            grad_reduce_scatter(ctx, peer_grad, m.n, rank, world);
+            peer_barrier(this);  // every slice of the mean has landed in this rank's buffer (and nobody still reads the old one)
+            adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1, m.p_lo());
+        } else {
+            adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, peer_grad, world, m.p_lo());
+            peer_barrier(this);  // everyone done reading before anyone overwrites
+        }
+        return;
     }
+    Exchange x = exchange();
+    x.ll_off = m.n; x.ll_cap = m.g_ll_cap;
+    int regions = 1;
+    if (early) {
+        const char* ll = getenv("BB_XCHG_LL");
+        if (split > 0 && split <= m.g_ll_cap && !(ll && !strcmp(ll, "0"))) grad_exchange_ll(ctx, x, 0, split);   // complete when the kernel ends
+        else if (split > 0) { grad_exchange(ctx, x, 0, split, 1); regions = 3; }
+    } else {
+        grad_exchange(ctx, x, 0, m.n, 0);
+    }
+    adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1, m.p_lo(), &x, regions);
 }
 
 // ------------------------------------------------------------------------------- checkpoints
@@ -590,6 +643,13 @@ int32_t bb_agent_inject_noise(bb_agent* a, int32_t slot, const float* host, size
     BB_API_BEGIN
     BB_CHECK(host, "null argument");
     A(a).inject_noise(slot, host, n);
+    BB_API_END
+}
+int32_t bb_agent_exchange_trace(bb_agent* a, uint32_t* out32) {
+    BB_API_BEGIN
+    bb::Agent& ag = A(a);
+    BB_CUDA(cudaStreamSynchronize(ag.ctx.stream));
+    BB_CUDA(cudaMemcpy(out32, ag.xchg_ctr, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     BB_API_END
 }
 int32_t bb_agent_grad_buffer(bb_agent* a, void** dev_ptr, uint64_t* n_floats) {

@@ -66,6 +66,9 @@ struct Model {
     uint64_t step = 0;
     AdamHyper hyper{};
     bool has_opt = true;
+    // floats behind g (same allocation, so the peers' CUDA-IPC mapping of g covers them): the receive area of the
+    // flag-in-data gradient exchange (nn.cuh: grad_exchange_ll), 8 sender slots x 2 x g_ll_cap floats
+    size_t g_ll_cap = 0;
     void alloc(bool with_opt);
     void release();
     void set_hyper(const bb_opt_cfg& o);
@@ -91,12 +94,20 @@ struct Agent {
     unsigned int* my_flags = nullptr;
     unsigned int sync_epoch = 0;
     const float* const* peer_grads() const { return world > 1 ? peer_grad : nullptr; }
+    // overlapped exchange (nn.cuh: Exchange): own stream so that waiting for peers never blocks a compute stream
+    Ctx comm_ctx;
+    unsigned int* xchg_ctr = nullptr;
+    Exchange exchange() const;
+    // region 0 = [split, n) is exchanged from inside the backward pass (begin_early_exchange, on comm_ctx), region 1 =
+    // [0, split) and the optimizer follow at the end (synced_adam with early = true)
+    void begin_early_exchange(Model& m, size_t split);
+    void join_early_exchange();
     void grad_sync_begin();  // all ranks' gradients complete before anyone reads them
     void grad_sync_end();    // everyone done reading before anyone overwrites
     // Optimizer step of a data-parallel replica.  world 1: plain Adam.  world 2-3: ONE kernel reads every rank's
     // gradient and applies Adam (fused all-reduce + optimizer).  world >= 4: sharded mean (reduce-scatter +
     // broadcast through peer stores) then local Adam.  BB_GRAD_SYNC=fused|sharded overrides the choice.
-    void synced_adam(Model& m);
+    void synced_adam(Model& m, bool early = false, size_t split = 0);
 
     virtual ~Agent();
     void init_base(int dev);

@@ -145,7 +145,7 @@ struct Dqn : Agent {
         train = c.train != 0;
         net.build(c.q_config, "");
         net.init_tables(device);
-        qnet.name = "qnet"; qnet.params = net.params; qnet.n = net.n_params; qnet.alloc(true); qnet.set_hyper(c.opt_config);
+        qnet.name = "qnet"; qnet.params = net.params; qnet.n = net.n_params; qnet.g_ll_cap = early_split(); qnet.alloc(true); qnet.set_hyper(c.opt_config);
         // qnet_tgt = qnet.clone(): own VarStore AND own optimizer in the reference (never stepped)
         qnet_tgt.name = "qnet_tgt"; qnet_tgt.params = net.params; qnet_tgt.n = net.n_params; qnet_tgt.alloc(false);
         net.init_params(ctx, qnet.p, c.init_seed);
@@ -179,6 +179,18 @@ struct Dqn : Agent {
         if (sgexec) { cudaGraphExecDestroy(sgexec); sgexec = nullptr; }
     }
     void grad_buffer(void** p, uint64_t* n) override { *p = qnet.g; *n = qnet.n; }
+
+    // first fully connected layer: its weight gradient and everything after it in the flat vector form the early region
+    int early_layer() const {
+        for (size_t i = 0; i < net.layers.size(); ++i)
+            if (net.layers[i].type == 0) return (int)i;
+        return 0;
+    }
+    size_t early_split() const { return net.layers[early_layer()].w_off; }
+    bool early_exchange_on() const {
+        const char* e = getenv("BB_GRAD_SYNC");
+        return world > 1 && ctx.concurrent() && !(e && (!strcmp(e, "legacy") || !strcmp(e, "sharded") || !strcmp(e, "fused") || !strcmp(e, "late")));
+    }
 
     void ensure_ws(int B) {
         if (B <= ws_batch) return;
@@ -241,7 +253,13 @@ struct Dqn : Agent {
         ctx.mark("d2h_32B");  // (profiled runs are serial: without its own mark the copy's latency lands on the next kernel)
         ctx.phase = "backward";
         // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
-        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0, 0, in_ix);
+        // data-parallel replicas: the gradients of the fully connected layers (95 % of the vector) are exchanged as soon as
+        // they exist, under the convolution backward (agent.cuh: begin_early_exchange)
+        const std::function<void()> hook = [this]() { begin_early_exchange(qnet, early_split()); };
+        const bool early = early_exchange_on();
+        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0, 0, in_ix, early ? early_layer() : -1,
+                     early ? &hook : nullptr);
+        if (early) join_early_exchange();
         if (conc) ctx.join_from(rctx);  // (backward joins the side streams it used; this one may not be among them)
     }
 
@@ -304,7 +322,7 @@ struct Dqn : Agent {
         }
         qnet.step += 1;
         ctx.phase = "optimizer";
-        synced_adam(qnet);
+        synced_adam(qnet, early_exchange_on(), early_split());
         if (bv.weight) {  // :142-143
             if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
             rb.update_priority_dev((const unsigned long long*)bv.ix_sample, d_td, B);

@@ -632,7 +632,7 @@ __device__ __forceinline__ float4 mean_over_ranks4(const PeerPtrs& peers, size_t
     float4 t[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
-        t[r] = r < world ? reinterpret_cast<const float4*>(peers.p[r])[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        t[r] = r < world ? __ldcv(reinterpret_cast<const float4*>(peers.p[r]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 1; s < 8; s *= 2)
 #pragma unroll
@@ -653,11 +653,42 @@ __device__ __forceinline__ float mean_over_ranks1(const PeerPtrs& peers, size_t 
     return t[0] / (float)world;
 }
 
+__device__ __forceinline__ unsigned int gtimer_lo() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return (unsigned int)t;
+}
+
+// Spin until every rank's slot of `kind` in this rank's flag array has reached `epoch` (threads 0..world-1 of the block).
+// No fence here: a system-scope fence costs 3-7 us on a busy GPU (measured through the %globaltimer stamps below), and the
+// data the flags guard is read with L1-bypassing loads (__ldcv) issued after the barrier -- the writer fenced before it
+// raised the flag, so by the time the flag is visible the data is in the owner's L2, where peer and local loads both go.
+__device__ __forceinline__ void wait_flags(const Exchange& x, int kind, unsigned int epoch) {
+    if ((int)threadIdx.x < x.world) {
+        volatile unsigned int* f = x.flags[x.rank] + xflag(kind, (int)threadIdx.x);
+        const long long t0 = clock64();
+        while ((int)(*f - epoch) < 0) {
+            if (clock64() - t0 > x.timeout_cycles) {   // a peer never arrived: raise the sticky failure flag, do not hang
+                *reinterpret_cast<volatile int*>(x.err) = 21;
+                __threadfence_system();
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // n4 = n / 4 float4 groups (every tensor of the flat vector is 16 B aligned and padded), tail scalars after.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float b1, float b2, float one_m_b1, float one_m_b2,
                             float eps, float bc2_sqrt, float neg_step, float wd, float decay, int adamw,
-                            PeerPtrs peers, int world, float* __restrict__ p_lo) {
+                            PeerPtrs peers, int world, float* __restrict__ p_lo, Exchange xw, int wait_regions) {
+    if (wait_regions) {   // every rank's slice of the mean gradient has landed in this rank's buffer
+        if (blockIdx.x == 0 && threadIdx.x == 0) xw.ctr[16] = gtimer_lo();
+        if (wait_regions & 1) wait_flags(xw, 1, xw.ctr[0]);
+        if (wait_regions & 2) wait_flags(xw, 3, xw.ctr[1]);
+        if (blockIdx.x == 0 && threadIdx.x == 0) xw.ctr[17] = gtimer_lo();
+    }
     const size_t n4 = n >> 2;
     const float inv_world = 1.0f;
     (void)inv_world;
@@ -666,7 +697,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         if (world > 1) {
             gi = mean_over_ranks4(peers, i, world);
         } else {
-            gi = reinterpret_cast<const float4*>(g)[i];
+            // (after an exchange the buffer was written by the peers: read it past L1, see wait_flags)
+            gi = wait_regions ? __ldcv(reinterpret_cast<const float4*>(g) + i) : reinterpret_cast<const float4*>(g)[i];
         }
         float4 pi = reinterpret_cast<float4*>(p)[i], mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
         adam_elem(pi.x, gi.x, mi.x, vi.x, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
@@ -681,7 +713,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         if (world > 1) {
             gi = mean_over_ranks1(peers, i, world);
         } else {
-            gi = g[i];
+            gi = wait_regions ? __ldcv(g + i) : g[i];
         }
         float pi = p[i], mi = m[i], vi = v[i];
         adam_elem(pi, gi, mi, vi, b1, b2, one_m_b1, one_m_b2, eps, bc2_sqrt, neg_step, wd, decay, adamw);
@@ -710,6 +742,149 @@ __global__ void grad_reduce_scatter_kernel(PeerPtrs peers, size_t n, int rank, i
         }
 }
 
+// One launch per region.  Each thread keeps U float4 of every rank in flight (the peer loads are NVLink round trips of
+// ~1 us: bandwidth comes from bytes in flight, not from loop iterations), reduces with the pairwise tree of mean_over_ranks4
+// and stores the mean to every rank.  W (the world size) is a template parameter so that every rank index is static: with a
+// runtime index the pointer table goes to local memory and ptxas serialises the loads (measured: 21 us per loop iteration).
+// ctr[8 + 4*region ..] receive %globaltimer stamps (start / after the rendezvous / end) for bench.py's exchange trace.
+template <int W>
+__global__ void __launch_bounds__(256) grad_exchange_kernel(Exchange x, size_t lo4, size_t hi4, int region) {
+    constexpr int U = W <= 2 ? 8 : W <= 4 ? 4 : 2;
+    __shared__ bool s_last;
+    const unsigned int epoch = x.ctr[region] + 1;   // (bumped by the last block of THIS launch, after every block has read it)
+    // (this rank's gradient kernels completed before this launch: their output is in this GPU's L2, where peer loads go)
+    if (blockIdx.x == 0 && (int)threadIdx.x < W)
+        *reinterpret_cast<volatile unsigned int*>(x.flags[threadIdx.x] + xflag(2 * region, x.rank)) = epoch;
+    if (blockIdx.x == 0 && threadIdx.x == 0) x.ctr[8 + 4 * region] = gtimer_lo();
+    wait_flags(x, 2 * region, epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) x.ctr[9 + 4 * region] = gtimer_lo();
+    const size_t per = (hi4 - lo4 + W - 1) / W;
+    const size_t a = lo4 + (size_t)x.rank * per, b = a + per < hi4 ? a + per : hi4;
+    for (size_t base = a + (size_t)blockIdx.x * (256 * U); base < b; base += (size_t)gridDim.x * (256 * U)) {
+        float4 t[U][W];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = base + u * 256 + threadIdx.x;
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                t[u][r] = i < b ? __ldcv(reinterpret_cast<const float4*>(x.grads[r]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int s = 1; s < W; s *= 2)
+#pragma unroll
+                for (int r = 0; r + s < W; r += 2 * s) {
+                    t[u][r].x += t[u][r + s].x; t[u][r].y += t[u][r + s].y; t[u][r].z += t[u][r + s].z; t[u][r].w += t[u][r + s].w;
+                }
+            const float w = (float)W;
+            t[u][0] = make_float4(t[u][0].x / w, t[u][0].y / w, t[u][0].z / w, t[u][0].w / w);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = base + u * 256 + threadIdx.x;
+            if (i < b) {
+#pragma unroll
+                for (int r = 0; r < W; ++r) reinterpret_cast<float4*>(const_cast<float*>(x.grads[r]))[i] = t[u][0];
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) x.ctr[11 + 4 * region] = gtimer_lo();
+    // the ONE system fence of the exchange: this thread's peer stores have landed.  (acq_rel, not __threadfence_system():
+    // that one is fence.sc.sys, which also joins the global order of all sc fences and costs several us more)
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&x.ctr[2 + region], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;      // (every other block fenced before its ticket, and this block drew the last ticket after them)
+    if ((int)threadIdx.x < W) *reinterpret_cast<volatile unsigned int*>(x.flags[threadIdx.x] + xflag(2 * region + 1, x.rank)) = epoch;
+    if (threadIdx.x == 0) { x.ctr[2 + region] = 0u; x.ctr[region] = epoch; x.ctr[10 + 4 * region] = gtimer_lo(); }
+}
+
+void grad_exchange(const Ctx& c, const Exchange& x, size_t lo, size_t hi, int region, int max_blocks) {
+    BB_CHECK((lo & 3) == 0 && (hi & 3) == 0, "grad_exchange: regions are whole 16-byte groups");
+    BB_CHECK(x.world >= 2 && x.world <= 8, "grad_exchange: 2..8 ranks");
+    const size_t per = ((hi - lo) / 4 + x.world - 1) / x.world;
+    const int U = x.world <= 2 ? 8 : x.world <= 4 ? 4 : 2;
+    // under the backward pass (max_blocks > 0) a bounded number of blocks keeps NVLink busy without taking SMs from the
+    // GEMMs (a resident exchange block costs a GEMM CTA its slot); alone on the GPU the kernel spreads over every SM
+    static const int mult = getenv("BB_XCHG_BLOCKS_PER_SM") ? atoi(getenv("BB_XCHG_BLOCKS_PER_SM")) : 2;
+    const size_t cap = max_blocks > 0 ? (size_t)max_blocks : (size_t)c.sms * mult;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((per + 256 * U - 1) / (256 * U), cap));
+    switch (x.world) {
+#define BB_XCHG_CASE(W) case W: grad_exchange_kernel<W><<<blocks, 256, 0, c.stream>>>(x, lo / 4, hi / 4, region); break;
+        BB_XCHG_CASE(2) BB_XCHG_CASE(3) BB_XCHG_CASE(4) BB_XCHG_CASE(5) BB_XCHG_CASE(6) BB_XCHG_CASE(7) BB_XCHG_CASE(8)
+#undef BB_XCHG_CASE
+    }
+    BB_LAUNCHED();
+    c.layer = region ? "conv" : "fc";
+    c.mark("grad_exchange");
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) grad_exchange_ll_kernel(Exchange x, size_t lo4, size_t hi4) {
+    __shared__ bool s_last;
+    const unsigned int epoch = x.ctr[1] + 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) x.ctr[12] = gtimer_lo();
+    float* mine = const_cast<float*>(x.grads[x.rank]);
+    const size_t slot = x.ll_cap / 2;   // uint4 entries per sender slot (one entry carries two floats)
+    const long long t0 = clock64();
+    for (size_t q = lo4 + (size_t)blockIdx.x * 256 + threadIdx.x; q < hi4; q += (size_t)gridDim.x * 256) {
+        const float4 own = reinterpret_cast<const float4*>(mine)[q];
+        const size_t e = (q - lo4) * 2;
+        const uint4 a = make_uint4(__float_as_uint(own.x), epoch, __float_as_uint(own.y), epoch);
+        const uint4 b = make_uint4(__float_as_uint(own.z), epoch, __float_as_uint(own.w), epoch);
+#pragma unroll
+        for (int r = 0; r < W; ++r)
+            if (r != x.rank) {
+                uint4* dst = reinterpret_cast<uint4*>(const_cast<float*>(x.grads[r]) + x.ll_off) + (size_t)x.rank * slot + e;
+                dst[0] = a; dst[1] = b;
+            }
+        float4 t[W];
+#pragma unroll
+        for (int r = 0; r < W; ++r) {
+            if (r == x.rank) { t[r] = own; continue; }
+            const uint4* src = reinterpret_cast<const uint4*>(mine + x.ll_off) + (size_t)r * slot + e;
+            uint4 u, v;
+            for (;;) {
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(src));
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + 1));
+                if (u.y == epoch && u.w == epoch && v.y == epoch && v.w == epoch) break;
+                if (clock64() - t0 > x.timeout_cycles) {   // a peer never sent: raise the sticky failure flag, do not hang
+                    *reinterpret_cast<volatile int*>(x.err) = 21;
+                    break;
+                }
+            }
+            t[r] = make_float4(__uint_as_float(u.x), __uint_as_float(u.z), __uint_as_float(v.x), __uint_as_float(v.z));
+        }
+#pragma unroll
+        for (int s = 1; s < W; s *= 2)
+#pragma unroll
+            for (int r = 0; r + s < W; r += 2 * s) { t[r].x += t[r + s].x; t[r].y += t[r + s].y; t[r].z += t[r + s].z; t[r].w += t[r + s].w; }
+        const float w = (float)W;
+        reinterpret_cast<float4*>(mine)[q] = make_float4(t[0].x / w, t[0].y / w, t[0].z / w, t[0].w / w);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&x.ctr[3], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) { x.ctr[3] = 0u; x.ctr[1] = epoch; x.ctr[14] = gtimer_lo(); }
+}
+
+void grad_exchange_ll(const Ctx& c, const Exchange& x, size_t lo, size_t hi) {
+    BB_CHECK((lo & 3) == 0 && (hi & 3) == 0 && hi - lo <= x.ll_cap, "grad_exchange_ll: region does not fit the receive area");
+    BB_CHECK(x.world >= 2 && x.world <= 8, "grad_exchange_ll: 2..8 ranks");
+    // every block must be resident (a block's sends are what its peers' twin blocks wait for): at most 4 light blocks per SM
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>(((hi - lo) / 4 + 255) / 256, (size_t)c.sms * 4));
+    switch (x.world) {
+#define BB_XCHG_CASE(W) case W: grad_exchange_ll_kernel<W><<<blocks, 256, 0, c.stream>>>(x, lo / 4, hi / 4); break;
+        BB_XCHG_CASE(2) BB_XCHG_CASE(3) BB_XCHG_CASE(4) BB_XCHG_CASE(5) BB_XCHG_CASE(6) BB_XCHG_CASE(7) BB_XCHG_CASE(8)
+#undef BB_XCHG_CASE
+    }
+    BB_LAUNCHED();
+    c.layer = "conv";
+    c.mark("grad_exchange_ll");
+}
+
 void grad_reduce_scatter(const Ctx& c, const float* const* peer_grads, size_t n, int rank, int world) {
     PeerPtrs pp;
     for (int r = 0; r < 8; ++r) pp.p[r] = r < world ? peer_grads[r] : nullptr;
@@ -722,7 +897,7 @@ void grad_reduce_scatter(const Ctx& c, const float* const* peer_grads, size_t n,
 }
 
 void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
-               uint64_t step, const float* const* peer_grads, int world, float* p_lo) {
+               uint64_t step, const float* const* peer_grads, int world, float* p_lo, const Exchange* wait, int wait_regions) {
     double bc1 = 1.0 - pow(h.beta1, (double)step);
     double bc2 = 1.0 - pow(h.beta2, (double)step);
     double step_size = h.lr / bc1;
@@ -734,7 +909,8 @@ void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_
     adam_kernel<<<blocks, 256, 0, c.stream>>>(p, g, m, v, n, (float)h.beta1, (float)h.beta2, (float)(1.0 - h.beta1),
                                               (float)(1.0 - h.beta2), (float)h.eps, (float)sqrt(bc2),
                                               (float)(-step_size), (float)h.wd, (float)(1.0 - h.lr * h.wd),
-                                              h.adamw ? 1 : 0, pp, peer_grads ? world : 1, p_lo);
+                                              h.adamw ? 1 : 0, pp, peer_grads ? world : 1, p_lo, wait ? *wait : Exchange{},
+                                              wait ? wait_regions : 0);
     BB_LAUNCHED();
     c.layer = "";
     c.mark("adam");
@@ -1184,7 +1360,8 @@ __global__ void relu_mask_kernel(float* __restrict__ d, const float* __restrict_
 }
 
 void Net::backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
-                   float* d_input, long ld_din, long p_plane, const unsigned long long* in_ix) const {
+                   float* d_input, long ld_din, long p_plane, const unsigned long long* in_ix, int after_layer,
+                   const std::function<void()>* hook) const {
     BB_CHECK(w.with_grad, "workspace was allocated without gradient buffers");
     int L = (int)layers.size();
     // d(output) arrives in w.dact[L-1] as the gradient wrt the post-activation output
@@ -1247,6 +1424,7 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
             if (dx) linear_bwd_data(c, w.dact[i], p + l.w_off, dx, lddx, B, l.out_dim, l.in_dim, mask, dy_plane, p_plane, dx_plane);
         }
         dy_lo = p_plane != 0;  // every data-gradient epilogue above wrote the lo plane of dact[i-1]
+        if (hook && g && i == after_layer) (*hook)();
     }
     if (n_side > 0) c.join_from(*c.side[0]);
     if (n_side > 1) c.join_from(*c.side[1]);

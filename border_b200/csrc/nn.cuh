@@ -11,6 +11,7 @@
 // stack has its input columns permuted from the reference's (c,h,w) flat_view order to (h,w,c).
 // Import/export (get_param/set_param, checkpoints, SyncModel) convert to/from the reference layout.
 #pragma once
+#include <functional>
 #include <string>
 #include <vector>
 #include "common.cuh"
@@ -111,6 +112,7 @@ void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const voi
 void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float* W, float* col, float* dX,
                    const float* mask);
 
+struct Exchange;
 // torch::optim::Adam / AdamW step over a flat parameter vector (one launch).
 struct AdamHyper {
     double lr, beta1, beta2, eps, wd;
@@ -118,9 +120,34 @@ struct AdamHyper {
 };
 // p_lo != null: the kernel also refreshes the parameters' lo plane (operand of the TMA-fed GEMMs)
 void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
-               uint64_t step /* 1-based */, const float* const* peer_grads = nullptr, int world = 1, float* p_lo = nullptr);
+               uint64_t step /* 1-based */, const float* const* peer_grads = nullptr, int world = 1, float* p_lo = nullptr,
+               const Exchange* wait = nullptr, int wait_regions = 0 /* bit r: wait for region r's delivered flags */);
 // mean of all ranks' gradients, slice-owner computes and stores it into every rank's buffer (peer memory)
 void grad_reduce_scatter(const Ctx& c, const float* const* peer_grads, size_t n, int rank, int world);
+
+// Gradient exchange of a data-parallel replica with the rendezvous FOLDED INTO the kernels (no barrier launches): the
+// gradient vector is exchanged in up to two regions -- region 0 as soon as its weight gradients exist (the fully connected
+// layers: 95 % of the AtariCnn, finished long before the convolution backward), region 1 at the end.  Per region ONE kernel:
+// announce "my gradients are ready" in every peer's flag array, wait for all ranks, reduce this rank's 1/world slice of the
+// region (pairwise-tree mean, so all ranks stay bit-identical) and store it into every rank's buffer over NVLink, then
+// announce "my slice is delivered".  The optimizer kernel waits in its prologue for every rank's "delivered" flag of the
+// regions it consumes.  Epochs live in device memory, so every launch is argument-invariant (CUDA-graph friendly).
+struct Exchange {
+    const float* grads[8];     // every rank's gradient buffer (CUDA-IPC peer pointers; [rank] = local)
+    unsigned int* flags[8];    // every rank's flag array; slots xflag(kind, r), written by rank r
+    unsigned int* ctr;         // local: [region] epoch delivered so far, [2 + region] block-completion counters
+    int rank, world;
+    int* err;                  // sticky failure flag (common.cuh)
+    long long timeout_cycles;
+    size_t ll_off, ll_cap;     // flag-in-data receive area behind each gradient buffer: float offset, floats per sender slot / 2
+};
+__host__ __device__ inline int xflag(int kind, int r) { return 16 + kind * 8 + r; }   // kind = 2*region (+1 = delivered)
+void grad_exchange(const Ctx& c, const Exchange& x, size_t lo, size_t hi, int region, int max_blocks = 0);
+// Small region on the critical path (the convolution gradients, 5 % of the AtariCnn): ONE hop instead of the four of
+// grad_exchange.  Every rank pushes its gradients to every peer as 16-byte {value, epoch, value, epoch} stores (each 8-byte
+// half lands atomically, so a receiver that sees the epoch sees the value: no fence, no flag round trip -- the "LL" protocol),
+// then reduces what it received with the same pairwise tree, so all ranks end bit-identical.  Needs hi - lo <= x.ll_cap.
+void grad_exchange_ll(const Ctx& c, const Exchange& x, size_t lo, size_t hi);
 // dest = tau*src + (1-tau)*dest  (util.rs:43)
 void track(const Ctx& c, float* dest, const float* src, size_t n, double tau, float* dest_lo = nullptr);
 void fill_uniform(const Ctx& c, float* p, size_t n, float bound, uint64_t seed);
@@ -200,8 +227,11 @@ class Net {
     // d_input (may be null) receives the gradient wrt a float input [B][in].
     // With c.concurrent() the weight gradients of all layers but the first run on the side contexts
     // while the data-gradient chain continues on c.stream; everything is joined before returning.
+    // after_layer / hook: called once the weight gradients of layers >= after_layer have been ENQUEUED (on c.stream and the
+    // side contexts) -- the data-parallel agents start exchanging those gradients there, under the rest of the backward pass
     void backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
-                  float* d_input, long ld_din, long p_plane = 0, const unsigned long long* in_ix = nullptr) const;
+                  float* d_input, long ld_din, long p_plane = 0, const unsigned long long* in_ix = nullptr, int after_layer = -1,
+                  const std::function<void()>* hook = nullptr) const;
     void free_tables();
     std::string layer_name(size_t i) const;
 };

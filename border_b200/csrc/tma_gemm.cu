@@ -249,7 +249,8 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     if (tiles * 2 <= want && nks >= 8 && !a.c_rowoff) {
         // as many splits as keep every CTA of the launch resident at once (one per SM with the deep ring): a second,
         // mostly empty wave doubled l1.fwd's time (160 CTAs on 148 SMs)
-        split = (int)std::min<long>(std::min<long>(want / tiles, 16), nks / 4);
+        static const int split_cap = env_i("BB_TMA_SPLIT_CAP", 16);
+        split = (int)std::min<long>(std::min<long>(want / tiles, split_cap), nks / 4);
         const size_t per = (size_t)a.M * a.N;
         const size_t usable = c.ws_floats - 1024;
         if (per * split > usable) split = (int)(usable / per);

@@ -37,10 +37,14 @@ def connect_gradient_peers(agent, dist, torch):
     fs = b"".join(b[HANDLE_BYTES:] for b in blobs)
     L.check(L.lib().bb_agent_ipc_connect(agent.handle, rank, world, hs, fs))
     import os
-    mode = os.environ.get("BB_GRAD_SYNC") or ("sharded" if world >= 4 else "fused")
-    if mode == "sharded":
-        return "sharded mean over NVLink (each rank reduces 1/%d of the gradient through CUDA-IPC peer loads and stores it to every rank) + local Adam" % world
-    return "fused P2P all-reduce + Adam over NVLink (CUDA IPC peer loads)"
+    mode = os.environ.get("BB_GRAD_SYNC") or "overlapped"
+    if mode in ("overlapped", "late"):
+        return ("sharded mean over NVLink (each rank reduces 1/%d of a gradient region through CUDA-IPC peer loads and stores it to "
+                "every rank; rendezvous flags folded into the reduce kernel and Adam's prologue%s)"
+                % (world, "; FC region exchanged under the convolution backward" if mode == "overlapped" else ""))
+    if mode == "sharded" or (mode == "legacy" and world >= 4):
+        return "legacy: barrier + sharded mean over NVLink + barrier + local Adam"
+    return "legacy: barrier + fused P2P all-reduce + Adam over NVLink + barrier"
 
 
 def max_over_ranks(value, dist, torch, device):

@@ -317,6 +317,9 @@ int32_t bb_agent_inject_noise(bb_agent* a, int32_t slot, const float* host, size
  * gradient buffer mapped into this process (CUDA IPC); the fused all-reduce + Adam kernel reads
  * them over NVLink.  world = 1 disables. */
 int32_t bb_agent_grad_buffer(bb_agent* a, void** dev_ptr, uint64_t* n_floats);
+/* Debug: the gradient exchange's device-side stamps of the last update (32 words: [8..10] FC region start / all ranks
+ * ready / done, [12..14] conv region, [16..17] Adam start / every slice delivered; low 32 bits of %globaltimer, ns). */
+int32_t bb_agent_exchange_trace(bb_agent* a, uint32_t* out32);
 int32_t bb_agent_ipc_export(bb_agent* a, void* handle_out /* 64 bytes grads */, void* flag_handle_out /* 64 bytes */);
 int32_t bb_agent_ipc_connect(bb_agent* a, int32_t rank, int32_t world, const void* handles /* world*64 */,
                              const void* flag_handles /* world*64 */);

@@ -67,8 +67,8 @@ def test_softmax_explorer_is_deterministic_and_follows_the_softmax_probabilities
     with torch.no_grad():
         p = torch.softmax(ao.mlp_forward(params, torch.from_numpy(obs), 3), -1).numpy()[0]
     n = 4000
-    s1 = [int(a1.sample(obs)[0]) for _ in range(n)]
-    s2 = [int(a2.sample(obs)[0]) for _ in range(n)]
+    s1 = [int(a1.sample(obs)[0, 0]) for _ in range(n)]
+    s2 = [int(a2.sample(obs)[0, 0]) for _ in range(n)]
     assert s1 == s2
     freq = np.bincount(s1, minlength=5) / n
     assert np.abs(freq - p).max() < 4.0 * np.sqrt(0.25 / n)
