@@ -416,7 +416,8 @@ def run_b200(args):
             rel = lambda a_, b_: int((a_ - b_) & 0xFFFFFFFF) if a_ and b_ else None
             rows.append({"step_ns": rel(t[16], prev) if prev else None, "fc_start_to_adam_ns": rel(t[16], t[8]),
                          "fc_wait_ns": rel(t[9], t[8]), "fc_reduce_ns": rel(t[10], t[9]), "conv_start_to_adam_ns": rel(t[16], t[12]),
-                         "conv_wait_ns": rel(t[13], t[12]), "conv_reduce_ns": rel(t[14], t[13]), "fc_fence_ns": rel(t[10], t[11]), "conv_fence_ns": rel(t[14], t[15]), "adam_wait_ns": rel(t[17], t[16])})
+                         "conv_wait_ns": rel(t[13], t[12]), "conv_reduce_ns": rel(t[14], t[13]), "fc_fence_ns": rel(t[10], t[11]), "conv_fence_ns": rel(t[14], t[15]), "adam_wait_ns": rel(t[17], t[16]), "ll_ns": rel(t[21], t[20]), "ll_start_to_adam_ns": rel(t[16], t[20]),
+                         "ll_mid_ns": rel(t[25], t[24]), "ll_mid_start_to_adam_ns": rel(t[16], t[24])})
             prev = t[16]
         exchange_trace = rows[1:]
 

@@ -161,15 +161,26 @@ Exchange Agent::exchange() const {
 
 // Called from inside Net::backward once the weight gradients of the region's layers are enqueued (main stream + both side
 // streams): the comm stream waits for all three and runs the region-0 exchange while the convolution backward continues.
-void Agent::begin_early_exchange(Model& m, size_t split) {
-    if (world <= 1) return;
+void Agent::comm_follows_compute() {
     for (const Ctx* s : {(const Ctx*)&ctx, ctx.side[0], ctx.side[1]}) {
         if (!s) continue;
         BB_CUDA(cudaEventRecord(s->ev, s->stream));
         BB_CUDA(cudaStreamWaitEvent(comm_ctx.stream, s->ev, 0));
     }
     comm_ctx.prof = ctx.prof; comm_ctx.phase = "optimizer";
-    static const int early_blocks = getenv("BB_XCHG_EARLY_BLOCKS") ? atoi(getenv("BB_XCHG_EARLY_BLOCKS")) : 24;
+}
+static bool ll_enabled() { const char* ll = getenv("BB_XCHG_LL"); return !(ll && !strcmp(ll, "0")); }
+void Agent::mid_exchange(Model& m, size_t lo, size_t hi) {
+    if (world <= 1 || hi <= lo) return;
+    comm_follows_compute();
+    Exchange x = exchange();
+    x.ll_off = m.n; x.ll_cap = m.g_ll_cap;
+    grad_exchange_ll(comm_ctx, x, lo, hi, 1);
+}
+void Agent::begin_early_exchange(Model& m, size_t split) {
+    if (world <= 1) return;
+    comm_follows_compute();
+    static const int early_blocks = getenv("BB_XCHG_EARLY_BLOCKS") ? atoi(getenv("BB_XCHG_EARLY_BLOCKS")) : 32;
     grad_exchange(comm_ctx, exchange(), split, m.n, 0, early_blocks);
 }
 void Agent::join_early_exchange() {
@@ -183,7 +194,7 @@ void Agent::join_early_exchange() {
 // folded into the kernels) and Adam waits in its prologue for every rank's slice: with `early` the big region [split, n) was
 // already exchanged under the backward pass (begin_early_exchange) and only [0, split) is exchanged here.
 // BB_GRAD_SYNC=legacy keeps the round-1 sequence (barrier launch, reduce-scatter or all-read Adam, barrier launch).
-void Agent::synced_adam(Model& m, bool early, size_t split) {
+void Agent::synced_adam(Model& m, bool early, size_t split, size_t mid) {
     if (world <= 1) {
         adam_step(ctx, m.p, m.g, m.m, m.v, m.n, m.hyper, m.step, nullptr, 1, m.p_lo());
         return;
@@ -207,9 +218,9 @@ void Agent::synced_adam(Model& m, bool early, size_t split) {
     x.ll_off = m.n; x.ll_cap = m.g_ll_cap;
     int regions = 1;
     if (early) {
-        const char* ll = getenv("BB_XCHG_LL");
-        if (split > 0 && split <= m.g_ll_cap && !(ll && !strcmp(ll, "0"))) grad_exchange_ll(ctx, x, 0, split);   // complete when the kernel ends
-        else if (split > 0) { grad_exchange(ctx, x, 0, split, 1); regions = 3; }
+        const size_t hi = mid > 0 ? mid : split;   // what is left for the end of the step
+        if (hi > 0 && split <= m.g_ll_cap && ll_enabled()) grad_exchange_ll(ctx, x, 0, hi, 0);   // complete when the kernel ends
+        else if (hi > 0) { BB_CHECK(mid == 0, "mid_exchange needs the flag-in-data path"); grad_exchange(ctx, x, 0, hi, 1); regions = 3; }
     } else {
         grad_exchange(ctx, x, 0, m.n, 0);
     }

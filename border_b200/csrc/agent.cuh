@@ -101,13 +101,16 @@ struct Agent {
     // region 0 = [split, n) is exchanged from inside the backward pass (begin_early_exchange, on comm_ctx), region 1 =
     // [0, split) and the optimizer follow at the end (synced_adam with early = true)
     void begin_early_exchange(Model& m, size_t split);
+    // [lo, hi) (gradients that exist before the end of the backward pass, but are small): flag-in-data exchange on comm_ctx
+    void mid_exchange(Model& m, size_t lo, size_t hi);
     void join_early_exchange();
+    void comm_follows_compute();
     void grad_sync_begin();  // all ranks' gradients complete before anyone reads them
     void grad_sync_end();    // everyone done reading before anyone overwrites
     // Optimizer step of a data-parallel replica.  world 1: plain Adam.  world 2-3: ONE kernel reads every rank's
     // gradient and applies Adam (fused all-reduce + optimizer).  world >= 4: sharded mean (reduce-scatter +
     // broadcast through peer stores) then local Adam.  BB_GRAD_SYNC=fused|sharded overrides the choice.
-    void synced_adam(Model& m, bool early = false, size_t split = 0);
+    void synced_adam(Model& m, bool early = false, size_t split = 0 /* start of the early region */, size_t mid = 0 /* [mid, split) went through mid_exchange */);
 
     virtual ~Agent();
     void init_base(int dev);

@@ -187,6 +187,12 @@ struct Dqn : Agent {
         return 0;
     }
     size_t early_split() const { return net.layers[early_layer()].w_off; }
+    // layers 1 .. early_layer()-1 (c2, c3) are exchanged under the first layer's weight gradient: [mid_split, early_split)
+    size_t mid_split() const {
+        // off by default: measured slower at 2 and 8 GPUs (the spinning blocks take SMs from c1's weight gradient)
+        static const bool on = getenv("BB_XCHG_MID") && !strcmp(getenv("BB_XCHG_MID"), "1") && !(getenv("BB_XCHG_LL") && !strcmp(getenv("BB_XCHG_LL"), "0"));
+        return on && early_layer() >= 2 ? net.layers[1].w_off : 0;
+    }
     bool early_exchange_on() const {
         const char* e = getenv("BB_GRAD_SYNC");
         return world > 1 && ctx.concurrent() && !(e && (!strcmp(e, "legacy") || !strcmp(e, "sharded") || !strcmp(e, "fused") || !strcmp(e, "late")));
@@ -255,10 +261,14 @@ struct Dqn : Agent {
         // qnet.backward_step(&loss): zero_grad, backward, Adam (opt.rs:74-83)
         // data-parallel replicas: the gradients of the fully connected layers (95 % of the vector) are exchanged as soon as
         // they exist, under the convolution backward (agent.cuh: begin_early_exchange)
-        const std::function<void()> hook = [this]() { begin_early_exchange(qnet, early_split()); };
+        // (BB_XCHG_MID=1: the gradients of every convolution but the first follow as soon as they exist, which leaves only
+        // c1's 8 k floats for the end of the step)
+        const std::function<void(int)> hook = [this](int layer) {
+            if (layer == early_layer()) begin_early_exchange(qnet, early_split());
+            else if (layer == 1 && mid_split() > 0) mid_exchange(qnet, mid_split(), early_split());
+        };
         const bool early = early_exchange_on();
-        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0, 0, in_ix, early ? early_layer() : -1,
-                     early ? &hook : nullptr);
+        net.backward(ctx, qnet.p, qnet.g, bv.obs, ld_in, B, ws_online, nullptr, 0, 0, in_ix, early ? &hook : nullptr);
         if (early) join_early_exchange();
         if (conc) ctx.join_from(rctx);  // (backward joins the side streams it used; this one may not be among them)
     }
@@ -322,7 +332,7 @@ struct Dqn : Agent {
         }
         qnet.step += 1;
         ctx.phase = "optimizer";
-        synced_adam(qnet, early_exchange_on(), early_split());
+        synced_adam(qnet, early_exchange_on(), early_split(), mid_split());
         if (bv.weight) {  // :142-143
             if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
             rb.update_priority_dev((const unsigned long long*)bv.ix_sample, d_td, B);

@@ -748,7 +748,7 @@ __global__ void grad_reduce_scatter_kernel(PeerPtrs peers, size_t n, int rank, i
 // runtime index the pointer table goes to local memory and ptxas serialises the loads (measured: 21 us per loop iteration).
 // ctr[8 + 4*region ..] receive %globaltimer stamps (start / after the rendezvous / end) for bench.py's exchange trace.
 template <int W>
-__global__ void __launch_bounds__(256) grad_exchange_kernel(Exchange x, size_t lo4, size_t hi4, int region) {
+__global__ void __launch_bounds__(256) grad_exchange_kernel(Exchange x, size_t lo4, size_t hi4, int region, int dbg) {
     constexpr int U = W <= 2 ? 8 : W <= 4 ? 4 : 2;
     __shared__ bool s_last;
     const unsigned int epoch = x.ctr[region] + 1;   // (bumped by the last block of THIS launch, after every block has read it)
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(256) grad_exchange_kernel(Exchange x, size_t l
     wait_flags(x, 2 * region, epoch);
     if (blockIdx.x == 0 && threadIdx.x == 0) x.ctr[9 + 4 * region] = gtimer_lo();
     const size_t per = (hi4 - lo4 + W - 1) / W;
-    const size_t a = lo4 + (size_t)x.rank * per, b = a + per < hi4 ? a + per : hi4;
+    const size_t a = lo4 + (size_t)x.rank * per, b = (dbg & 1) ? a : (a + per < hi4 ? a + per : hi4);   // dbg 1: rendezvous only (timing experiments)
     for (size_t base = a + (size_t)blockIdx.x * (256 * U); base < b; base += (size_t)gridDim.x * (256 * U)) {
         float4 t[U][W];
 #pragma unroll
@@ -811,8 +811,9 @@ void grad_exchange(const Ctx& c, const Exchange& x, size_t lo, size_t hi, int re
     static const int mult = getenv("BB_XCHG_BLOCKS_PER_SM") ? atoi(getenv("BB_XCHG_BLOCKS_PER_SM")) : 2;
     const size_t cap = max_blocks > 0 ? (size_t)max_blocks : (size_t)c.sms * mult;
     const int blocks = (int)std::max<size_t>(1, std::min<size_t>((per + 256 * U - 1) / (256 * U), cap));
+    static const int dbg = getenv("BB_XCHG_DBG") ? atoi(getenv("BB_XCHG_DBG")) : 0;
     switch (x.world) {
-#define BB_XCHG_CASE(W) case W: grad_exchange_kernel<W><<<blocks, 256, 0, c.stream>>>(x, lo / 4, hi / 4, region); break;
+#define BB_XCHG_CASE(W) case W: grad_exchange_kernel<W><<<blocks, 256, 0, c.stream>>>(x, lo / 4, hi / 4, region, dbg); break;
         BB_XCHG_CASE(2) BB_XCHG_CASE(3) BB_XCHG_CASE(4) BB_XCHG_CASE(5) BB_XCHG_CASE(6) BB_XCHG_CASE(7) BB_XCHG_CASE(8)
 #undef BB_XCHG_CASE
     }
@@ -822,16 +823,16 @@ void grad_exchange(const Ctx& c, const Exchange& x, size_t lo, size_t hi, int re
 }
 
 template <int W>
-__global__ void __launch_bounds__(256) grad_exchange_ll_kernel(Exchange x, size_t lo4, size_t hi4) {
+__global__ void __launch_bounds__(256) grad_exchange_ll_kernel(Exchange x, size_t lo4, size_t hi4, int k) {
     __shared__ bool s_last;
-    const unsigned int epoch = x.ctr[1] + 1;
-    if (blockIdx.x == 0 && threadIdx.x == 0) x.ctr[12] = gtimer_lo();
+    const unsigned int epoch = x.ctr[4 + 2 * k] + 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) x.ctr[20 + 4 * k] = gtimer_lo();
     float* mine = const_cast<float*>(x.grads[x.rank]);
     const size_t slot = x.ll_cap / 2;   // uint4 entries per sender slot (one entry carries two floats)
     const long long t0 = clock64();
     for (size_t q = lo4 + (size_t)blockIdx.x * 256 + threadIdx.x; q < hi4; q += (size_t)gridDim.x * 256) {
         const float4 own = reinterpret_cast<const float4*>(mine)[q];
-        const size_t e = (q - lo4) * 2;
+        const size_t e = q * 2;   // (entries are addressed by absolute position: concurrent exchanges use disjoint ranges)
         const uint4 a = make_uint4(__float_as_uint(own.x), epoch, __float_as_uint(own.y), epoch);
         const uint4 b = make_uint4(__float_as_uint(own.z), epoch, __float_as_uint(own.w), epoch);
 #pragma unroll
@@ -865,23 +866,25 @@ __global__ void __launch_bounds__(256) grad_exchange_ll_kernel(Exchange x, size_
         reinterpret_cast<float4*>(mine)[q] = make_float4(t[0].x / w, t[0].y / w, t[0].z / w, t[0].w / w);
     }
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&x.ctr[3], 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) s_last = atomicAdd(&x.ctr[5 + 2 * k], 1u) == gridDim.x - 1;
     __syncthreads();
-    if (s_last && threadIdx.x == 0) { x.ctr[3] = 0u; x.ctr[1] = epoch; x.ctr[14] = gtimer_lo(); }
+    if (s_last && threadIdx.x == 0) { x.ctr[5 + 2 * k] = 0u; x.ctr[4 + 2 * k] = epoch; x.ctr[21 + 4 * k] = gtimer_lo(); }
 }
 
-void grad_exchange_ll(const Ctx& c, const Exchange& x, size_t lo, size_t hi) {
-    BB_CHECK((lo & 3) == 0 && (hi & 3) == 0 && hi - lo <= x.ll_cap, "grad_exchange_ll: region does not fit the receive area");
+void grad_exchange_ll(const Ctx& c, const Exchange& x, size_t lo, size_t hi, int k) {
+    BB_CHECK((lo & 3) == 0 && (hi & 3) == 0 && hi <= x.ll_cap && (k == 0 || k == 1), "grad_exchange_ll: region does not fit the receive area");
     BB_CHECK(x.world >= 2 && x.world <= 8, "grad_exchange_ll: 2..8 ranks");
     // every block must be resident (a block's sends are what its peers' twin blocks wait for): at most 4 light blocks per SM
     const int blocks = (int)std::max<size_t>(1, std::min<size_t>(((hi - lo) / 4 + 255) / 256, (size_t)c.sms * 4));
+    static const int dbg = getenv("BB_XCHG_DBG") ? atoi(getenv("BB_XCHG_DBG")) : 0;
+    if (dbg & 2) return;   // timing experiments only: no exchange at all
     switch (x.world) {
-#define BB_XCHG_CASE(W) case W: grad_exchange_ll_kernel<W><<<blocks, 256, 0, c.stream>>>(x, lo / 4, hi / 4); break;
+#define BB_XCHG_CASE(W) case W: grad_exchange_ll_kernel<W><<<blocks, 256, 0, c.stream>>>(x, lo / 4, hi / 4, k); break;
         BB_XCHG_CASE(2) BB_XCHG_CASE(3) BB_XCHG_CASE(4) BB_XCHG_CASE(5) BB_XCHG_CASE(6) BB_XCHG_CASE(7) BB_XCHG_CASE(8)
 #undef BB_XCHG_CASE
     }
     BB_LAUNCHED();
-    c.layer = "conv";
+    c.layer = k ? "conv.mid" : "conv";
     c.mark("grad_exchange_ll");
 }
 
@@ -1360,8 +1363,8 @@ __global__ void relu_mask_kernel(float* __restrict__ d, const float* __restrict_
 }
 
 void Net::backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
-                   float* d_input, long ld_din, long p_plane, const unsigned long long* in_ix, int after_layer,
-                   const std::function<void()>* hook) const {
+                   float* d_input, long ld_din, long p_plane, const unsigned long long* in_ix,
+                   const std::function<void(int)>* hook) const {
     BB_CHECK(w.with_grad, "workspace was allocated without gradient buffers");
     int L = (int)layers.size();
     // d(output) arrives in w.dact[L-1] as the gradient wrt the post-activation output
@@ -1424,7 +1427,8 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
             if (dx) linear_bwd_data(c, w.dact[i], p + l.w_off, dx, lddx, B, l.out_dim, l.in_dim, mask, dy_plane, p_plane, dx_plane);
         }
         dy_lo = p_plane != 0;  // every data-gradient epilogue above wrote the lo plane of dact[i-1]
-        if (hook && g && i == after_layer) (*hook)();
+        // (after the data gradient is enqueued too: an exchange that starts while it runs takes SMs from the critical path)
+        if (hook && g) (*hook)(i);
     }
     if (n_side > 0) c.join_from(*c.side[0]);
     if (n_side > 1) c.join_from(*c.side[1]);

@@ -135,7 +135,8 @@ void grad_reduce_scatter(const Ctx& c, const float* const* peer_grads, size_t n,
 struct Exchange {
     const float* grads[8];     // every rank's gradient buffer (CUDA-IPC peer pointers; [rank] = local)
     unsigned int* flags[8];    // every rank's flag array; slots xflag(kind, r), written by rank r
-    unsigned int* ctr;         // local: [region] epoch delivered so far, [2 + region] block-completion counters
+    unsigned int* ctr;         // local: [region] epoch delivered so far, [2 + region] block-completion counters;
+                               // [4 + 2k], [5 + 2k] the same for grad_exchange_ll k; [8..27] %globaltimer stamps
     int rank, world;
     int* err;                  // sticky failure flag (common.cuh)
     long long timeout_cycles;
@@ -147,7 +148,8 @@ void grad_exchange(const Ctx& c, const Exchange& x, size_t lo, size_t hi, int re
 // grad_exchange.  Every rank pushes its gradients to every peer as 16-byte {value, epoch, value, epoch} stores (each 8-byte
 // half lands atomically, so a receiver that sees the epoch sees the value: no fence, no flag round trip -- the "LL" protocol),
 // then reduces what it received with the same pairwise tree, so all ranks end bit-identical.  Needs hi - lo <= x.ll_cap.
-void grad_exchange_ll(const Ctx& c, const Exchange& x, size_t lo, size_t hi);
+// `k` (0 or 1) selects the epoch counter: two such exchanges may be in flight on different streams.
+void grad_exchange_ll(const Ctx& c, const Exchange& x, size_t lo, size_t hi, int k = 0);
 // dest = tau*src + (1-tau)*dest  (util.rs:43)
 void track(const Ctx& c, float* dest, const float* src, size_t n, double tau, float* dest_lo = nullptr);
 void fill_uniform(const Ctx& c, float* p, size_t n, float bound, uint64_t seed);
@@ -227,11 +229,11 @@ class Net {
     // d_input (may be null) receives the gradient wrt a float input [B][in].
     // With c.concurrent() the weight gradients of all layers but the first run on the side contexts
     // while the data-gradient chain continues on c.stream; everything is joined before returning.
-    // after_layer / hook: called once the weight gradients of layers >= after_layer have been ENQUEUED (on c.stream and the
-    // side contexts) -- the data-parallel agents start exchanging those gradients there, under the rest of the backward pass
+    // hook(i): called once the weight gradients of layers >= i have been ENQUEUED (on c.stream and the side contexts) --
+    // the data-parallel agents start exchanging those gradients there, under the rest of the backward pass
     void backward(const Ctx& c, const float* p, float* g, const void* input, long ld_in, int B, NetWorkspace& w,
-                  float* d_input, long ld_din, long p_plane = 0, const unsigned long long* in_ix = nullptr, int after_layer = -1,
-                  const std::function<void()>* hook = nullptr) const;
+                  float* d_input, long ld_din, long p_plane = 0, const unsigned long long* in_ix = nullptr,
+                  const std::function<void(int)>* hook = nullptr) const;
     void free_tables();
     std::string layer_name(size_t i) const;
 };
