@@ -125,6 +125,59 @@ struct Agent {
     void load_params(const char* dir);
 };
 
+// One update step as a CUDA graph (what Dqn::update_critic does by hand, for the other agents): after three eager updates
+// the launches of `enqueue` are captured once per (replay, batch, stream) and replayed.  Everything `enqueue` launches must
+// be argument-invariant: step-dependent scalars live in device memory (AdamScalars), the replay draws from its device-side
+// position.  `advance` does the host-side bookkeeping of a replayed sample (rb.sample(B, &bv, false)).
+struct UpdateGraph {
+    cudaGraphExec_t exec = nullptr;
+    const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t eager = 0, kernels = 0;
+    bool broken = false;
+    void reset() { if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; } }
+    ~UpdateGraph() { reset(); }
+    template <class Enqueue, class Advance>
+    void run(const Ctx& ctx, Replay& rb, int B, bool allowed, Enqueue enqueue, Advance advance) {
+        const char* genv = getenv("BB_GRAPH");  // read per call so tests can flip it
+        const bool want = allowed && !(genv && atoi(genv) == 0) && !broken && !ctx.prof && !rb.per && ctx.stream != nullptr &&
+                          ctx.stream != cudaStreamLegacy && ctx.stream != cudaStreamPerThread && rb.stream == ctx.stream &&
+                          eager >= 3 && rb.batch_cap >= (size_t)B;
+        if (want) {
+            const void* k[4] = {&rb, (const void*)(uintptr_t)B, (const void*)ctx.stream, (const void*)rb.b_obs};
+            if (exec && memcmp(k, key, sizeof(k)) == 0) {
+                advance();
+                BB_CUDA(cudaGraphLaunch(exec, ctx.stream));
+                g_launch_count.fetch_add(kernels, std::memory_order_relaxed);
+                return;
+            }
+            reset();
+            const uint64_t rng0 = rb.rng_pos;
+            const size_t lb0 = rb.last_batch;
+            const uint64_t n0 = g_launch_count.load();
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                try { enqueue(); } catch (...) { ok = false; }
+                if (cudaStreamEndCapture(ctx.stream, &graph) != cudaSuccess || !graph) ok = false;
+            }
+            if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { ok = false; exec = nullptr; }
+            if (graph) cudaGraphDestroy(graph);
+            if (ok) {
+                kernels = g_launch_count.load() - n0;
+                memcpy(key, k, sizeof(k));
+                BB_CUDA(cudaGraphLaunch(exec, ctx.stream));  // the capture enqueued nothing: run this update now
+                return;
+            }
+            cudaGetLastError();  // clear the sticky capture error, fall back to eager launches for good
+            broken = true;
+            rb.rng_pos = rng0; rb.last_batch = lb0;
+            g_launch_count.store(n0);
+        }
+        enqueue();
+        eager += 1;
+    }
+};
+
 Agent* make_dqn(const bb_dqn_cfg& cfg);
 Agent* make_sac(const bb_sac_cfg& cfg);
 Agent* make_iqn(const bb_iqn_cfg& cfg);

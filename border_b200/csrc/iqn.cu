@@ -23,9 +23,12 @@ __device__ __forceinline__ unsigned long long iqn_mix64(unsigned long long x) {
 
 // IqnSample::sample (iqn/model/base.rs:347-372) -> tau [B][N]; uniform modes draw U[0,1) in the
 // kernel (the reference uses Tensor::rand on the CPU generator; parity tests inject tau).
-__global__ void iqn_tau_kernel(float* tau, int B, int N, int mode, unsigned long long seed, unsigned long long ctr0) {
+// ctr_dev != null: the counter is read from device memory (the update's launches are argument-invariant: CUDA graph)
+__global__ void iqn_tau_kernel(float* tau, int B, int N, int mode, unsigned long long seed, unsigned long long ctr0,
+                               const unsigned long long* __restrict__ ctr_dev) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * N) return;
+    if (ctr_dev) ctr0 = *ctr_dev;
     int n = i % N;
     float t;
     switch (mode) {
@@ -38,6 +41,10 @@ __global__ void iqn_tau_kernel(float* tau, int B, int N, int mode, unsigned long
 }
 
 // cos(tau * (pi * i)), i = 1..E  -> [B*N][E]   (iqn/model/base.rs:170-179)
+__global__ void iqn_set_ctr_kernel(unsigned long long a, unsigned long long b, unsigned long long* dst) {
+    if (threadIdx.x == 0) { dst[0] = a; dst[1] = b; }
+}
+
 __global__ void iqn_cos_kernel(const float* __restrict__ tau, float* __restrict__ out, int BN, int E) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= BN * E) return;
@@ -204,6 +211,8 @@ struct Iqn : Agent {
     float* d_inject[2] = {nullptr, nullptr};
     size_t inject_n[2] = {0, 0};
     uint64_t tau_ctr = 0, soft_update_counter = 0, eps_n_opts = 0;
+    unsigned long long* d_ctr = nullptr;   // tau counters of the update's two forwards (device memory)
+    UpdateGraph graph;
     FastRand fr;
     uint8_t *d_obs_in = nullptr, *h_obs_in = nullptr;
     float* h_q = nullptr;
@@ -248,11 +257,14 @@ struct Iqn : Agent {
         iqn_tgt.copy_params_from(iqn, ctx.stream);
         models = {&iqn, &iqn_tgt};
         d_out = dev_alloc_zero<float>(8, ctx.stream);
+        d_ctr = dev_alloc_zero<unsigned long long>(2, ctx.stream);
         BB_CUDA(cudaStreamSynchronize(ctx.stream));
     }
     ~Iqn() override {
         DeviceGuard g(device);
         cudaStreamSynchronize(ctx.stream);
+        graph.reset();
+        cudaFree(d_ctr);
         ws_online.release(); ws_tgt.release(); ws_act.release();
         iqn.release(); iqn_tgt.release();
         f_net.free_tables();
@@ -262,6 +274,7 @@ struct Iqn : Agent {
         if (h_q) cudaFreeHost(h_q);
     }
     Model* sync_model_src() override { return &iqn; }
+    void precision_changed() override { graph.reset(); }
     void grad_buffer(void** p, uint64_t* n) override { *p = iqn.g; *n = iqn.n; }
 
     void inject_noise(int slot, const float* host, size_t n) override {
@@ -294,9 +307,11 @@ struct Iqn : Agent {
             BB_CHECK(inject_n[slot] == (size_t)B * N, "injected tau has the wrong size");
             BB_CUDA(cudaMemcpyAsync(w.tau, d_inject[slot], (size_t)B * N * 4, cudaMemcpyDeviceToDevice, ctx.stream));
         } else {
-            iqn_tau_kernel<<<(B * N + 255) / 256, 256, 0, ctx.stream>>>(w.tau, B, N, mode, cfg.tau_seed, tau_ctr);
+            // (slots 0 / 1 = the update's two forwards: their counters were written to d_ctr by update_critic)
+            iqn_tau_kernel<<<(B * N + 255) / 256, 256, 0, ctx.stream>>>(w.tau, B, N, mode, cfg.tau_seed, tau_ctr,
+                                                                        slot >= 0 ? d_ctr + slot : nullptr);
             BB_LAUNCHED();
-            tau_ctr += (uint64_t)B * N;
+            if (slot < 0) tau_ctr += (uint64_t)B * N;
         }
         const float* psi = f_net.forward(ctx, mdl.p + base_f, obs, f_net.in_elems, B, w.f);
         iqn_cos_kernel<<<(B * N * E + 255) / 256, 256, 0, ctx.stream>>>(w.tau, w.cos, B * N, E);
@@ -321,9 +336,32 @@ struct Iqn : Agent {
         BB_CHECK(rb.obs_row_bytes == (uint32_t)f_net.in_elems * (f_net.u8_input ? 1u : 4u),
                  "replay obs rows do not match the feature extractor input");
         BB_CHECK(rb.cfg.act_kind == BB_I64, "IQN needs i64 action rows");
-        if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
+        // this update's tau counters -> device memory (one launch), so that everything below is argument-invariant
+        const uint64_t c0 = tau_ctr;
+        if (!inject_n[0]) tau_ctr += (uint64_t)B * N;
+        const uint64_t c1 = tau_ctr;
+        if (!inject_n[1]) tau_ctr += (uint64_t)B * Nt;
+        iqn_set_ctr_kernel<<<1, 32, 0, ctx.stream>>>(c0, c1, d_ctr);
+        BB_LAUNCHED();
         bb_batch_view bv;
-        rb.sample(B, &bv);
+        graph.run(ctx, rb, B, inject_n[0] == 0 && inject_n[1] == 0, [&]() { enqueue_update(rb, B, N, Nt, bv, true); },
+                  [&]() { rb.sample(B, &bv, false); });
+        iqn.step += 1;
+        ctx.phase = "optimizer";
+        synced_adam(iqn);
+        inject_n[0] = inject_n[1] = 0;
+        if (want_loss) {
+            BB_CUDA(cudaMemcpyAsync(h_scratch, d_out, 4, cudaMemcpyDeviceToHost, ctx.stream));
+            BB_CUDA(cudaStreamSynchronize(ctx.stream));
+            return h_scratch[0];
+        }
+        return 0.f;
+    }
+
+    // every launch of one update up to the optimizer (update_critic, iqn/base.rs:110-170); argument-invariant
+    void enqueue_update(Replay& rb, int B, int N, int Nt, bb_batch_view& bv, bool launch_sample) {
+        if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
+        rb.sample(B, &bv, launch_sample);
         if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
         ctx.phase = "replay"; ctx.layer = "batch"; ctx.mark("sample_gather");
         ctx.phase = "fwd_online";
@@ -349,16 +387,6 @@ struct Iqn : Agent {
         ctx.layer = "merge"; ctx.mark("iqn_merge_bwd");
         phi_net.backward(ctx, iqn.p + base_phi, iqn.g + base_phi, ws_online.cos, E, B * N, ws_online.phi, nullptr, 0);
         f_net.backward(ctx, iqn.p + base_f, iqn.g + base_f, bv.obs, f_net.in_elems, B, ws_online.f, nullptr, 0);
-        iqn.step += 1;
-        ctx.phase = "optimizer";
-        synced_adam(iqn);
-        inject_n[0] = inject_n[1] = 0;
-        if (want_loss) {
-            BB_CUDA(cudaMemcpyAsync(h_scratch, d_out, 4, cudaMemcpyDeviceToHost, ctx.stream));
-            BB_CUDA(cudaStreamSynchronize(ctx.stream));
-            return h_scratch[0];
-        }
-        return 0.f;
     }
 
     void opt(Replay& rb, bb_record* rec) override {  // opt_, iqn/base.rs:172-190

@@ -682,7 +682,9 @@ __device__ __forceinline__ void wait_flags(const Exchange& x, int kind, unsigned
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float b1, float b2, float one_m_b1, float one_m_b2,
                             float eps, float bc2_sqrt, float neg_step, float wd, float decay, int adamw,
-                            PeerPtrs peers, int world, float* __restrict__ p_lo, Exchange xw, int wait_regions) {
+                            PeerPtrs peers, int world, float* __restrict__ p_lo, Exchange xw, int wait_regions,
+                            const AdamScalars* __restrict__ dev_scalars) {
+    if (dev_scalars) { bc2_sqrt = dev_scalars->bc2_sqrt; neg_step = dev_scalars->neg_step; decay = dev_scalars->decay; }
     if (wait_regions) {   // every rank's slice of the mean gradient has landed in this rank's buffer
         if (blockIdx.x == 0 && threadIdx.x == 0) xw.ctr[16] = gtimer_lo();
         if (wait_regions & 1) wait_flags(xw, 1, xw.ctr[0]);
@@ -899,21 +901,26 @@ void grad_reduce_scatter(const Ctx& c, const float* const* peer_grads, size_t n,
     c.mark("grad_reduce_scatter");
 }
 
-void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
-               uint64_t step, const float* const* peer_grads, int world, float* p_lo, const Exchange* wait, int wait_regions) {
+AdamScalars adam_scalars(const AdamHyper& h, uint64_t step) {
     double bc1 = 1.0 - pow(h.beta1, (double)step);
     double bc2 = 1.0 - pow(h.beta2, (double)step);
     double step_size = h.lr / bc1;
+    return AdamScalars{(float)sqrt(bc2), (float)(-step_size), (float)(1.0 - h.lr * h.wd), 0.f};
+}
+
+void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
+               uint64_t step, const float* const* peer_grads, int world, float* p_lo, const Exchange* wait, int wait_regions,
+               const AdamScalars* dev_scalars) {
+    const AdamScalars sc = adam_scalars(h, step);
     PeerPtrs pp;
     for (int r = 0; r < 8; ++r) pp.p[r] = (peer_grads && r < world) ? peer_grads[r] : nullptr;
     BB_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                reinterpret_cast<uintptr_t>(v)) & 15) == 0, "adam_step: buffers must be 16 B aligned");
     int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)c.sms * 8);
     adam_kernel<<<blocks, 256, 0, c.stream>>>(p, g, m, v, n, (float)h.beta1, (float)h.beta2, (float)(1.0 - h.beta1),
-                                              (float)(1.0 - h.beta2), (float)h.eps, (float)sqrt(bc2),
-                                              (float)(-step_size), (float)h.wd, (float)(1.0 - h.lr * h.wd),
+                                              (float)(1.0 - h.beta2), (float)h.eps, sc.bc2_sqrt, sc.neg_step, (float)h.wd, sc.decay,
                                               h.adamw ? 1 : 0, pp, peer_grads ? world : 1, p_lo, wait ? *wait : Exchange{},
-                                              wait ? wait_regions : 0);
+                                              wait ? wait_regions : 0, dev_scalars);
     BB_LAUNCHED();
     c.layer = "";
     c.mark("adam");

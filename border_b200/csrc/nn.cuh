@@ -121,7 +121,13 @@ struct AdamHyper {
 // p_lo != null: the kernel also refreshes the parameters' lo plane (operand of the TMA-fed GEMMs)
 void adam_step(const Ctx& c, float* p, const float* g, float* m, float* v, size_t n, const AdamHyper& h,
                uint64_t step /* 1-based */, const float* const* peer_grads = nullptr, int world = 1, float* p_lo = nullptr,
-               const Exchange* wait = nullptr, int wait_regions = 0 /* bit r: wait for region r's delivered flags */);
+               const Exchange* wait = nullptr, int wait_regions = 0 /* bit r: wait for region r's delivered flags */,
+               const struct AdamScalars* dev_scalars = nullptr);
+// The step-dependent scalars of one Adam launch (bias corrections folded with lr).  With `dev_scalars` the kernel reads them
+// from device memory -- the caller writes adam_scalars(h, step) there before the launch -- so that the launch itself is
+// argument-invariant and can be replayed from a CUDA graph (sac.cu).
+struct AdamScalars { float bc2_sqrt, neg_step, decay, pad; };
+AdamScalars adam_scalars(const AdamHyper& h, uint64_t step);
 // mean of all ranks' gradients, slice-owner computes and stores it into every rank's buffer (peer memory)
 void grad_reduce_scatter(const Ctx& c, const float* const* peer_grads, size_t n, int rank, int world);
 

@@ -35,9 +35,10 @@ __device__ __forceinline__ float sac_normal(unsigned long long seed, unsigned lo
 __global__ void sac_action_kernel(const float* __restrict__ heads, const float* __restrict__ z_in, float* __restrict__ z_out,
                                   const float* __restrict__ obs, int obs_dim, float* __restrict__ xa,
                                   float* __restrict__ a_out, float* __restrict__ logp, int B, int A, float lo, float hi,
-                                  float eps, unsigned long long seed, unsigned long long ctr0) {
+                                  float eps, unsigned long long seed, const unsigned long long* __restrict__ ctr_dev) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const unsigned long long ctr0 = *ctr_dev;   // (device memory: the launch is argument-invariant, see SacScalars)
     const float* hd = heads + (size_t)b * 2 * A;
     float lp_n = 0.f, lp_t = 0.f;
     for (int j = 0; j < A; ++j) {
@@ -78,9 +79,10 @@ __device__ __forceinline__ float sac_block_sum(float v, float* s) {
 
 // EntCoef::update (ent_coef.rs:69-75): loss = -mean(log_alpha * (logp + target)); Adam on the scalar.
 __global__ void __launch_bounds__(1024) sac_entcoef_kernel(const float* __restrict__ logp, int B, float target,
-                                                           float* log_alpha, float* m_, float* v_, float lr, float bc1,
-                                                           float bc2_sqrt) {
+                                                           float* log_alpha, float* m_, float* v_, float lr,
+                                                           const float* __restrict__ bc /* bc1, sqrt(bc2) */) {
     __shared__ float s[1024];
+    const float bc1 = bc[0], bc2_sqrt = bc[1];
     float acc = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) acc += logp[b] + target;
     float tot = sac_block_sum(acc, s);
@@ -95,6 +97,17 @@ __global__ void __launch_bounds__(1024) sac_entcoef_kernel(const float* __restri
 }
 
 struct QPtrs { const float* q[8]; float* dq[8]; };
+
+// Everything that changes from one update to the next, in device memory: one tiny launch writes it (kernel parameters are
+// copied at launch time, so the host can run ahead), every other launch of the update reads it and is argument-invariant.
+struct SacScalars {
+    AdamScalars pi, q[8];
+    float ent_bc1, ent_bc2_sqrt;
+    unsigned long long ctr[2];   // noise counters of update_actor's and update_critic's action_logp
+};
+__global__ void sac_set_scalars_kernel(SacScalars s, SacScalars* dst) {
+    if (threadIdx.x == 0) *dst = s;
+}
 
 // actor loss pieces (sac/base.rs:151-164): qmin over critics, dL/dQ_i, loss = mean(alpha*logp - qmin)
 __global__ void __launch_bounds__(1024) sac_actor_loss_kernel(QPtrs qp, int n_critics, const float* __restrict__ logp,
@@ -186,6 +199,8 @@ struct Sac : Agent {
     float* d_inject[2] = {nullptr, nullptr};
     size_t inject_n[2] = {0, 0};
     uint64_t noise_ctr = 0;
+    SacScalars* d_sc = nullptr;
+    UpdateGraph graph;
     FastRand fr;
     float *h_in = nullptr, *h_heads = nullptr;
     float* d_in = nullptr;
@@ -240,6 +255,7 @@ struct Sac : Agent {
         for (auto& q : qnets) models.push_back(&q);
         for (auto& q : qnets_tgt) models.push_back(&q);
         d_out = dev_alloc_zero<float>(8, ctx.stream);
+        d_sc = dev_alloc_zero<SacScalars>(1, ctx.stream);
         BB_CUDA(cudaStreamSynchronize(ctx.stream));
         ws_qa.resize(n_critics); ws_qc.resize(n_critics);
         pi_net.alloc_workspace(ws_pi_act, 1, false);
@@ -248,6 +264,8 @@ struct Sac : Agent {
     ~Sac() override {
         DeviceGuard g(device);
         cudaStreamSynchronize(ctx.stream);
+        graph.reset();
+        cudaFree(d_sc);
         ws_pi.release(); ws_pi_next.release(); ws_pi_act.release(); ws_qt.release();
         for (auto& w : ws_qa) w.release();
         for (auto& w : ws_qc) w.release();
@@ -261,6 +279,7 @@ struct Sac : Agent {
         if (h_heads) cudaFreeHost(h_heads);
     }
     Model* sync_model_src() override { return &pi; }  // sac/base.rs:377-386 ships only pi
+    void precision_changed() override { graph.reset(); }
     void grad_buffer(void** p, uint64_t* n) override { *p = pi.g; *n = pi.n; }
 
     void inject_noise(int slot, const float* host, size_t n) override {
@@ -301,10 +320,9 @@ struct Sac : Agent {
         }
         sac_action_kernel<<<(B + 127) / 128, 128, 0, ctx.stream>>>(heads, zin, z_keep, obs, obs_dim, xa, a, logp, B, act_dim,
                                                                     (float)cfg.min_lstd, (float)cfg.max_lstd, (float)cfg.epsilon,
-                                                                    cfg.noise_seed, noise_ctr);
+                                                                    cfg.noise_seed, &d_sc->ctr[slot]);
         BB_LAUNCHED();
         ctx.layer = "pi"; ctx.mark("sac_action");
-        noise_ctr += (uint64_t)B * act_dim;
     }
 
     QPtrs qptrs(std::vector<NetWorkspace>& ws) {
@@ -319,9 +337,40 @@ struct Sac : Agent {
         ensure_ws(B);
         BB_CHECK(rb.cfg.obs_kind == BB_F32 && (int)rb.cfg.obs_elems == obs_dim, "replay obs rows must be f32[obs_dim]");
         BB_CHECK(rb.cfg.act_kind == BB_F32 && (int)rb.cfg.act_elems == act_dim, "replay act rows must be f32[act_dim]");
-        if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
+        // host-side bookkeeping of this update: optimizer steps, noise counters -> SacScalars (one launch)
+        SacScalars sc{};
+        const bool auto_ent = cfg.ent_coef_mode == BB_ENTCOEF_AUTO;
+        if (auto_ent) {
+            ent.step += 1;
+            sc.ent_bc1 = (float)(1.0 - pow(0.9, (double)ent.step));
+            sc.ent_bc2_sqrt = (float)sqrt(1.0 - pow(0.999, (double)ent.step));
+        }
+        pi.step += 1;
+        sc.pi = adam_scalars(pi.hyper, pi.step);
+        for (int i = 0; i < n_critics; ++i) { qnets[i].step += 1; sc.q[i] = adam_scalars(qnets[i].hyper, qnets[i].step); }
+        sc.ctr[0] = noise_ctr; sc.ctr[1] = noise_ctr + (uint64_t)B * act_dim;
+        noise_ctr += 2 * (uint64_t)B * act_dim;
+        sac_set_scalars_kernel<<<1, 32, 0, ctx.stream>>>(sc, d_sc);
+        BB_LAUNCHED();
+        ctx.phase = "replay"; ctx.layer = "scalars"; ctx.mark("sac_set_scalars");
         bb_batch_view bv;
-        rb.sample(B, &bv);  // buffer.batch(self.batch_size), sac/base.rs:180
+        bool launch_sample = true;
+        auto enqueue = [&]() { enqueue_update(rb, B, bv, launch_sample); };
+        graph.run(ctx, rb, B, inject_n[0] == 0 && inject_n[1] == 0, enqueue, [&]() { rb.sample(B, &bv, false); });
+        n_opts += 1;
+        inject_n[0] = inject_n[1] = 0;
+        if (h_rec) {
+            BB_CUDA(cudaMemcpyAsync(h_scratch, d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx.stream));
+            BB_CUDA(cudaStreamSynchronize(ctx.stream));
+            h_rec[0] += h_scratch[0]; h_rec[1] += h_scratch[1]; h_rec[2] = h_scratch[2];
+        }
+    }
+
+    // every launch of one update (sac/base.rs:175-198 order: update_actor, update_critic, soft_update); argument-invariant
+    void enqueue_update(Replay& rb, int B, bb_batch_view& bv, bool launch_sample) {
+        const bool auto_ent = cfg.ent_coef_mode == BB_ENTCOEF_AUTO;
+        if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
+        rb.sample(B, &bv, launch_sample);  // buffer.batch(self.batch_size), sac/base.rs:180
         if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
         ctx.phase = "replay"; ctx.layer = "batch"; ctx.mark("sample_gather");
         const float* obs = (const float*)bv.obs;
@@ -331,11 +380,9 @@ struct Sac : Agent {
         // ---------------- update_actor (sac/base.rs:151-167)
         ctx.phase = "actor";
         action_logp(obs, B, ws_pi, 0, d_a, d_logp, d_z, d_xa);
-        if (cfg.ent_coef_mode == BB_ENTCOEF_AUTO) {  // ent_coef.update(&log_p.detach())
-            ent.step += 1;
-            double bc1 = 1.0 - pow(0.9, (double)ent.step), bc2 = 1.0 - pow(0.999, (double)ent.step);
+        if (auto_ent) {  // ent_coef.update(&log_p.detach())
             sac_entcoef_kernel<<<1, 1024, 0, ctx.stream>>>(d_logp, B, (float)cfg.ent_coef_target, ent.p, ent.m, ent.v,
-                                                          (float)cfg.ent_coef_lr, (float)bc1, (float)sqrt(bc2));
+                                                          (float)cfg.ent_coef_lr, &d_sc->ent_bc1);
             BB_LAUNCHED();
             ctx.layer = "ent_coef"; ctx.mark("entcoef_adam");
         }
@@ -355,8 +402,7 @@ struct Sac : Agent {
         BB_LAUNCHED();
         ctx.layer = "pi"; ctx.mark("sac_actor_grad");
         pi_net.backward(ctx, pi.p, pi.g, obs, obs_dim, B, ws_pi, nullptr, 0);
-        pi.step += 1;
-        adam_step(ctx, pi.p, pi.g, pi.m, pi.v, pi.n, pi.hyper, pi.step);
+        adam_step(ctx, pi.p, pi.g, pi.m, pi.v, pi.n, pi.hyper, pi.step, nullptr, 1, nullptr, nullptr, 0, &d_sc->pi);
 
         // ---------------- update_critic (sac/base.rs:107-149)
         ctx.phase = "critic";
@@ -378,19 +424,12 @@ struct Sac : Agent {
         ctx.layer = "loss"; ctx.mark("sac_critic_loss");
         for (int i = 0; i < n_critics; ++i) {  // separate Adam per critic (sac/base.rs:137-139)
             q_net.backward(ctx, qnets[i].p, qnets[i].g, d_xa, D, B, ws_qc[i], nullptr, 0);
-            qnets[i].step += 1;
-            adam_step(ctx, qnets[i].p, qnets[i].g, qnets[i].m, qnets[i].v, qnets[i].n, qnets[i].hyper, qnets[i].step);
+            adam_step(ctx, qnets[i].p, qnets[i].g, qnets[i].m, qnets[i].v, qnets[i].n, qnets[i].hyper, qnets[i].step, nullptr, 1,
+                      nullptr, nullptr, 0, &d_sc->q[i]);
         }
         // ---------------- soft_update (sac/base.rs:169-173)
         ctx.phase = "target_update";
         for (int i = 0; i < n_critics; ++i) track(ctx, qnets_tgt[i].p, qnets[i].p, qnets[i].n, cfg.tau);
-        n_opts += 1;
-        inject_n[0] = inject_n[1] = 0;
-        if (h_rec) {
-            BB_CUDA(cudaMemcpyAsync(h_scratch, d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx.stream));
-            BB_CUDA(cudaStreamSynchronize(ctx.stream));
-            h_rec[0] += h_scratch[0]; h_rec[1] += h_scratch[1]; h_rec[2] = h_scratch[2];
-        }
     }
 
     void opt(Replay& rb, bb_record* rec) override {  // opt_, sac/base.rs:175-198

@@ -267,7 +267,10 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
     g.workspace = c.ws; g.counters = c.tickets; g.error = device_error_flag();
     g.trace = env_i("BB_TMA_TRACE", 0) ? tma_trace_buffer() : nullptr;
     dim3 grid(tn, tm, split);
-    static const int cfg = env_i("BB_TMA_CFG", 0);
+    // one CTA per SM anyway (small or split-K grids): give it the 6-stage ring -- with 3 stages a k-slice's round trip
+    // (TMA 650 + lo split 380 + MMA 700 cycles) bounds the loop at ~750 cycles per slice, MMA issue alone is ~490
+    static const int cfg_env = env_i("BB_TMA_CFG", -1);
+    const int cfg = cfg_env >= 0 ? cfg_env : (tiles * split <= (long)c.sms ? 1 : 0);
     // debugging aid: BB_TMA_MASK bit i enables operand combination i (dense forward, conv forward / data gradient,
     // linear data gradient, linear weight gradient, conv weight gradient, conv data gradient); the others fall back to tc_gemm.cu
     const int combo = (AK == OP_K_TILED && BKIND == OP_K_TILED) ? 0 : (AK == OP_K_IM2COL && BKIND == OP_K_TILED) ? (g.ga.flip_w >= 0 ? 5 : 1)

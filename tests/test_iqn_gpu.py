@@ -133,3 +133,21 @@ def test_iqn_const_modes_policy_and_errors():
     bad = Iqn.build(cfg)
     with pytest.raises(L.BorderB200Error, match="Const32"):
         bad.opt(dev)
+
+
+def test_iqn_graph_replay_is_bit_identical_to_eager_launches(monkeypatch):
+    """Iqn captures sample .. backward into a CUDA graph after three eager updates (uniform ring, in-kernel tau draws read
+    their counters from device memory); the parameters after 8 updates equal the eager run's bit for bit."""
+    outs = []
+    stream = torch.cuda.Stream(device=0)
+    for graph in ("1", "0"):
+        monkeypatch.setenv("BB_GRAPH", graph)
+        rng, dev, orc, agent, oracle, params, psi_fn, m_fn, E = _setup("cnn", 16, 4, 1e-4)
+        dev.set_stream(stream.cuda_stream)
+        agent.set_stream(stream.cuda_stream)
+        losses = [agent.opt_with_record(dev)["loss_critic"] for _ in range(8)]
+        outs.append((losses, agent.named_parameters("iqn"), agent.named_parameters("iqn_tgt")))
+    assert outs[0][0] == outs[1][0]
+    for k in outs[0][1]:
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
+        assert np.array_equal(outs[0][2][k], outs[1][2][k]), k

@@ -109,3 +109,23 @@ def test_sac_policy_sample_and_inkernel_noise():
     assert np.isfinite(rec["loss_critic"]) and np.isfinite(rec["loss_actor"])
     n_opts, blob = agent.model_info()  # SyncModel ships pi only (sac/base.rs:377-386)
     assert blob.size == sum(v.numel() for v in oracle.pi.values())
+
+
+def test_sac_graph_replay_is_bit_identical_to_eager_launches(monkeypatch):
+    """After three eager updates Sac captures the whole update (sample .. soft_update, optimizers included: their
+    step-dependent scalars live in device memory) into a CUDA graph; 12 updates with in-kernel noise must leave the same
+    parameters as the eager run, bit for bit."""
+    outs = []
+    stream = torch.cuda.Stream(device=0)
+    for graph in ("1", "0"):
+        monkeypatch.setenv("BB_GRAPH", graph)
+        rng, dev, orc, agent, oracle = _setup(2, ("Auto", -8.0, 3e-4), "Mse", 64)
+        dev.set_stream(stream.cuda_stream)
+        agent.set_stream(stream.cuda_stream)
+        recs = [agent.opt_with_record(dev) for _ in range(12)]
+        outs.append((recs, {m: agent.named_parameters(m) for m in ("pi", "qnet_0", "qnet_1", "qnet_tgt_0", "ent_coef")}))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert a["loss_critic"] == b["loss_critic"] and a["loss_actor"] == b["loss_actor"] and a["ent_coef"] == b["ent_coef"]
+    for m in outs[0][1]:
+        for k in outs[0][1][m]:
+            assert np.array_equal(outs[0][1][m][k], outs[1][1][m][k]), (m, k)
