@@ -327,6 +327,13 @@ def run_b200(args):
     t0 = time.perf_counter()
     hl.env_steps(agent, rb, h_obs, h_next, h_rew, h_term, h_trunc, env_n)  # C++ loop over the C ABI (bbh_env_steps)
     torch.cuda.synchronize()
+    env_sps_host_push = world * env_n / (time.perf_counter() - t0)
+    # ... and through bb_actor_step (the observation crosses PCIe once, explorer on the device, push from device copies)
+    hl.actor_steps(agent, rb, h_obs, h_next, h_rew, h_term, h_trunc, 20)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    hl.actor_steps(agent, rb, h_obs, h_next, h_rew, h_term, h_trunc, env_n)
+    torch.cuda.synchronize()
     env_sps = world * env_n / (time.perf_counter() - t0)
 
     # ---- roofline of the dominant kernel, measured live with CUDA events after every kernel
@@ -438,6 +445,8 @@ def run_b200(args):
                        "loss read back every step"},
                "gpu_launches": launches,
                "env_steps_per_sec": env_sps,
+               "env_steps": {"value": env_sps, "unit": "env-steps/s", "path": "bb_actor_step (device-side explorer, device->ring push)",
+                             "host_sample_plus_host_push": env_sps_host_push, "h2d_bytes_per_step": ROW + 16, "d2h_bytes_per_step": 8},
                "roofline": roof, "roofline_replay": roof_replay,
                "step_flop": STEP_FLOP, "step_tflops": STEP_FLOP / (ms / args.steps * 1e-3) / 1e12,
                "kernel_breakdown_ms": {k: round(v, 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:12]}}

@@ -271,6 +271,20 @@ class Agent:
     def _act_dim(self):
         return 1
 
+    def actor_step(self, buffer, obs, reward=0.0, is_terminated=0, is_truncated=0, reset_obs=None):
+        """Sampler::sample_and_push (trainer/sampler.rs:99-144) for one env step with device-resident observations
+        (include/border_b200.h: bb_actor_step): pushes (previous obs, previous action, obs, reward, flags) -- nothing on
+        the first call -- and returns the action for `reset_obs if the episode ended else obs`."""
+        obs = np.ascontiguousarray(obs)
+        ro = None if reset_obs is None else np.ascontiguousarray(reset_obs)
+        act = C.c_int64()
+        L.check(L.lib().bb_actor_step(self._h, buffer.handle, _p(obs), None if ro is None else _p(ro), float(reward),
+                                      int(is_terminated), int(is_truncated), C.byref(act)))
+        return act.value
+
+    def actor_reset(self):
+        L.check(L.lib().bb_actor_reset(self._h))
+
     # Agent::opt / opt_with_record
     def opt(self, buffer: SimpleReplayBuffer):
         L.check(L.lib().bb_agent_opt(self._h, buffer.handle, None))

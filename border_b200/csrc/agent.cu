@@ -101,6 +101,9 @@ Model* Agent::model(const std::string& name) {
 }
 void Agent::inject_noise(int, const float*, size_t) { throw Error("this agent takes no injected noise"); }
 void Agent::grad_buffer(void** p, uint64_t* n) { *p = nullptr; *n = 0; }
+void Agent::actor_step(Replay&, const void*, const void*, float, int8_t, int8_t, int64_t*) {
+    BB_CHECK(false, "bb_actor_step: this agent has no device-side actor path (DQN only)");
+}
 
 // Cross-GPU barrier on flags in peer memory: rank r writes its epoch into slot r of every peer's
 // flag array (system-scope store over NVLink), then waits until all slots of its own array reach
@@ -446,6 +449,19 @@ int32_t bb_agent_sample(bb_agent* a, const void* obs, size_t n, void* act_out) {
     BB_CHECK(obs && act_out, "null argument");
     bb::check_device_error("bb_agent_sample");
     A(a).sample(obs, n, act_out);
+    BB_API_END
+}
+int32_t bb_actor_step(bb_agent* a, bb_replay* rb, const void* obs, const void* reset_obs, float reward, int8_t is_terminated,
+                      int8_t is_truncated, int64_t* act_out) {
+    BB_API_BEGIN
+    BB_CHECK(rb && obs && act_out, "null argument");
+    bb::check_device_error("bb_actor_step");
+    A(a).actor_step(rb->impl, obs, reset_obs, reward, is_terminated, is_truncated, act_out);
+    BB_API_END
+}
+int32_t bb_actor_reset(bb_agent* a) {
+    BB_API_BEGIN
+    A(a).actor_reset();
     BB_API_END
 }
 int32_t bb_agent_opt(bb_agent* a, bb_replay* rb, bb_record* record) {

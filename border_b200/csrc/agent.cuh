@@ -117,6 +117,11 @@ struct Agent {
     Model* model(const std::string& name);
     virtual void opt(Replay& rb, bb_record* rec) = 0;
     virtual void sample(const void* obs, size_t n, void* act_out) = 0;
+    // Sampler::sample_and_push (border-core/src/trainer/sampler.rs:99-144) with the observation crossing PCIe once:
+    // see bb_actor_step in border_b200.h.  Discrete-action agents only.
+    virtual void actor_step(Replay& rb, const void* obs, const void* reset_obs, float reward, int8_t term, int8_t trunc,
+                            int64_t* act_out);
+    virtual void actor_reset() {}
     virtual Model* sync_model_src() = 0;  // which VarStore SyncModel ships (DQN qnet, SAC pi)
     virtual void inject_noise(int slot, const float* host, size_t n);
     virtual void precision_changed() {}   // drop captured graphs (they hold the GEMM kernels of the previous precision mode)

@@ -204,4 +204,25 @@ int32_t bbh_env_steps(bb_agent* agent, bb_replay* replay, const void* obs, const
     BBH_END
 }
 
+/* The same loop through bb_actor_step: the observation crosses PCIe once, the action is chosen on the device and the
+ * transition is pushed from the device-resident copies.  Zero-cost environment: step i returns obs[i % n_slots] (and, when
+ * that slot's flags end the episode, next_obs[i % n_slots] plays env.reset()). */
+int32_t bbh_actor_steps(bb_agent* agent, bb_replay* replay, const void* obs, const void* next_obs, const float* reward,
+                        const int8_t* is_terminated, const int8_t* is_truncated, uint64_t obs_row_bytes, uint64_t n_slots,
+                        uint64_t n_steps, int64_t* last_act) {
+    BBH_BEGIN
+    if (!agent || !replay || !obs || !next_obs || !reward || !is_terminated || !is_truncated || !n_slots)
+        throw Error("null argument");
+    int64_t act = 0;
+    for (uint64_t i = 0; i < n_steps; ++i) {
+        const uint64_t j = i % n_slots;
+        const bool done = is_terminated[j] || is_truncated[j];
+        check(bb_actor_step(agent, replay, (const uint8_t*)obs + j * obs_row_bytes,
+                            done ? (const uint8_t*)next_obs + j * obs_row_bytes : nullptr, reward[j], is_terminated[j],
+                            is_truncated[j], &act));
+    }
+    if (last_act) *last_act = act;
+    BBH_END
+}
+
 }  // extern "C"

@@ -52,6 +52,8 @@ def host_lib():
         l.bbh_sampler_trace.argtypes = [C.POINTER(bbh_env_cfg), C.c_uint64, C.c_uint64, C.c_void_p]
         l.bbh_env_steps.restype = C.c_int32
         l.bbh_env_steps.argtypes = [C.c_void_p] * 7 + [C.c_uint64] * 3 + [C.POINTER(C.c_int64)]
+        l.bbh_actor_steps.restype = C.c_int32
+        l.bbh_actor_steps.argtypes = [C.c_void_p] * 7 + [C.c_uint64] * 3 + [C.POINTER(C.c_int64)]
         _hl = l
     return _hl
 
@@ -111,6 +113,18 @@ def env_steps(agent, buffer, obs, next_obs, reward, is_terminated, is_truncated,
     act = C.c_int64()
     _check(host_lib().bbh_env_steps(agent.handle, buffer.handle, *[a.ctypes.data for a in arrs], arrs[0].nbytes // n, n,
                                     n_steps, C.byref(act)))
+    return act.value
+
+
+def actor_steps(agent, buffer, obs, next_obs, reward, is_terminated, is_truncated, n_steps):
+    """env_steps through bb_actor_step: the observation crosses PCIe once per step, the explorer runs in the tail of the
+    policy forward and the transition is pushed from its device-resident copies.  Returns the last action."""
+    import numpy as np
+    n = len(reward)
+    arrs = [np.ascontiguousarray(a) for a in (obs, next_obs, reward, is_terminated, is_truncated)]
+    act = C.c_int64()
+    _check(host_lib().bbh_actor_steps(agent.handle, buffer.handle, *[a.ctypes.data for a in arrs], arrs[0].nbytes // n, n,
+                                      n_steps, C.byref(act)))
     return act.value
 
 

@@ -278,6 +278,20 @@ int32_t bb_agent_is_train(const bb_agent* a, int32_t* out);
 /* Policy::sample for `n` observations (host pointers; n = 1 in Sampler::sample_and_push).
  * act_out: int64[n] for DQN/IQN, float[n*act_dim] for SAC. */
 int32_t bb_agent_sample(bb_agent* a, const void* obs, size_t n, void* act_out);
+/* Sampler::sample_and_push (border-core/src/trainer/sampler.rs:99-144) for one environment step of a discrete-action
+ * agent, with the observation crossing PCIe ONCE and the action chosen on the device (dqn/explorer.rs:29-31,68-90; the
+ * fastrand draws stay on the host, in the reference's order, so the action sequence is the one bb_agent_sample gives):
+ *   `obs`      the observation env.step returned (host), i.e. next_obs of the transition that started at the previous
+ *              call's observation with the previous call's action; (reward, is_terminated, is_truncated) belong to it.
+ *              That transition is pushed into `rb` from the device-resident copies (nothing is pushed on the first call
+ *              after create / bb_actor_reset);
+ *   `reset_obs` NULL, or -- when the episode ended -- the observation env.reset() returned: the policy acts on it;
+ *   `act_out`  the action for the next env.step (Policy::sample on `reset_obs ? reset_obs : obs`).
+ * One host->device copy (the observation row + 6 bytes), one push kernel, the policy forward with the explorer in the
+ * tail, an 8-byte action written to pinned host memory, one synchronisation. */
+int32_t bb_actor_step(bb_agent* a, bb_replay* rb, const void* obs, const void* reset_obs, float reward, int8_t is_terminated,
+                      int8_t is_truncated, int64_t* act_out);
+int32_t bb_actor_reset(bb_agent* a);   /* forget the previous observation (new Sampler / after a manual env.reset) */
 /* Agent::opt / opt_with_record (record may be NULL => no device->host copy at all). */
 int32_t bb_agent_opt(bb_agent* a, bb_replay* rb, bb_record* record);
 int32_t bb_agent_n_opts(const bb_agent* a, uint64_t* out);

@@ -71,6 +71,10 @@ int32_t bbh_e2e_steps(bb_agent* agent, bb_replay* replay, const void* obs, const
 int32_t bbh_env_steps(bb_agent* agent, bb_replay* replay, const void* obs, const void* next_obs, const float* reward,
                       const int8_t* is_terminated, const int8_t* is_truncated, uint64_t obs_row_bytes, uint64_t n_slots,
                       uint64_t n_steps, int64_t* last_act);
+/* bbh_env_steps through bb_actor_step (border_b200.h): one PCIe crossing per step, action chosen on the device. */
+int32_t bbh_actor_steps(bb_agent* agent, bb_replay* replay, const void* obs, const void* next_obs, const float* reward,
+                      const int8_t* is_terminated, const int8_t* is_truncated, uint64_t obs_row_bytes, uint64_t n_slots,
+                      uint64_t n_steps, int64_t* last_act);
 
 #ifdef __cplusplus
 }
