@@ -5,7 +5,7 @@ NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
 CSRC      := border_b200/csrc
 OBJDIR    := build/obj
 LIB       := border_b200/libborder_b200.so
-SRCS      := common.cu replay.cu nn.cu agent.cu dqn.cu sac.cu iqn.cu tc_gemm.cu tma_gemm.cu tma_gemm_fast.cu conv1_tc.cu
+SRCS      := common.cu replay.cu nn.cu agent.cu dqn.cu sac.cu iqn.cu tc_gemm.cu tma_gemm.cu tma_gemm_fast.cu conv1_tc.cu atari.cu
 SRCS      := $(filter $(notdir $(wildcard $(CSRC)/*.cu)),$(SRCS))
 OBJS      := $(patsubst %.cu,$(OBJDIR)/%.o,$(SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.inc) include/border_b200.h

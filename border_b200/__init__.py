@@ -6,3 +6,4 @@ and the examples); the product is libborder_b200.so (include/border_b200.h).
 from .replay import GenericTransitionBatch, PerConfig, SimpleReplayBuffer, SimpleReplayBufferConfig  # noqa: F401
 from .agents import (AtariCnnConfig, Dqn, DqnConfig, DqnModelConfig, EpsilonGreedy, Iqn, IqnConfig, MlpConfig,  # noqa: F401
                      OptimizerConfig, Sac, SacConfig, Softmax)
+from .atari import AtariPreprocessor  # noqa: F401

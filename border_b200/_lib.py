@@ -147,6 +147,14 @@ _SIGS = {
     "bb_agent_exchange_trace": (C.c_int32, [_P, C.POINTER(C.c_uint32)]),
     "bb_actor_step": (C.c_int32, [_P, _P, _P, _P, C.c_float, C.c_int8, C.c_int8, C.POINTER(C.c_int64)]),
     "bb_actor_reset": (C.c_int32, [_P]),
+    "bb_actor_step_dev": (C.c_int32, [_P, _P, _P, _P, C.c_float, C.c_int8, C.c_int8, C.POINTER(C.c_int64)]),
+    "bb_atari_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "bb_atari_destroy": (C.c_int32, [_P]),
+    "bb_atari_set_stream": (C.c_int32, [_P, _P]),
+    "bb_atari_reset": (C.c_int32, [_P, _P]),
+    "bb_atari_step": (C.c_int32, [_P, _P, _P, C.c_float, C.POINTER(C.c_float)]),
+    "bb_atari_obs_device": (C.c_int32, [_P, _P, C.POINTER(_P)]),
+    "bb_atari_obs_host": (C.c_int32, [_P, _P]),
     "bb_agent_ipc_export": (C.c_int32, [_P, _P, _P]),
     "bb_agent_ipc_connect": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, _P]),
     "bb_kernel_launch_count": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32]),

@@ -282,6 +282,14 @@ class Agent:
                                       int(is_terminated), int(is_truncated), C.byref(act)))
         return act.value
 
+    def actor_step_dev(self, buffer, obs_dev, reward=0.0, is_terminated=0, is_truncated=0, reset_obs_dev=None):
+        """actor_step with the observation already in HBM (device pointers, e.g. AtariPreprocessor.obs_device())."""
+        act = C.c_int64()
+        L.check(L.lib().bb_actor_step_dev(self._h, buffer.handle, C.c_void_p(obs_dev),
+                                          None if reset_obs_dev is None else C.c_void_p(reset_obs_dev), float(reward),
+                                          int(is_terminated), int(is_truncated), C.byref(act)))
+        return act.value
+
     def actor_reset(self):
         L.check(L.lib().bb_actor_reset(self._h))
 

@@ -101,7 +101,7 @@ Model* Agent::model(const std::string& name) {
 }
 void Agent::inject_noise(int, const float*, size_t) { throw Error("this agent takes no injected noise"); }
 void Agent::grad_buffer(void** p, uint64_t* n) { *p = nullptr; *n = 0; }
-void Agent::actor_step(Replay&, const void*, const void*, float, int8_t, int8_t, int64_t*) {
+void Agent::actor_step(Replay&, const void*, const void*, float, int8_t, int8_t, int64_t*, bool) {
     BB_CHECK(false, "bb_actor_step: this agent has no device-side actor path (DQN only)");
 }
 
@@ -457,6 +457,14 @@ int32_t bb_actor_step(bb_agent* a, bb_replay* rb, const void* obs, const void* r
     BB_CHECK(rb && obs && act_out, "null argument");
     bb::check_device_error("bb_actor_step");
     A(a).actor_step(rb->impl, obs, reset_obs, reward, is_terminated, is_truncated, act_out);
+    BB_API_END
+}
+int32_t bb_actor_step_dev(bb_agent* a, bb_replay* rb, const void* obs_dev, const void* reset_obs_dev, float reward,
+                          int8_t is_terminated, int8_t is_truncated, int64_t* act_out) {
+    BB_API_BEGIN
+    BB_CHECK(rb && obs_dev && act_out, "null argument");
+    bb::check_device_error("bb_actor_step_dev");
+    A(a).actor_step(rb->impl, obs_dev, reset_obs_dev, reward, is_terminated, is_truncated, act_out, true);
     BB_API_END
 }
 int32_t bb_actor_reset(bb_agent* a) {

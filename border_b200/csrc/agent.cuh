@@ -120,7 +120,7 @@ struct Agent {
     // Sampler::sample_and_push (border-core/src/trainer/sampler.rs:99-144) with the observation crossing PCIe once:
     // see bb_actor_step in border_b200.h.  Discrete-action agents only.
     virtual void actor_step(Replay& rb, const void* obs, const void* reset_obs, float reward, int8_t term, int8_t trunc,
-                            int64_t* act_out);
+                            int64_t* act_out, bool obs_on_device = false);
     virtual void actor_reset() {}
     virtual Model* sync_model_src() = 0;  // which VarStore SyncModel ships (DQN qnet, SAC pi)
     virtual void inject_noise(int slot, const float* host, size_t n);

@@ -416,7 +416,7 @@ struct Dqn : Agent {
 
     // bb_actor_step (border_b200.h): Sampler::sample_and_push with device-resident observations
     void actor_step(Replay& rb, const void* obs, const void* reset_obs, float reward, int8_t term, int8_t trunc,
-                    int64_t* act_out) override {
+                    int64_t* act_out, bool obs_on_device) override {
         DeviceGuard g(device);
         const size_t row = (size_t)net.in_elems * (net.u8_input ? 1 : 4);
         BB_CHECK(rb.obs_row_bytes == row && rb.cfg.act_kind == BB_I64 && rb.cfg.act_elems == 1,
@@ -433,10 +433,15 @@ struct Dqn : Agent {
         // the transition's next_obs (+ reward / flags behind it) -> the slot that is not the previous observation
         const int cur = actor_prev ^ 1;
         uint8_t* h = h_actor_stage;
-        memcpy(h, obs, row);
         memcpy(h + actor_row_pad, &reward, 4);
         h[actor_row_pad + 4] = (uint8_t)term; h[actor_row_pad + 5] = (uint8_t)trunc;
-        BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], h, actor_row_pad + 16, cudaMemcpyHostToDevice, ctx.stream));
+        if (obs_on_device) {   // e.g. the frame stack bb_atari_step left in HBM: only reward + flags cross PCIe
+            BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], obs, row, cudaMemcpyDeviceToDevice, ctx.stream));
+            BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur] + actor_row_pad, h + actor_row_pad, 16, cudaMemcpyHostToDevice, ctx.stream));
+        } else {
+            memcpy(h, obs, row);
+            BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], h, actor_row_pad + 16, cudaMemcpyHostToDevice, ctx.stream));
+        }
         if (actor_has_prev) {
             if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
             const uint8_t* m = d_actor_obs[cur] + actor_row_pad;
@@ -447,8 +452,9 @@ struct Dqn : Agent {
         int act_src = cur;
         if (reset_obs) {   // the episode ended: the next action is for the reset observation (sampler.rs:128-137)
             uint8_t* h2 = h_actor_stage + actor_row_pad + 16;
-            memcpy(h2, reset_obs, row);
-            BB_CUDA(cudaMemcpyAsync(d_actor_obs[actor_prev], h2, row, cudaMemcpyHostToDevice, ctx.stream));   // after the push read it
+            if (!obs_on_device) memcpy(h2, reset_obs, row);
+            BB_CUDA(cudaMemcpyAsync(d_actor_obs[actor_prev], obs_on_device ? reset_obs : h2, row,   // after the push read it
+                                    obs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
             act_src = actor_prev;
         }
         const float* q = net.forward_small(ctx, qnet.p, d_actor_obs[act_src], net.in_elems, 1, ws_actor);

@@ -291,6 +291,10 @@ int32_t bb_agent_sample(bb_agent* a, const void* obs, size_t n, void* act_out);
  * tail, an 8-byte action written to pinned host memory, one synchronisation. */
 int32_t bb_actor_step(bb_agent* a, bb_replay* rb, const void* obs, const void* reset_obs, float reward, int8_t is_terminated,
                       int8_t is_truncated, int64_t* act_out);
+/* The same with `obs` / `reset_obs` already in HBM (device pointers, e.g. bb_atari_obs_device): only reward and flags
+ * cross PCIe.  The pointers must stay valid and unchanged until the call returns (it synchronises). */
+int32_t bb_actor_step_dev(bb_agent* a, bb_replay* rb, const void* obs_dev, const void* reset_obs_dev, float reward,
+                          int8_t is_terminated, int8_t is_truncated, int64_t* act_out);
 int32_t bb_actor_reset(bb_agent* a);   /* forget the previous observation (new Sampler / after a manual env.reset) */
 /* Agent::opt / opt_with_record (record may be NULL => no device->host copy at all). */
 int32_t bb_agent_opt(bb_agent* a, bb_replay* rb, bb_record* record);
@@ -339,6 +343,24 @@ int32_t bb_agent_ipc_connect(bb_agent* a, int32_t rank, int32_t world, const voi
                              const void* flag_handles /* world*64 */);
 /* Launch count of this library's kernels since the last reset (bench.py's gpu_launches). */
 int32_t bb_kernel_launch_count(uint64_t* out, int32_t reset);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Atari observation pipeline (border-atari-env/src/env.rs) on the device: RGB24 frames in, the [4][84][84] u8 frame
+ * stack (newest first) out, left in HBM for bb_actor_step_dev / bb_replay_push(on_device).
+ *   bb_atari_reset   env.rs:263-300  all four frames = warp_and_grayscale(first render)
+ *   bb_atari_step    env.rs:126-147 (max of the two last repeated frames), :161-185 (resize 84x84 Triangle + grey),
+ *                    :187-199 (stack_frame), :149-159 (clip_reward: sign(r) when built with train != 0)
+ * The emulator itself (atari-env-sys) stays on the host and is out of scope. */
+typedef struct bb_atari bb_atari;
+int32_t bb_atari_create(int32_t device, int32_t width /* 160 */, int32_t height /* 210 */, int32_t train, bb_atari** out);
+int32_t bb_atari_destroy(bb_atari* st);
+int32_t bb_atari_set_stream(bb_atari* st, void* cuda_stream);
+int32_t bb_atari_reset(bb_atari* st, const uint8_t* rgb /* host [h][w][3] */);
+int32_t bb_atari_step(bb_atari* st, const uint8_t* rgb_a, const uint8_t* rgb_b, float reward, float* reward_out);
+/* current observation: device pointer (valid until the next-but-one step; `consumer_stream` is made to wait for it) ... */
+int32_t bb_atari_obs_device(bb_atari* st, void* consumer_stream, const uint8_t** dev_ptr);
+/* ... or a host copy of the 28,224 bytes (synchronises) */
+int32_t bb_atari_obs_host(bb_atari* st, uint8_t* out);
 
 #ifdef __cplusplus
 }
