@@ -587,6 +587,109 @@ def roofline_for(label, ms, step_ms, pk):
             "traffic": None, "ms_per_launch": ms, "share_of_step": ms / step_ms, "peak_source": pk["src"]}
 
 
+def run_async(args):
+    """BASELINE configs[4] (border-async-trainer/src/util.rs:31-92, actor_manager/base.rs:141-175): per GPU `--actors` actor
+    threads (own agent + synthetic zero-cost env, seed = actor id + rank offset) push bulks of transitions through the
+    ReplayBufferProxy channel into the learner's device-resident ring while the learner runs B=256 NatureCNN updates; with
+    N GPUs the learners exchange gradients every update (bb_agent_ipc_*).  One JSON line: grad-steps/s and env-steps/s of
+    the whole job, measured over `--steps` synchronised updates per learner (wall clock of the slowest rank: the loop is
+    host-driven, CUDA events would time the same span)."""
+    import ctypes as C
+    import hashlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from border_b200 import _lib as L
+    from border_b200 import dist as bd
+    from border_b200 import host_loops as H
+    from border_b200.agents import AtariCnnConfig, DqnConfig, DqnModelConfig, EpsilonGreedy, OptimizerConfig
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    cfg = DqnConfig(model_config=DqnModelConfig(q_config=AtariCnnConfig(4, N_ACT), opt_config=OptimizerConfig(lr=1e-4)),
+                    soft_update_interval=10000, n_updates_per_opt=1, batch_size=B, discount_factor=0.99, tau=1.0, train=True,
+                    explorer=EpsilonGreedy(), device=local, critic_loss="Mse", init_seed=0).to_c()
+    rc = L.bb_replay_cfg()
+    L.lib().bb_replay_cfg_default(C.byref(rc))
+    cap = min(args.capacity, 1 << 16)
+    rc.capacity, rc.seed, rc.per_config_some, rc.device = cap, 42 + rank, 0, local
+    rc.obs_kind, rc.obs_elems, rc.act_kind, rc.act_elems = L.BB_U8, 4 * 84 * 84, L.BB_I64, 1
+    env = H.bbh_env_cfg(L.BB_U8, 4 * 84 * 84, 1000, 0)
+    warm = 4 * B
+    tc = H.trainer_cfg(max_opts=args.steps + args.warmup, warmup_period=warm, sync_interval=100, n_actors=args.actors,
+                       n_buffer=16, record_agent_info_interval=args.steps + args.warmup)
+    state = {"sync": "none", "digest": None, "t_loop": None, "t_end": None}
+
+    class _H:   # what border_b200.dist expects of an agent
+        def __init__(self, h):
+            self.handle = h
+
+    def on_learner(handle, phase):
+        if phase == 0 and world > 1:
+            state["sync"] = bd.connect_gradient_peers(_H(handle), dist, torch)
+        elif phase == 2:
+            if world > 1:
+                dist.barrier()   # every learner is warm: the updates below are synchronised across ranks anyway
+            state["t_loop"] = time.perf_counter()
+        elif phase == 1:
+            torch.cuda.synchronize()
+            state["t_end"] = time.perf_counter()
+            n, no = C.c_uint64(), C.c_uint64()
+            L.check(L.lib().bb_agent_model_info_size(handle, C.byref(n)))
+            blob = np.empty(n.value, np.float32)   # (the size is in floats)
+            L.check(L.lib().bb_agent_model_info(handle, blob.ctypes.data_as(C.c_void_p), blob.size, C.byref(no)))
+            state["digest"] = hashlib.sha256(blob.tobytes()).digest()
+
+    # zero-cost environments outrun the learner's drain: wait for room in the bounded channel instead of failing the actor
+    os.environ["BBH_ACTOR_BACKPRESSURE"] = "1"
+    # one emulated env step = 4 ALE frames at ~6,000 frames/s/core (the reference's frame skip, border-atari-env/src/env.rs:131)
+    os.environ.setdefault("BBH_ENV_STEP_US", "600")
+    t0 = time.perf_counter()
+    st = H.train_async("dqn", cfg, rc, env, tc, on_learner=on_learner)
+    wall = time.perf_counter() - t0
+    opt_s, env_s = st["opt_per_sec"], st["samples_per_sec"]
+    secs = state["t_end"] - state["t_loop"]   # the optimisation loop only (the reference's own stat also counts the warm-up)
+    total_secs = st["total_seconds"]
+    identical = None
+    if world > 1:
+        t = torch.tensor([secs, st["samples_total"] / total_secs, st["env_steps"] / total_secs], device="cuda", dtype=torch.float64)
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        secs = float(mx[0].item())
+        samples_ps, env_ps = float(sm[1].item()), float(sm[2].item())
+        d = torch.tensor(list(state["digest"]), dtype=torch.uint8, device="cuda")
+        ds = [torch.empty_like(d) for _ in range(world)]
+        dist.all_gather(ds, d)
+        identical = all(bool(torch.equal(x, ds[0])) for x in ds)
+    else:
+        samples_ps, env_ps = st["samples_total"] / total_secs, st["env_steps"] / total_secs
+    if rank == 0:
+        total_opts = args.steps + args.warmup
+        print(json.dumps({
+            "metric": "grad-steps/sec", "value": world * total_opts / secs, "unit": "grad-steps/s", "n_gpus": world,
+            "steps": total_opts, "warmup": 0, "ms_per_step": 1e3 * secs / total_opts, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "async_" + WORKLOAD, "topology": "train_async: %d actor threads per GPU -> ReplayBufferProxy channel "
+                       "-> learner (B=256), model sync every 100 updates; learners exchange gradients every update" % args.actors,
+                       "batch_per_gpu": B, "replay_capacity": cap, "warmup_period": warm, "grad_sync": state["sync"],
+                       "env": "synthetic u8 frames, %s us busy-wait per step (4 ALE frames at ~6,000 fps/core)" % os.environ["BBH_ENV_STEP_US"],
+                       "timed_region": "the optimisation loop of train_async (after the %d-transition warm-up): %d updates with the "
+                                       "actors pushing concurrently; wall clock of the slowest rank, device synchronised at the end" % (warm, total_opts)},
+            "env_steps_per_sec": env_ps, "pushed_transitions_per_sec": samples_ps,
+            "reference_stat_opt_per_sec_rank0": opt_s, "reference_stat_samples_per_sec_rank0": env_s,
+            "ranks_bit_identical": identical, "wall_s_rank0": wall, "last_loss": st["last_loss"], "model_syncs": st["syncs"]}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -599,10 +702,16 @@ def main():
     ap.add_argument("--repeats", type=int, default=5, help="time the K-step region this many times, report the median")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the SAC / IQN / PER / large-batch gather side measurements")
+    ap.add_argument("--topology", default="sync", choices=["sync", "async"],
+                    help="async = BASELINE configs[4]: actor threads per GPU feed a learner (train_async), learners "
+                         "synchronised across GPUs; a side measurement, the driver's line is the default sync topology")
+    ap.add_argument("--actors", type=int, default=4, help="actor threads per GPU for --topology async")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
+    elif args.topology == "async":
+        run_async(args)
     else:
         run_b200(args)
 

@@ -76,6 +76,9 @@ struct ExperienceBufferBase {  // replay_buffer.rs:38-62
 
 struct ReplayBufferBase : ExperienceBufferBase {  // replay_buffer.rs:74-127 (batch() stays on the device)
     virtual bb_replay* handle() = 0;
+    // the items of one PushedItemMessage, in order (async_trainer/base.rs:280-282 pushes them one by one; an implementation
+    // may move them in one call as long as the ring ends up identical)
+    virtual void push_all(std::vector<Transition>&& items) { for (auto& it : items) push(std::move(it)); }
 };
 
 struct Policy {  // policy.rs:49-63
@@ -110,10 +113,31 @@ class B200ReplayBuffer : public ReplayBufferBase {
         check(bb_replay_push(h_, tr.obs.data(), tr.act.data(), tr.next_obs.data(), &tr.reward, &tr.is_terminated,
                              &tr.is_truncated, 1, 0));
     }
+    // one bb_replay_push of n rows (= n pushes of one row: same ring indices, same PER priorities), one H2D copy
+    void push_all(std::vector<Transition>&& items) override {
+        const size_t n = items.size();
+        if (n == 0) return;
+        if (n == 1) { push(std::move(items[0])); return; }
+        const size_t ob = items[0].obs.size(), ab = items[0].act.size();
+        pk_obs_.resize(n * ob); pk_next_.resize(n * ob); pk_act_.resize(n * ab);
+        pk_r_.resize(n); pk_t_.resize(n); pk_tr_.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            const Transition& t = items[i];
+            if (t.obs.size() != ob || t.next_obs.size() != ob || t.act.size() != ab) throw Error("push_all: ragged transitions");
+            memcpy(pk_obs_.data() + i * ob, t.obs.data(), ob);
+            memcpy(pk_next_.data() + i * ob, t.next_obs.data(), ob);
+            memcpy(pk_act_.data() + i * ab, t.act.data(), ab);
+            pk_r_[i] = t.reward; pk_t_[i] = t.is_terminated; pk_tr_[i] = t.is_truncated;
+        }
+        check(bb_replay_push(h_, pk_obs_.data(), pk_act_.data(), pk_next_.data(), pk_r_.data(), pk_t_.data(), pk_tr_.data(), n, 0));
+    }
     size_t len() const override { uint64_t n = 0; check(bb_replay_len(h_, &n)); return (size_t)n; }
     bb_replay* handle() override { return h_; }
   private:
     bb_replay* h_ = nullptr;
+    Bytes pk_obs_, pk_next_, pk_act_;
+    std::vector<float> pk_r_;
+    std::vector<int8_t> pk_t_, pk_tr_;
 };
 
 class B200Agent : public Agent, public SyncModel {
@@ -283,7 +307,8 @@ struct PushedItemMessage { size_t id; std::vector<Transition> pushed_items; };  
 
 class ReplayBufferProxy : public ExperienceBufferBase {  // replay_buffer_proxy.rs:30-72
   public:
-    ReplayBufferProxy(size_t id, size_t n_buffer, Channel<PushedItemMessage>& sender) : id_(id), n_buffer_(n_buffer), sender_(sender) {
+    ReplayBufferProxy(size_t id, size_t n_buffer, Channel<PushedItemMessage>& sender, const std::atomic<bool>* stop = nullptr)
+        : id_(id), n_buffer_(n_buffer), sender_(sender), stop_(stop) {
         buffer_.reserve(n_buffer);
     }
     void push(Transition&& tr) override {
@@ -292,13 +317,21 @@ class ReplayBufferProxy : public ExperienceBufferBase {  // replay_buffer_proxy.
             PushedItemMessage msg{id_, std::move(buffer_)};
             buffer_ = {};
             buffer_.reserve(n_buffer_);
-            if (!sender_.try_send(std::move(msg))) throw Error("SendMsgForPush");  // error.rs:4-7
+            // error.rs:4-7: the reference fails the actor when the bounded channel is full.  BBH_ACTOR_BACKPRESSURE=1 (the
+            // benchmark's zero-cost environments produce faster than any learner drains) waits for room instead.
+            static const bool backpressure = getenv("BBH_ACTOR_BACKPRESSURE") && atoi(getenv("BBH_ACTOR_BACKPRESSURE")) != 0;
+            while (!sender_.try_send(std::move(msg))) {
+                if (!backpressure) throw Error("SendMsgForPush");
+                if (stop_ && stop_->load()) return;
+                std::this_thread::yield();
+            }
         }
     }
     size_t len() const override { throw Error("ReplayBufferProxy::len is unimplemented"); }
   private:
     size_t id_, n_buffer_;
     Channel<PushedItemMessage>& sender_;
+    const std::atomic<bool>* stop_;
     std::vector<Transition> buffer_;
 };
 
@@ -318,7 +351,7 @@ class Actor {  // actor/base.rs:37-178
         : id_(id), af_(std::move(af)), ef_(std::move(ef)), env_seed_(env_seed), n_buffer_(n_buffer), stop_(stop) {}
     ActorStat run(Channel<PushedItemMessage>& sender, SharedModel& model_info) {
         auto agent = af_();
-        ReplayBufferProxy buffer(id_, n_buffer_, sender);
+        ReplayBufferProxy buffer(id_, n_buffer_, sender, &stop_);
         Sampler sampler(ef_(env_seed_), SimpleStepProcessor());
         size_t n_opt_steps = 0;
         auto t0 = std::chrono::steady_clock::now();
@@ -361,8 +394,12 @@ struct AsyncTrainStat { double samples_per_sec = 0, opt_per_sec = 0, seconds = 0
                         std::vector<ActorStat> actors; };
 
 // train_async (util.rs:31-92): N actor threads -> channel -> learner thread (the caller's).
+// on_learner(agent, phase): called on the learner thread with phase 0 right after the learner agent exists (a data-parallel
+// job connects its gradient peers there), phase 2 when the warm-up is over and the optimisation loop starts, phase 1 after
+// the last optimisation step (parameter checksums).
 inline AsyncTrainStat train_async(const AsyncTrainerConfig& cfg, size_t n_actors, size_t n_buffer, AgentFactory af,
-                                  EnvFactory ef, ReplayBufferBase& buffer) {
+                                  EnvFactory ef, ReplayBufferBase& buffer,
+                                  const std::function<void(B200Agent&, int)>& on_learner = nullptr) {
     using clk = std::chrono::steady_clock;
     Channel<PushedItemMessage> items(1000 * std::max<size_t>(1, n_actors));  // bounded(1000) per forwarding hop
     SharedModel shared;
@@ -381,6 +418,7 @@ inline AsyncTrainStat train_async(const AsyncTrainerConfig& cfg, size_t n_actors
     try {
         auto agent = af();                                         // async_trainer/base.rs:314
         agent->train();
+        if (on_learner) on_learner(*agent, 0);
         auto sync = [&] {                                          // :268-272
             ModelInfo m = agent->model_info();
             std::lock_guard<std::mutex> lk(shared.mu);
@@ -390,7 +428,7 @@ inline AsyncTrainStat train_async(const AsyncTrainerConfig& cfg, size_t n_actors
         auto update_replay_buffer = [&] {                          // :275-284
             for (auto& msg : items.try_iter()) {
                 out.samples_total += msg.pushed_items.size();
-                for (auto& it : msg.pushed_items) buffer.push(std::move(it));
+                buffer.push_all(std::move(msg.pushed_items));
             }
         };
         auto t_all = clk::now();
@@ -400,6 +438,7 @@ inline AsyncTrainStat train_async(const AsyncTrainerConfig& cfg, size_t n_actors
             for (auto& e : errors) if (!e.empty()) throw Error("actor failed: " + e);
             std::this_thread::yield();
         }
+        if (on_learner) on_learner(*agent, 2);                     // warm-up over: the optimisation loop starts
         size_t opt_steps = 0;
         for (;;) {
             update_replay_buffer();                                // :340
@@ -417,6 +456,7 @@ inline AsyncTrainStat train_async(const AsyncTrainerConfig& cfg, size_t n_actors
                 stop.store(true);
                 items.try_iter();
                 sync();
+                if (on_learner) on_learner(*agent, 1);
                 break;
             }
         }

@@ -29,6 +29,13 @@ class SyntheticEnv : public Env {
         return make_obs();
     }
     Step step(const Bytes& act) override {
+        // BBH_ENV_STEP_US: emulated cost of one environment step (default 0 = free).  bench.py --topology async sets it to an
+        // ALE-like figure so that the actors of BASELINE configs[4] produce at a realistic rate instead of flooding the learner.
+        static const long step_us = getenv("BBH_ENV_STEP_US") ? atol(getenv("BBH_ENV_STEP_US")) : 0;
+        if (step_us > 0) {
+            const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(step_us);
+            while (std::chrono::steady_clock::now() < until) {}
+        }
         t_ += 1;
         steps_ += 1;
         Step s;
@@ -119,6 +126,11 @@ int32_t bbh_train(int32_t algo, const void* agent_cfg, const bb_replay_cfg* repl
 
 int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg, const bbh_env_cfg* env_cfg,
                         const bbh_trainer_cfg* tc, bbh_train_stat* out) {
+    return bbh_train_async_ex(algo, agent_cfg, replay_cfg, env_cfg, tc, nullptr, nullptr, out);
+}
+
+int32_t bbh_train_async_ex(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg, const bbh_env_cfg* env_cfg,
+                           const bbh_trainer_cfg* tc, bbh_learner_hook hook, void* user, bbh_train_stat* out) {
     BBH_BEGIN
     if (!agent_cfg || !replay_cfg || !env_cfg || !tc || !out) throw Error("null argument");
     B200ReplayBuffer buffer(*replay_cfg);
@@ -128,7 +140,9 @@ int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg
     bbh_env_cfg ec = *env_cfg;
     AsyncTrainStat st = train_async(
         cfg, (size_t)tc->n_actors, (size_t)tc->n_buffer, [=] { return make_agent(algo, agent_cfg); },
-        [=](size_t seed) { return std::unique_ptr<Env>(new SyntheticEnv(ec, seed)); }, buffer);
+        [=](size_t seed) { return std::unique_ptr<Env>(new SyntheticEnv(ec, seed)); }, buffer,
+        hook ? std::function<void(B200Agent&, int)>([=](B200Agent& a, int phase) { hook(a.handle(), phase, user); })
+             : std::function<void(B200Agent&, int)>());
     memset(out, 0, sizeof(*out));
     out->opt_steps = cfg.max_opts; out->samples_total = st.samples_total; out->syncs = st.syncs;
     out->samples_per_sec = st.samples_per_sec; out->opt_per_sec = st.opt_per_sec; out->total_seconds = st.seconds;

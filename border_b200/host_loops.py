@@ -83,11 +83,30 @@ def train(algo, agent_cfg, replay_cfg, env_cfg, tcfg, save_dir=None):
     return _stat(st)
 
 
-def train_async(algo, agent_cfg, replay_cfg, env_cfg, tcfg):
-    """train_async (border-async-trainer/src/util.rs:31-92)."""
+LEARNER_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_void_p)
+
+
+def train_async(algo, agent_cfg, replay_cfg, env_cfg, tcfg, on_learner=None):
+    """train_async (border-async-trainer/src/util.rs:31-92).  on_learner(handle, phase): called on the learner thread with
+    the learner's bb_agent handle, phase 0 after it was created (connect gradient peers here), 1 after the last update."""
     st = bbh_train_stat()
-    _check(host_lib().bbh_train_async(ALGO[algo], C.cast(C.pointer(agent_cfg), C.c_void_p), C.byref(replay_cfg),
-                                      C.byref(env_cfg), C.byref(tcfg), C.byref(st)))
+    lib = host_lib()
+    lib.bbh_train_async_ex.restype = C.c_int32
+    lib.bbh_train_async_ex.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, LEARNER_HOOK, C.c_void_p,
+                                       C.c_void_p]
+    errors = []
+
+    def _hook(handle, phase, _user):
+        try:
+            on_learner(C.c_void_p(handle), phase)
+        except BaseException as e:  # an exception must not unwind through the C++ frames
+            errors.append(e)
+
+    cb = LEARNER_HOOK(_hook) if on_learner else LEARNER_HOOK(0)
+    _check(lib.bbh_train_async_ex(ALGO[algo], C.cast(C.pointer(agent_cfg), C.c_void_p), C.byref(replay_cfg), C.byref(env_cfg),
+                                  C.byref(tcfg), cb, None, C.byref(st)))
+    if errors:
+        raise errors[0]
     return _stat(st)
 
 

@@ -50,6 +50,15 @@ int32_t bbh_train(int32_t algo, const void* agent_cfg, const bb_replay_cfg* repl
 int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg,
                         const bbh_env_cfg* env_cfg, const bbh_trainer_cfg* trainer_cfg, bbh_train_stat* out);
 
+/* The same with a hook on the learner thread: phase 0 right after the learner agent exists (a data-parallel job -- BASELINE
+ * configs[4]: actors per GPU feeding a learner, learners synchronised across GPUs -- connects the learner's gradient peers
+ * there, bb_agent_ipc_export / bb_agent_ipc_connect), phase 2 when the replay warm-up is over and the optimisation loop
+ * starts, phase 1 after the last optimisation step. */
+typedef void (*bbh_learner_hook)(bb_agent* learner, int32_t phase, void* user);
+int32_t bbh_train_async_ex(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg,
+                           const bbh_env_cfg* env_cfg, const bbh_trainer_cfg* trainer_cfg, bbh_learner_hook hook, void* user,
+                           bbh_train_stat* out);
+
 /* Test hook (no device work): n_steps x Sampler::sample_and_push (trainer/sampler.rs:99-144 + SimpleStepProcessor::process,
  * step_proc.rs:103-137) with a scripted policy (action of step i = i) and a recording buffer over the synthetic u8 environment;
  * row i of out[n_steps][8] = {obs episode, obs word, next_obs episode, next_obs word, act, reward, is_terminated, is_truncated}

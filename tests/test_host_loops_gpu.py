@@ -84,3 +84,20 @@ def test_host_errors_surface():
     env = H.bbh_env_cfg(L.BB_F32, 5, 10, 0)  # obs_elems 5 != network in_dim 4
     with pytest.raises(L.BorderB200Error):
         H.train("dqn", _dqn_mlp(8), _replay_cfg(100, L.BB_F32, 5, L.BB_I64, 1), env, H.trainer_cfg(max_opts=2, warmup_period=8))
+
+
+def test_train_async_learner_hook_phases():
+    """bbh_train_async_ex: the hook sees the learner's handle after creation (phase 0: where a data-parallel job connects
+    its gradient peers) and after the last update (phase 1), on the calling thread."""
+    env = H.bbh_env_cfg(L.BB_F32, 4, 23, 0)
+    tc = H.trainer_cfg(max_opts=20, warmup_period=64, sync_interval=5, n_actors=2, n_buffer=8, record_agent_info_interval=20)
+    seen = []
+
+    def hook(handle, phase):
+        n = C.c_uint64()
+        L.check(L.lib().bb_agent_n_opts(handle, C.byref(n)))
+        seen.append((phase, n.value))
+
+    st = H.train_async("dqn", _dqn_mlp(16), _replay_cfg(1000, L.BB_F32, 4, L.BB_I64, 1), env, tc, on_learner=hook)
+    assert st["opt_steps"] == 20
+    assert seen == [(0, 0), (2, 0), (1, 20)]
