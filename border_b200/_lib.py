@@ -96,6 +96,7 @@ _SIGS = {
                                  C.c_int32, _P]),
     "bb_test_conv": (C.c_int32, [C.c_int32] * 10 + [_P] * 5),
     "bb_tma_trace": (C.c_int32, [_P]),
+    "bb_tma_trace_ctas": (C.c_int32, [_P]),
     "bb_tma_stats": (C.c_int32, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int32]),
     "bb_bench_gemm": (C.c_int32, [C.c_int32] * 7 + [C.POINTER(C.c_float)]),
     "bb_debug_tc_trace": (C.c_int32, [_P]),

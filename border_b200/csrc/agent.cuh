@@ -148,7 +148,8 @@ struct UpdateGraph {
                           ctx.stream != cudaStreamLegacy && ctx.stream != cudaStreamPerThread && rb.stream == ctx.stream &&
                           eager >= 3 && rb.batch_cap >= (size_t)B;
         if (want) {
-            const void* k[4] = {&rb, (const void*)(uintptr_t)B, (const void*)ctx.stream, (const void*)rb.b_obs};
+            const void* k[4] = {&rb, (const void*)(uintptr_t)B, (const void*)ctx.stream,
+                                (const void*)((uintptr_t)rb.b_obs ^ (uintptr_t)(rb.batch_generation << 48))};
             if (exec && memcmp(k, key, sizeof(k)) == 0) {
                 advance();
                 BB_CUDA(cudaGraphLaunch(exec, ctx.stream));

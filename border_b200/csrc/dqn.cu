@@ -279,6 +279,7 @@ struct Dqn : Agent {
         ctx.phase = "fwd_target";
         if (cfg.double_dqn) {                                                              // :93-99
             // online net on next_obs: borrow the target workspace first, keep its Q in d_scratch
+            BB_CHECK((size_t)B * net.out_dim <= (size_t)(1 << 20), "double DQN: batch x actions exceeds the scratch buffer");
             const float* qn = net.forward(tctx, qnet.p, bv.next_obs, ld_in, B, ws_tgt, 0, in_ix);
             BB_CUDA(cudaMemcpyAsync(d_scratch, qn, (size_t)B * net.out_dim * 4, cudaMemcpyDeviceToDevice, tctx.stream));
             q_next = d_scratch;
@@ -338,7 +339,8 @@ struct Dqn : Agent {
                                 rb.stream == ctx.stream && eager_updates >= 3 && rb.batch_cap >= (size_t)B;
         bool done = false;
         if (want_graph) {
-            const void* key[4] = {&rb, (const void*)(uintptr_t)B, (const void*)ctx.stream, (const void*)rb.b_obs};
+            const void* key[4] = {&rb, (const void*)(uintptr_t)B, (const void*)ctx.stream,
+                                  (const void*)((uintptr_t)rb.b_obs ^ (uintptr_t)(rb.batch_generation << 48))};   // (buffers may be reallocated at the same address)
             if (gexec && memcmp(key, g_key, sizeof(key)) == 0) {
                 rb.sample(B, &bv, false);
                 BB_CUDA(cudaGraphLaunch(gexec, ctx.stream));

@@ -643,6 +643,7 @@ void Replay::ensure_batch(size_t B) {
     b_ix = dev_alloc<unsigned long long>(B);
     b_weight = dev_alloc<float>(B);
     batch_cap = B;
+    batch_generation += 1;
 }
 
 PerParams Replay::per_params() const {

@@ -48,6 +48,7 @@ struct Replay {
     uint64_t head = 0, size = 0, n_samples = 0, n_opts = 0, rng_pos = 0, fr_draws = 0, inject_pending = 0;
     // last sampled batch
     size_t batch_cap = 0, last_batch = 0;
+    uint64_t batch_generation = 0;   // bumped whenever the batch buffers are reallocated: captured CUDA graphs key on it
     uint8_t *b_obs = nullptr, *b_next_obs = nullptr, *b_act = nullptr;
     float* b_reward = nullptr;
     int8_t *b_term = nullptr, *b_trunc = nullptr;

@@ -138,8 +138,8 @@ void make_lo(const Ctx& c, const float* x, float* lo, size_t n) {
 static long long* tma_trace_buffer() {
     static long long* buf = nullptr;
     if (!buf) {
-        BB_CUDA(cudaMalloc(&buf, 3 * 64 * 4 * sizeof(long long)));
-        BB_CUDA(cudaMemset(buf, 0, 3 * 64 * 4 * sizeof(long long)));
+        BB_CUDA(cudaMalloc(&buf, (3 * 64 * 4 + 4 * 1024) * sizeof(long long)));
+        BB_CUDA(cudaMemset(buf, 0, (3 * 64 * 4 + 4 * 1024) * sizeof(long long)));
     }
     return buf;
 }
@@ -295,6 +295,15 @@ extern "C" int32_t bb_tma_trace(int64_t* out) {
     BB_API_BEGIN
     BB_CUDA(cudaDeviceSynchronize());
     BB_CUDA(cudaMemcpy(out, bb::tma_trace_buffer(), 3 * 64 * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    BB_API_END
+}
+// ... and the per-CTA part: out[1024][4] = {entry ns, after the dependency wait, exit ns, SM id} (zero rows: CTA did not exist)
+extern "C" int32_t bb_tma_trace_ctas(int64_t* out) {
+    BB_API_BEGIN
+    BB_CHECK(out, "null argument");
+    BB_CUDA(cudaDeviceSynchronize());
+    BB_CUDA(cudaMemcpy(out, bb::tma_trace_buffer() + 3 * 64 * 4, 4 * 1024 * sizeof(long long), cudaMemcpyDeviceToHost));
+    BB_CUDA(cudaMemset(bb::tma_trace_buffer() + 3 * 64 * 4, 0, 4 * 1024 * sizeof(long long)));
     BB_API_END
 }
 

@@ -31,6 +31,7 @@
 // Tile 128 x BN x 32, STAGES-deep TMA ring, 192 threads.  Every mbarrier wait is bounded: a mis-programmed
 // pipeline raises the error flag (checked by the host after every update) instead of hanging the GPU.
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -74,7 +75,8 @@ struct Args {
     float* workspace;      // [split_k][M][N] partial tiles
     unsigned int* counters;  // [tiles] tickets, zero between launches
     int* error;            // device flag: a bounded wait timed out
-    long long* trace;      // debug (BB_TMA_TRACE=1): clock64 stamps of CTA (0,0,0): [role 0..2][slice < 64][4]
+    long long* trace;      // debug (BB_TMA_TRACE=1): clock64 stamps of CTA (0,0,0): [role 0..2][slice < 64][4], then per CTA
+                           // (first 1024) %globaltimer at entry / after the dependency wait / at exit and its SM id
     Im2col ga;
 };
 
@@ -258,8 +260,11 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    const unsigned cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (g.trace && tid == 0 && cta_lin < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); g.trace[768 + cta_lin * 4 + 0] = (long long)t; }
     pdl_sync();  // barriers / tensor memory are set up while the previous kernel of the stream drains
     if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) g.trace[(1 * 64 + 63) * 4 + 0] = clock64();
+    if (g.trace && tid == 0 && cta_lin < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); g.trace[768 + cta_lin * 4 + 1] = (long long)t; }
 
     if (warp == 0) {
         // ================================================================ TMA producer
@@ -460,16 +465,25 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool ov4 = (mapped || (g.ldc & 3) == 0) && (g.c_plane & 3) == 0 &&
                          ((reinterpret_cast<uintptr_t>(g.C) | reinterpret_cast<uintptr_t>(g.mask)) & 15) == 0;
 
+        const bool bias_v4 = (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;   // (cc is a multiple of 4)
         // final values of storage-space group (rr, cc .. cc+nv-1) -> C (+ lo plane)
         auto store_final = [&](int rr, int cc, float4 a, int nv) {
             float x[4] = {a.x, a.y, a.z, a.w};
             const size_t o = mapped ? (size_t)g.c_rowoff[rr] + (size_t)g.c_coloff[cc] : (size_t)rr * g.ldc + cc;
+            if (g.bias) {
+                if (tr) {
+                    const float b = __ldg(g.bias + rr);
+                    x[0] += b; x[1] += b; x[2] += b; x[3] += b;
+                } else if (nv == 4 && bias_v4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
+                    x[0] += b.x; x[1] += b.y; x[2] += b.z; x[3] += b.w;
+                } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j >= nv) break;
-                if (g.bias) x[j] += g.bias[tr ? rr : cc + j];
-                if (g.relu) x[j] = fmaxf(x[j], 0.f);
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nv) x[j] += __ldg(g.bias + cc + j);
+                }
             }
+            if (g.relu) { x[0] = fmaxf(x[0], 0.f); x[1] = fmaxf(x[1], 0.f); x[2] = fmaxf(x[2], 0.f); x[3] = fmaxf(x[3], 0.f); }
             if (ov4 && nv == 4) {
                 if (g.mask) {
                     const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + o));
@@ -529,31 +543,42 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + ((uint32_t)(c0 + j) * LDT + row) * 4u), "r"(r[j]) : "memory");
             }
         }
+        if (tr3) g.trace[(2 * 64 + 62) * 4 + 0] = clock64();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        // ---- phase B
+        if (tr3) g.trace[(2 * 64 + 62) * 4 + 1] = clock64();
+        // ---- phase B: compile-time tile geometry per output orientation (the index arithmetic and the loop were ~100
+        // instructions per 16-byte group with runtime extents: 4400 cycles per tile), 4 groups in flight per thread
         float* part = split ? g.workspace + (size_t)blockIdx.z * g.M * g.N : nullptr;
         const bool pv4 = (ldp & 3) == 0;
-        const uint32_t ldst = tr ? LDT : LDN;
-        for (int idx = te; idx < RT * G; idx += 256) {
-            const int rl = idx / G, cl = (idx - rl * G) * 4;
-            const int rr = R0 + rl, cc = C0 + cl;
-            if (rr >= Rmax || cc >= Cmax) continue;
-            const int nv = min(4, Cmax - cc);
-            float4 x;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(stg + ((uint32_t)rl * ldst + (uint32_t)cl) * 4u));
-            if (!split) {
-                store_final(rr, cc, x, nv);
-            } else {
-                float* pz = part + (size_t)rr * ldp + cc;
-                if (pv4 && nv == 4) *reinterpret_cast<float4*>(pz) = x;
-                else {
-                    pz[0] = x.x;
-                    if (nv > 1) pz[1] = x.y;
-                    if (nv > 2) pz[2] = x.z;
-                    if (nv > 3) pz[3] = x.w;
+        auto phase_b = [&](auto tr_tag) {
+            constexpr bool kTr = decltype(tr_tag)::value;
+            constexpr int kRT = kTr ? BN : BM, kG = (kTr ? BM : BN) / 4, kLd = kTr ? LDT : LDN;
+            constexpr int kIters = kRT * kG / 256;
+            static_assert(kRT * kG % 256 == 0, "tile groups are a multiple of the epilogue threads");
+#pragma unroll 4
+            for (int it = 0; it < kIters; ++it) {
+                const int idx = te + it * 256;
+                const int rl = idx / kG, cl = (idx % kG) * 4;
+                const int rr = R0 + rl, cc = C0 + cl;
+                if (rr >= Rmax || cc >= Cmax) continue;
+                const int nv = min(4, Cmax - cc);
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(stg + ((uint32_t)rl * kLd + (uint32_t)cl) * 4u));
+                if (!split) {
+                    store_final(rr, cc, x, nv);
+                } else {
+                    float* pz = part + (size_t)rr * ldp + cc;
+                    if (pv4 && nv == 4) *reinterpret_cast<float4*>(pz) = x;
+                    else {
+                        pz[0] = x.x;
+                        if (nv > 1) pz[1] = x.y;
+                        if (nv > 2) pz[2] = x.z;
+                        if (nv > 3) pz[3] = x.w;
+                    }
                 }
             }
-        }
+        };
+        if (tr) phase_b(std::true_type{}); else phase_b(std::false_type{});
         if (split) {
             // The last CTA of this tile to arrive (atomic ticket) folds the partials in split order -- deterministic -- and runs
             // the final epilogue: a coalesced pass with 16 independent 16-byte loads in flight per thread (4 positions x 4 splits).
@@ -617,6 +642,12 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 64) g.trace[(2 * 64 + 63) * 4 + 3] = clock64();
+    if (g.trace && tid == 0 && cta_lin < 1024) {   // whole-grid view: when did every CTA start / end, on which SM
+        unsigned long long t; unsigned sm;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+        g.trace[768 + cta_lin * 4 + 2] = (long long)t; g.trace[768 + cta_lin * 4 + 3] = sm;
+    }
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }

@@ -76,6 +76,9 @@ int32_t bb_test_conv(int32_t device, int32_t mode, int32_t use_tma, int32_t B, i
 /* Debug: clock64 stamps of CTA (0,0,0) of the last TMA GEMM launched with BB_TMA_TRACE=1: [3 roles: TMA producer, MMA issuer,
  * split warp][64 k-slices][4 stamps]. */
 int32_t bb_tma_trace(int64_t* out);
+/* ... and of every CTA (first 1024) of that launch: out[1024][4] = %globaltimer at entry / after the dependency wait / at
+ * exit (ns) and the SM id; rows of CTAs that did not exist are zero.  Clears the buffer. */
+int32_t bb_tma_trace_ctas(int64_t* out);
 
 /* GEMM launches that took the TMA-fed path / tensor-map constructions the driver refused, since the last reset. */
 int32_t bb_tma_stats(uint64_t* launches, uint64_t* rejects, int32_t reset);
