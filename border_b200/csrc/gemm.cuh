@@ -30,6 +30,8 @@ struct TmaConv {
     int N, H, W, C;   // tensor dims
     int KH, KW, S;    // filter taps and traversal stride
     int flip;         // 1: tap offsets run backwards (transposed convolution over a zero-padded gradient)
+    int pad;          // zero padding on every side, supplied by the TMA unit's out-of-bounds fill (the tensor itself is
+                      // unpadded): filter bases start at -pad
 };
 
 struct GemmArgs {

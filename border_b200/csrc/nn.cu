@@ -561,35 +561,59 @@ __global__ void dgrad_prep_kernel(const float4* __restrict__ dY, float4* __restr
     }
 }
 
+bool dgrad_gather_path(const ConvGeom& g) {
+    return g.dypad && g.dg_rowbase && g.dg_wt && env_int("BB_TC", 1) && env_int("BB_DGRAD_GATHER", 1);
+}
+
+// Wt[n][k] = W[brow[k] + bnoff[n]]: the weights of the gather-form data gradient, k-contiguous (the weight-only blocks of
+// dgrad_prep_kernel).  Depends on the parameters only, so it runs beside the start of the backward pass.
+void conv_dgrad_prepare_weights(const Ctx& c, const ConvGeom& g, const float* W) {
+    const int Jh = g.KH / g.S, Jw = g.KW / g.S;
+    const int N = g.S * g.S * g.C, K = Jh * Jw * g.OC;
+    const int w_blocks = std::min((N * K + 255) / 256, c.sms * 2);
+    dgrad_prep_kernel<<<w_blocks, 256, 0, c.stream>>>(nullptr, nullptr, g.B, g.OH, g.OW, g.OC / 4, g.dg_hp(), g.dg_wp(), Jh - 1, Jw - 1,
+                                                      0, W, g.dg_wt, g.dg_brow, g.dg_bnoff, N, K, 0, 0, g.w_plane, g.wt_plane);
+    BB_LAUNCHED();
+    c.mark("dgrad_weights");
+}
+
 void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float* W, float* col, float* dX,
                    const float* mask) {
     BB_CHECK(!g.u8_chw && g.C % 4 == 0, "conv_bwd_data expects an NHWC float input with C % 4 == 0");
     // Default since the whole-tile producer path of the tcgen05 kernel: DQN step 415 -> 382 us at B = 256 (c2: 9 + 41 us
     // instead of 46 + 22 us for dY*W + col2im, c3: 9 + 36 us instead of 35 + 18 us).  BB_DGRAD_GATHER=0 keeps the col2im path.
-    if (g.dypad && g.dg_rowbase && g.dg_wt && env_int("BB_TC", 1) && env_int("BB_DGRAD_GATHER", 1)) {
+    if (dgrad_gather_path(g)) {
         // dX[b][S hq + ph][S wq + pw][c] = sum_{jh,jw,oc} dYpad[b][hq + Jh-1-jh][wq + Jw-1-jw][oc] W[oc][S jh + ph][S jw + pw][c]:
         // one tcgen05 GEMM, no [M][K] column buffer and no col2im pass (the buffer was 42 MB for c2 at B = 256)
         const int Jh = g.KH / g.S, Jw = g.KW / g.S;
         const int N = g.S * g.S * g.C, K = Jh * Jw * g.OC;
+        if (!g.wt_ready) conv_dgrad_prepare_weights(c, g, W);   // (Net::backward does it on a side stream at the start of the pass)
+        GemmArgs a = zero_args();
+        a.a_rowbase = g.dg_rowbase; a.a_koff = g.dg_koff;
+        a.B = g.dg_wt; a.ldb = K;
+        a.C = dX; a.ldc = N; a.c_rowoff = g.dg_crow; a.c_coloff = g.dg_ccol; a.mask = mask;
+        a.M = g.B * (g.H / g.S) * (g.W / g.S); a.N = N; a.K = K;
+        a.tables_vec4 = 1;  // OC % 4 == 0 and C % 4 == 0 (dgrad_gather_ok)
+        a.b_plane = g.wt_plane; a.c_plane = g.dx_plane;
+        // TMA form 1: a stride-1 im2col walk of dY ITSELF with the tap offsets running backwards; the zero halo of the
+        // transposed convolution is the tensor map's out-of-bounds fill -- no padded copy of dY (DQN step 283.6 -> 282.0 us;
+        // BB_DGRAD_DIRECT=0 restores the copy)
+        if (Jh == Jw && env_int("BB_DGRAD_DIRECT", 1)) {
+            const TmaConv cv{g.B, g.OH, g.OW, g.OC, Jh, Jw, 1, 1, Jh - 1};
+            a.A = dY; a.a_conv = &cv; a.a_plane = g.y_plane;
+            if (tma_gemm(c, G_FWD, a)) return;
+        }
+        // form 2 / SIMT-fed fallback: over a zero-padded copy of dY
         size_t total = (size_t)g.B * g.OH * g.OW * (g.OC / 4);
         int pad_blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.sms * 6);
-        int w_blocks = std::min((N * K + 255) / 256, c.sms * 2);
-        dgrad_prep_kernel<<<pad_blocks + w_blocks, 256, 0, c.stream>>>(
+        dgrad_prep_kernel<<<pad_blocks, 256, 0, c.stream>>>(
             reinterpret_cast<const float4*>(dY), reinterpret_cast<float4*>(g.dypad), g.B, g.OH, g.OW, g.OC / 4, g.dg_hp(),
             g.dg_wp(), Jh - 1, Jw - 1, pad_blocks, W, g.dg_wt, g.dg_brow, g.dg_bnoff, N, K,
             g.y_plane && g.dypad_plane ? g.y_plane / 4 : 0, g.y_plane && g.dypad_plane ? g.dypad_plane / 4 : 0, g.w_plane, g.wt_plane);
         BB_LAUNCHED();
         c.mark("dgrad_prep");
-        GemmArgs a = zero_args();
-        a.A = g.dypad; a.a_rowbase = g.dg_rowbase; a.a_koff = g.dg_koff;
-        a.B = g.dg_wt; a.ldb = K;
-        a.C = dX; a.ldc = N; a.c_rowoff = g.dg_crow; a.c_coloff = g.dg_ccol; a.mask = mask;
-        a.M = g.B * (g.H / g.S) * (g.W / g.S); a.N = N; a.K = K;
-        a.tables_vec4 = 1;  // OC % 4 == 0 and C % 4 == 0 (dgrad_gather_ok)
-        // TMA form: a stride-1 im2col walk of the padded dY with the tap offsets running backwards
-        const TmaConv cv{g.B, g.dg_hp(), g.dg_wp(), g.OC, Jh, Jw, 1, 1};
-        a.a_conv = &cv; a.a_plane = g.dypad_plane; a.b_plane = g.wt_plane;
-        a.c_plane = g.dx_plane;
+        const TmaConv cv{g.B, g.dg_hp(), g.dg_wp(), g.OC, Jh, Jw, 1, 1, 0};
+        a.A = g.dypad; a.a_conv = &cv; a.a_plane = g.dypad_plane;
         if (tma_gemm(c, G_FWD, a)) return;
         if (tc_gemm(c, G_FWD, a)) return;
     }
@@ -1388,6 +1412,27 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
     }
     const bool conc = c.concurrent() && g;
     int n_side = 0;
+    auto conv_geom = [&](int i) {
+        ConvGeom cg = layers[i].geom;
+        cg.B = B; cg.rowbase = w.rowbase[i];
+        cg.dg_rowbase = w.dg_rowbase[i]; cg.dg_crow = w.dg_crow[i]; cg.dypad = w.dypad[i]; cg.dg_wt = w.dg_wt[i];
+        return cg;
+    };
+    // The re-laid weights of the gather-form data gradients depend on the parameters only, so they could run beside the start
+    // of the pass -- measured SLOWER (DQN step 283.6 -> 286.8 us: the extra fork / join costs more than the 2 x 3 us launches
+    // it takes off the critical path), so it is opt-in (BB_DGRAD_WT_SIDE=1).
+    bool wt_side = false, wt_joined = false;
+    if (conc && env_int("BB_DGRAD_WT_SIDE", 0)) {
+        for (int i = L - 1; i >= 1; --i) {
+            if (layers[i].type != 1) continue;
+            ConvGeom cg = conv_geom(i);
+            cg.w_plane = p_plane; cg.wt_plane = p_plane ? w.wt_plane[i] : 0;
+            if (!dgrad_gather_path(cg)) continue;
+            if (!wt_side) { c.fork_to(*c.side[0]); wt_side = true; }
+            c.side[0]->layer = layer_name(i) + ".dgrad";
+            conv_dgrad_prepare_weights(*c.side[0], cg, p + layers[i].w_off);
+        }
+    }
     for (int i = L - 1; i >= 0; --i) {
         const Layer& l = layers[i];
         const void* x = i ? (const void*)w.act[i - 1] : input;
@@ -1411,9 +1456,9 @@ void Net::backward(const Ctx& c, const float* p, float* g, const void* input, lo
         const long x_plane = (p_plane && i) ? w.plane[i - 1] : 0, dy_plane = dy_lo ? w.plane[i] : 0;
         const long dx_plane = (p_plane && i) ? w.plane[i - 1] : 0;
         if (l.type == 1) {
-            ConvGeom cg = l.geom;
-            cg.B = B; cg.rowbase = w.rowbase[i];
-            cg.dg_rowbase = w.dg_rowbase[i]; cg.dg_crow = w.dg_crow[i]; cg.dypad = w.dypad[i]; cg.dg_wt = w.dg_wt[i];
+            ConvGeom cg = conv_geom(i);
+            cg.wt_ready = (wt_side && dx) ? 1 : 0;
+            if (cg.wt_ready && !wt_joined) { c.join_from(*c.side[0]); wt_joined = true; }
             cg.x_plane = x_plane; cg.y_plane = dy_plane; cg.w_plane = p_plane; cg.dx_plane = dx_plane;
             cg.dypad_plane = p_plane ? w.dypad_plane[i] : 0; cg.wt_plane = p_plane ? w.wt_plane[i] : 0;
             cg.in_ix = i == 0 ? in_ix : nullptr;

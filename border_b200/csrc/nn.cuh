@@ -90,6 +90,7 @@ struct ConvGeom {
     const int* dg_ccol = nullptr;     // [S*S*C]
     float* dypad = nullptr;           // [B][H/S + KH/S - 1][W/S + KW/S - 1][OC] per workspace, borders stay zero
     float* dg_wt = nullptr;           // [S*S*C][(KH/S)*(KW/S)*OC] per workspace: the weights re-laid k-contiguous per step
+    int wt_ready = 0;                 // dg_wt already holds this step's weights (conv_dgrad_prepare_weights ran)
     // lo planes (element offsets; 0 = none): input X, output Y / its gradient dY, weights, input gradient dX, dypad, dg_wt
     long x_plane = 0, y_plane = 0, w_plane = 0, dx_plane = 0, dypad_plane = 0, wt_plane = 0;
     // u8 first layer only: image b of the batch is row in_ix[b] of X (the replay ring; conv1_tc.cu reads it through the list)
@@ -111,6 +112,8 @@ void conv_bwd_weight(const Ctx& c, const ConvGeom& g, const float* dY, const voi
 // dX[B][H][W][C] = col2im(dY W) * (mask > 0); `col` is [M][K] scratch
 void conv_bwd_data(const Ctx& c, const ConvGeom& g, const float* dY, const float* W, float* col, float* dX,
                    const float* mask);
+bool dgrad_gather_path(const ConvGeom& g);   // the data gradient of g runs as one gather-form GEMM (needs dg_wt)
+void conv_dgrad_prepare_weights(const Ctx& c, const ConvGeom& g, const float* W);
 
 struct Exchange;
 // torch::optim::Adam / AdamW step over a flat parameter vector (one launch).

@@ -90,7 +90,7 @@ static bool im2col_map(CUtensorMap* out, const float* base, const TmaConv& cv, i
     MapKey k;
     memset(&k, 0, sizeof(k));
     k.p = base; k.v[0] = mn_major ? 250 : 200; k.v[1] = cv.N; k.v[2] = cv.H; k.v[3] = cv.W; k.v[4] = cv.C; k.v[5] = cv.KH; k.v[6] = cv.KW;
-    k.v[7] = cv.S; k.v[8] = pixels;
+    k.v[7] = cv.S; k.v[8] = pixels; k.v[9] = cv.pad;
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = map_cache().find(k);
     if (it != map_cache().end()) { *out = it->second; return true; }
@@ -98,8 +98,9 @@ static bool im2col_map(CUtensorMap* out, const float* base, const TmaConv& cv, i
     if (!enc) return false;
     cuuint64_t gd[4] = {(cuuint64_t)cv.C, (cuuint64_t)cv.W, (cuuint64_t)cv.H, (cuuint64_t)cv.N};
     cuuint64_t gs[3] = {(cuuint64_t)cv.C * 4, (cuuint64_t)cv.W * cv.C * 4, (cuuint64_t)cv.H * cv.W * cv.C * 4};
-    int lower[2] = {0, 0};
-    int upper[2] = {-(cv.KW - 1), -(cv.KH - 1)};
+    // bounding box of the filter bases: [-pad, W + pad - (KW - 1)) -- elements outside the tensor read as zero
+    int lower[2] = {-cv.pad, -cv.pad};
+    int upper[2] = {cv.pad - (cv.KW - 1), cv.pad - (cv.KH - 1)};
     cuuint32_t es[4] = {1, (cuuint32_t)cv.S, (cuuint32_t)cv.S, 1};
     CUtensorMap m;
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gd, gs, lower, upper, 32, (cuuint32_t)pixels, es,
@@ -187,10 +188,10 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
             const TmaConv& cv = *a.a_conv;
             if (cv.C % 32) return false;
             AK = OP_K_IM2COL;
-            const int OH = (cv.H - cv.KH) / cv.S + 1, OW = (cv.W - cv.KW) / cv.S + 1;
+            const int OH = (cv.H + 2 * cv.pad - cv.KH) / cv.S + 1, OW = (cv.W + 2 * cv.pad - cv.KW) / cv.S + 1;
             if (a.M != cv.N * OH * OW || a.K != cv.KH * cv.KW * cv.C) return false;
             if (!im2col_map(&ta, A, cv, 128)) { g_tma_rejects++; return false; }
-            g.ga.ow = OW; g.ga.ohw = OH * OW; g.ga.stride = cv.S; g.ga.kw = cv.KW; g.ga.cblocks = cv.C / 32;
+            g.ga.ow = OW; g.ga.ohw = OH * OW; g.ga.stride = cv.S; g.ga.kw = cv.KW; g.ga.cblocks = cv.C / 32; g.ga.pad = cv.pad;
             if (cv.flip) { g.ga.flip_w = cv.KW - 1; g.ga.flip_h = cv.KH - 1; }
         } else {
             if (a.lda & 3) return false;
@@ -204,7 +205,7 @@ bool tma_gemm(const Ctx& c, GemmMode mode, GemmArgs& a) {
         if (a.a_conv) {
             // transposed im2col matrix: GEMM rows = (kh, kw, c), contraction over filter positions
             const TmaConv& cv = *a.a_conv;
-            if (cv.C % 32) return false;
+            if (cv.C % 32 || cv.pad) return false;
             AK = OP_MN_IM2COL;
             const int OH = (cv.H - cv.KH) / cv.S + 1, OW = (cv.W - cv.KW) / cv.S + 1;
             if (a.K != cv.N * OH * OW || a.M != cv.KH * cv.KW * cv.C) return false;

@@ -57,6 +57,7 @@ struct Im2col {
     int cblocks;         // 32-channel blocks per tap
     int flip_w, flip_h;  // < 0: offset = tap coordinate; >= 0: offset = flip - tap coordinate (transposed convolution)
     int nblocks;         // OP_MN_IM2COL: number of 32-row blocks (taps * cblocks)
+    int pad;             // filter bases start at -pad (padding = the tensor map's out-of-bounds zero fill)
 };
 
 struct Args {
@@ -202,8 +203,8 @@ __device__ __forceinline__ void pixel_of(const Im2col& g, int p, int& n, int& h,
     n = p / g.ohw;
     const int r = p - n * g.ohw;
     const int oh = r / g.ow;
-    h = oh * g.stride;
-    w = (r - oh * g.ow) * g.stride;
+    h = oh * g.stride - g.pad;
+    w = (r - oh * g.ow) * g.stride - g.pad;
 }
 
 }  // namespace tg

@@ -45,6 +45,29 @@ def run_per_trace(normalize, capacity=1000, pushes=1500, rounds=40, batch=64):
     return out
 
 
+def run_uniform_ixs(seed=42):
+    """`ixs[k] = next_u32() % size` (base.rs:384-387) for seed 42 over rings of capacity 32, 10 k, 262,144 and
+    2^20 -- 10^4 draws each, taken as batches WHILE the ring fills (size grows between batches, then the ring wraps).  Stored
+    per capacity: the (size, batch) schedule, the first 8 indices of every batch and a SHA-256 over all draws."""
+    import hashlib
+    out = {"seed": seed, "cases": []}
+    for cap in (32, 10000, 262144, 1 << 20):
+        rng = ro.StdRng(seed)
+        size, drawn, sched, heads, h = 0, 0, [], [], hashlib.sha256()
+        k = 0
+        while drawn < 10000:
+            push = [1, 7, cap // 3 + 1, 5, cap][k % 5]           # grow (and wrap) the ring between batches
+            size = min(cap, size + push)
+            B = [1, 32, 256, 1000, 64][k % 5]
+            B = min(B, 10000 - drawn)
+            ix = np.array([rng.next_u32() % size for _ in range(B)], np.uint64)
+            sched.append([push, size, B]); heads.append(ix[:8].tolist()); h.update(ix.tobytes())
+            drawn += B
+            k += 1
+        out["cases"].append({"capacity": cap, "schedule": sched, "heads": heads, "sha256": h.hexdigest()})
+    return out
+
+
 def dqn_mlp_setup():
     """The fixed DQN-MLP case of the agent fixture: parameters, ring contents and the oracle agent (seeds only)."""
     import torch
@@ -99,5 +122,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, "per_trace_%s.npz" % norm.lower()), **run_per_trace(norm))
 
 
+def write_uniform_ixs():
+    json.dump(run_uniform_ixs(), open(os.path.join(HERE, "uniform_ixs_seed42.json"), "w"))
+
+
 if __name__ == "__main__":
+    write_uniform_ixs()
     main()

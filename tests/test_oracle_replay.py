@@ -178,3 +178,23 @@ def test_per_new_sample_priority_drifts_up():
         leaves.append(t[64 - 1 + n - 1])
     assert all(b >= a for a, b in zip(leaves, leaves[1:]))
     assert abs(r.beta() - 0.4) < 1e-7
+
+
+def test_uniform_ixs_golden_g2_sizes():
+    """the committed index stream of seed 42 over capacities 32 / 10 k / 262,144 / 2^20 (drawn while the ring
+    fills and wraps) is what the C oracle's StdRng produces -- the Python and C restatements agree with the fixture."""
+    import ctypes
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "uniform_ixs_seed42.json")))
+    assert [c["capacity"] for c in gold["cases"]] == [32, 10000, 262144, 1 << 20]
+    for case in gold["cases"]:
+        rng = ro.StdRng(gold["seed"])
+        h = hashlib.sha256()
+        n = 0
+        for (push, size, B), head in zip(case["schedule"], case["heads"]):
+            ix = np.array([rng.next_u32() % size for _ in range(B)], np.uint64)
+            assert ix[:8].tolist() == head
+            h.update(ix.tobytes())
+            n += B
+        assert n == 10000 and h.hexdigest() == case["sha256"]

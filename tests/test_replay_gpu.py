@@ -92,6 +92,36 @@ def test_uniform_indices_10k_draws_seed42_golden():
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("case_ix", [0, 1, 2, 3])
+def test_uniform_ixs_golden_g2_sizes_on_device(case_ix):
+    """SURVEY 8c G2 on the device: 10^4 draws of seed 42 over capacities 32 / 10 k / 262,144 / 2^20 while the ring fills and
+    wraps -- every batch's indices equal the committed fixture (heads) and the SHA-256 over all draws matches."""
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(GOLD, "uniform_ixs_seed42.json")))
+    case = gold["cases"][case_ix]
+    cap = case["capacity"]
+    dev = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=cap, seed=gold["seed"]))
+    dev.allocate((2,), np.float32, (1,), np.int64)
+    h = hashlib.sha256()
+    row = 0
+    for (push, size, B), head in zip(case["schedule"], case["heads"]):
+        obs = np.arange(row, row + push, dtype=np.float32)[:, None].repeat(2, 1)
+        dev.push(GenericTransitionBatch(obs, np.zeros((push, 1), np.int64), obs, np.zeros(push, np.float32),
+                                        np.zeros(push, np.int8), np.zeros(push, np.int8)))
+        row += push
+        assert dev.len() == size
+        b = dev.batch(B)
+        assert b.ix_sample[:8].tolist() == head
+        # the gathered row is the ring row the index names: row r holds the value of the LAST push that landed on r
+        pos = b.ix_sample.astype(np.int64)
+        newest = row - 1 - ((row - 1 - pos) % cap)
+        assert np.array_equal(b.obs[:, 0], newest.astype(np.float32))
+        h.update(np.ascontiguousarray(b.ix_sample, np.uint64).tobytes())
+    assert h.hexdigest() == case["sha256"]
+    dev.close()
+
+
 def test_empty_buffer_and_zero_push():
     dev, _ = _pair(10, 1, (3,), np.float32, (1,), np.int64)
     dev.allocate((3,), np.float32, (1,), np.int64)
