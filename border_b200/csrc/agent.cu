@@ -83,6 +83,10 @@ Agent::~Agent() {
     if (comm_ctx.stream) { cudaStreamSynchronize(comm_ctx.stream); cudaStreamDestroy(comm_ctx.stream); }
     if (comm_ctx.ev) cudaEventDestroy(comm_ctx.ev);
     cudaFree(xchg_ctr);
+    cudaFree(d_actor_obs[0]); cudaFree(d_actor_obs[1]); cudaFree(d_actor_act);
+    if (h_actor_stage) cudaFreeHost(h_actor_stage);
+    if (h_actor_act) cudaFreeHost(h_actor_act);
+    if (ev_actor) cudaEventDestroy(ev_actor);
     for (int i = 0; i < 2; ++i) {
         if (side_ctx[i].stream) { cudaStreamSynchronize(side_ctx[i].stream); cudaStreamDestroy(side_ctx[i].stream); }
         side_ctx[i].free_scratch();
@@ -100,9 +104,94 @@ Model* Agent::model(const std::string& name) {
     throw Error("no such model (VarStore): " + name);
 }
 void Agent::inject_noise(int, const float*, size_t) { throw Error("this agent takes no injected noise"); }
+// Explorer in the tail of the policy forward (dqn/explorer.rs:29-31,68-90, iqn/explorer.rs:78-97; eval: dqn/base.rs:229-236).  The fastrand draws
+// are made on the host in the reference's order and arrive as (mode, forced, u): 0 = argmax Q, 1 = the random action
+// `forced`, 2 = softmax(Q).multinomial(1) by inverse CDF on u.  The action goes to device memory (the next push reads it)
+// and to pinned host memory (the env reads it).
+struct SelectParams { const float* q; int A; int mode; long long forced; double u; long long* act_dev; long long* act_host; };
+__global__ void actor_select_kernel(SelectParams s) {
+    if (threadIdx.x != 0) return;
+    long long a = 0;
+    if (s.mode == 1) {
+        a = s.forced;
+    } else if (s.mode == 0) {
+        int best = 0;
+        for (int j = 1; j < s.A; ++j)
+            if (s.q[j] > s.q[best]) best = j;
+        a = best;
+    } else {
+        float mx = s.q[0];
+        for (int j = 1; j < s.A; ++j) mx = fmaxf(mx, s.q[j]);
+        double z = 0;
+        for (int j = 0; j < s.A; ++j) z += exp((double)(s.q[j] - mx));
+        const double u = s.u * z;
+        double acc = 0;
+        int pick = s.A - 1;
+        for (int j = 0; j < s.A; ++j) {
+            acc += exp((double)(s.q[j] - mx));
+            if (u < acc) { pick = j; break; }
+        }
+        a = pick;
+    }
+    *s.act_dev = a;
+    *reinterpret_cast<volatile long long*>(s.act_host) = a;
+}
+
 void Agent::grad_buffer(void** p, uint64_t* n) { *p = nullptr; *n = 0; }
-void Agent::actor_step(Replay&, const void*, const void*, float, int8_t, int8_t, int64_t*, bool) {
-    BB_CHECK(false, "bb_actor_step: this agent has no device-side actor path (DQN only)");
+// bb_actor_step (border_b200.h): Sampler::sample_and_push with device-resident observations
+void Agent::actor_step(Replay& rb, const void* obs, const void* reset_obs, float reward, int8_t term, int8_t trunc,
+                       int64_t* act_out, bool obs_on_device) {
+    DeviceGuard g(device);
+    const size_t row = actor_obs_row_bytes();
+    BB_CHECK(row > 0, "bb_actor_step: this agent has no device-side actor path (discrete-action agents only: DQN, IQN)");
+    BB_CHECK(rb.obs_row_bytes == row && rb.cfg.act_kind == BB_I64 && rb.cfg.act_elems == 1,
+             "bb_actor_step: the replay rows do not match the network (obs row) / a scalar i64 action");
+    if (!d_actor_act) {
+        actor_row_pad = (row + 15) / 16 * 16;
+        for (int k = 0; k < 2; ++k) d_actor_obs[k] = dev_alloc<uint8_t>(actor_row_pad + 16);
+        d_actor_act = dev_alloc_zero<long long>(2);
+        BB_CUDA(cudaMallocHost(&h_actor_stage, 2 * (actor_row_pad + 16)));
+        BB_CUDA(cudaMallocHost(&h_actor_act, 16));
+        BB_CUDA(cudaEventCreateWithFlags(&ev_actor, cudaEventDisableTiming));
+    }
+    // the transition's next_obs (+ reward / flags behind it) -> the slot that is not the previous observation
+    const int cur = actor_prev ^ 1;
+    uint8_t* h = h_actor_stage;
+    memcpy(h + actor_row_pad, &reward, 4);
+    h[actor_row_pad + 4] = (uint8_t)term; h[actor_row_pad + 5] = (uint8_t)trunc;
+    if (obs_on_device) {   // e.g. the frame stack bb_atari_step left in HBM: only reward + flags cross PCIe
+        BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], obs, row, cudaMemcpyDeviceToDevice, ctx.stream));
+        BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur] + actor_row_pad, h + actor_row_pad, 16, cudaMemcpyHostToDevice, ctx.stream));
+    } else {
+        memcpy(h, obs, row);
+        BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], h, actor_row_pad + 16, cudaMemcpyHostToDevice, ctx.stream));
+    }
+    if (actor_has_prev) {
+        if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
+        const uint8_t* m = d_actor_obs[cur] + actor_row_pad;
+        rb.push(d_actor_obs[actor_prev], d_actor_act, d_actor_obs[cur], (const float*)m, (const int8_t*)(m + 4),
+                (const int8_t*)(m + 5), 1, true);
+        if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
+    }
+    int act_src = cur;
+    if (reset_obs) {   // the episode ended: the next action is for the reset observation (sampler.rs:128-137)
+        uint8_t* h2 = h_actor_stage + actor_row_pad + 16;
+        if (!obs_on_device) memcpy(h2, reset_obs, row);
+        BB_CUDA(cudaMemcpyAsync(d_actor_obs[actor_prev], obs_on_device ? reset_obs : h2, row,   // after the push read it
+                                obs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
+        act_src = actor_prev;
+    }
+    const float* q = actor_q(d_actor_obs[act_src]);
+    const ActorPick k = actor_pick();
+    SelectParams sp{q, actor_n_actions(), k.mode, k.forced, k.u, d_actor_act, h_actor_act};
+    actor_select_kernel<<<1, 32, 0, ctx.stream>>>(sp);
+    BB_LAUNCHED();
+    ctx.phase = "policy"; ctx.layer = "explorer"; ctx.mark("actor_select");
+    BB_CUDA(cudaEventRecord(ev_actor, ctx.stream));
+    BB_CUDA(cudaEventSynchronize(ev_actor));
+    *act_out = (int64_t)h_actor_act[0];
+    actor_prev = act_src;
+    actor_has_prev = true;
 }
 
 // Cross-GPU barrier on flags in peer memory: rank r writes its epoch into slot r of every peer's

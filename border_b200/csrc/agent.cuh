@@ -119,9 +119,25 @@ struct Agent {
     virtual void sample(const void* obs, size_t n, void* act_out) = 0;
     // Sampler::sample_and_push (border-core/src/trainer/sampler.rs:99-144) with the observation crossing PCIe once:
     // see bb_actor_step in border_b200.h.  Discrete-action agents only.
-    virtual void actor_step(Replay& rb, const void* obs, const void* reset_obs, float reward, int8_t term, int8_t trunc,
-                            int64_t* act_out, bool obs_on_device = false);
-    virtual void actor_reset() {}
+    // The generic loop is Agent::actor_step; a discrete-action agent supplies its observation row size, action count, the
+    // policy forward for one device-resident observation and the explorer's host-side draws.
+    struct ActorPick { int mode = 0; long long forced = 0; double u = 0.0; };   // 0 argmax, 1 forced action, 2 softmax on u
+    virtual size_t actor_obs_row_bytes() const { return 0; }                     // 0 = no device-side actor path
+    virtual int actor_n_actions() const { return 0; }
+    virtual const float* actor_q(const uint8_t* d_obs) { (void)d_obs; return nullptr; }
+    virtual ActorPick actor_pick() { return ActorPick{}; }
+    void actor_step(Replay& rb, const void* obs, const void* reset_obs, float reward, int8_t term, int8_t trunc,
+                    int64_t* act_out, bool obs_on_device = false);
+    void actor_reset() { actor_has_prev = false; }
+    // the last two observations and the last action stay on the device
+    uint8_t* d_actor_obs[2] = {nullptr, nullptr};
+    uint8_t* h_actor_stage = nullptr;   // pinned: [obs row | reward, term, trunc] x 2 (transition obs, reset obs)
+    long long* d_actor_act = nullptr;
+    long long* h_actor_act = nullptr;   // pinned, written by the explorer kernel
+    size_t actor_row_pad = 0;
+    int actor_prev = 0;
+    bool actor_has_prev = false;
+    cudaEvent_t ev_actor = nullptr;
     virtual Model* sync_model_src() = 0;  // which VarStore SyncModel ships (DQN qnet, SAC pi)
     virtual void inject_noise(int slot, const float* host, size_t n);
     virtual void precision_changed() {}   // drop captured graphs (they hold the GEMM kernels of the previous precision mode)

@@ -107,39 +107,6 @@ __global__ void __launch_bounds__(1024) dqn_loss_kernel(DqnLossParams p) {
     }
 }
 
-// Explorer in the tail of the policy forward (dqn/explorer.rs:29-31,68-90; eval: dqn/base.rs:229-236).  The fastrand draws
-// are made on the host in the reference's order and arrive as (mode, forced, u): 0 = argmax Q, 1 = the random action
-// `forced`, 2 = softmax(Q).multinomial(1) by inverse CDF on u.  The action goes to device memory (the next push reads it)
-// and to pinned host memory (the env reads it).
-struct SelectParams { const float* q; int A; int mode; long long forced; double u; long long* act_dev; long long* act_host; };
-__global__ void dqn_select_kernel(SelectParams s) {
-    if (threadIdx.x != 0) return;
-    long long a = 0;
-    if (s.mode == 1) {
-        a = s.forced;
-    } else if (s.mode == 0) {
-        int best = 0;
-        for (int j = 1; j < s.A; ++j)
-            if (s.q[j] > s.q[best]) best = j;
-        a = best;
-    } else {
-        float mx = s.q[0];
-        for (int j = 1; j < s.A; ++j) mx = fmaxf(mx, s.q[j]);
-        double z = 0;
-        for (int j = 0; j < s.A; ++j) z += exp((double)(s.q[j] - mx));
-        const double u = s.u * z;
-        double acc = 0;
-        int pick = s.A - 1;
-        for (int j = 0; j < s.A; ++j) {
-            acc += exp((double)(s.q[j] - mx));
-            if (u < acc) { pick = j; break; }
-        }
-        a = pick;
-    }
-    *s.act_dev = a;
-    *reinterpret_cast<volatile long long*>(s.act_host) = a;
-}
-
 struct Dqn : Agent {
     bb_dqn_cfg cfg;
     Net net;
@@ -170,16 +137,7 @@ struct Dqn : Agent {
     uint8_t* d_obs_in = nullptr;  // policy input staging
     uint8_t* h_obs_in = nullptr;
     float* h_q = nullptr;
-    // device-side actor path (actor_step): the last two observations stay on the device, the action too
-    uint8_t* d_actor_obs[2] = {nullptr, nullptr};
-    uint8_t* h_actor_stage = nullptr;   // pinned: [obs row | reward, term, trunc] x 2 (transition obs, reset obs)
-    long long* d_actor_act = nullptr;
-    long long* h_actor_act = nullptr;   // pinned, written by the explorer kernel
-    size_t actor_row_pad = 0;
-    int actor_prev = 0;
-    bool actor_has_prev = false;
-    NetWorkspace ws_actor;
-    cudaEvent_t ev_actor = nullptr;
+    NetWorkspace ws_actor;   // policy forward of the device-side actor path (Agent::actor_step)
     size_t obs_in_cap = 0;
 
     explicit Dqn(const bb_dqn_cfg& c) : cfg(c), fr(c.explorer_seed) {
@@ -215,10 +173,6 @@ struct Dqn : Agent {
         cudaFree(d_td); cudaFree(d_out); cudaFree(d_obs_in);
         if (h_obs_in) cudaFreeHost(h_obs_in);
         if (h_q) cudaFreeHost(h_q);
-        cudaFree(d_actor_obs[0]); cudaFree(d_actor_obs[1]); cudaFree(d_actor_act);
-        if (h_actor_stage) cudaFreeHost(h_actor_stage);
-        if (h_actor_act) cudaFreeHost(h_actor_act);
-        if (ev_actor) cudaEventDestroy(ev_actor);
         ws_actor.release();
     }
     Model* sync_model_src() override { return &qnet; }
@@ -414,54 +368,18 @@ struct Dqn : Agent {
         if (rec) rec->n_opts = n_opts;
     }
 
-    void actor_reset() override { actor_has_prev = false; }
-
-    // bb_actor_step (border_b200.h): Sampler::sample_and_push with device-resident observations
-    void actor_step(Replay& rb, const void* obs, const void* reset_obs, float reward, int8_t term, int8_t trunc,
-                    int64_t* act_out, bool obs_on_device) override {
-        DeviceGuard g(device);
-        const size_t row = (size_t)net.in_elems * (net.u8_input ? 1 : 4);
-        BB_CHECK(rb.obs_row_bytes == row && rb.cfg.act_kind == BB_I64 && rb.cfg.act_elems == 1,
-                 "bb_actor_step: the replay rows do not match the Q network (obs row) / a scalar i64 action");
-        if (!d_actor_act) {
-            actor_row_pad = (row + 15) / 16 * 16;
-            for (int k = 0; k < 2; ++k) d_actor_obs[k] = dev_alloc<uint8_t>(actor_row_pad + 16);
-            d_actor_act = dev_alloc_zero<long long>(2);
-            BB_CUDA(cudaMallocHost(&h_actor_stage, 2 * (actor_row_pad + 16)));
-            BB_CUDA(cudaMallocHost(&h_actor_act, 16));
-            BB_CUDA(cudaEventCreateWithFlags(&ev_actor, cudaEventDisableTiming));
-            net.alloc_workspace(ws_actor, 1, false);
-        }
-        // the transition's next_obs (+ reward / flags behind it) -> the slot that is not the previous observation
-        const int cur = actor_prev ^ 1;
-        uint8_t* h = h_actor_stage;
-        memcpy(h + actor_row_pad, &reward, 4);
-        h[actor_row_pad + 4] = (uint8_t)term; h[actor_row_pad + 5] = (uint8_t)trunc;
-        if (obs_on_device) {   // e.g. the frame stack bb_atari_step left in HBM: only reward + flags cross PCIe
-            BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], obs, row, cudaMemcpyDeviceToDevice, ctx.stream));
-            BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur] + actor_row_pad, h + actor_row_pad, 16, cudaMemcpyHostToDevice, ctx.stream));
-        } else {
-            memcpy(h, obs, row);
-            BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], h, actor_row_pad + 16, cudaMemcpyHostToDevice, ctx.stream));
-        }
-        if (actor_has_prev) {
-            if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
-            const uint8_t* m = d_actor_obs[cur] + actor_row_pad;
-            rb.push(d_actor_obs[actor_prev], d_actor_act, d_actor_obs[cur], (const float*)m, (const int8_t*)(m + 4),
-                    (const int8_t*)(m + 5), 1, true);
-            if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
-        }
-        int act_src = cur;
-        if (reset_obs) {   // the episode ended: the next action is for the reset observation (sampler.rs:128-137)
-            uint8_t* h2 = h_actor_stage + actor_row_pad + 16;
-            if (!obs_on_device) memcpy(h2, reset_obs, row);
-            BB_CUDA(cudaMemcpyAsync(d_actor_obs[actor_prev], obs_on_device ? reset_obs : h2, row,   // after the push read it
-                                    obs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
-            act_src = actor_prev;
-        }
-        const float* q = net.forward_small(ctx, qnet.p, d_actor_obs[act_src], net.in_elems, 1, ws_actor);
-        if (!q) q = net.forward(ctx, qnet.p, d_actor_obs[act_src], net.in_elems, 1, ws_actor);
-        SelectParams sp{q, net.out_dim, 0, 0, 0.0, d_actor_act, h_actor_act};
+    // ---- device-side actor path (Agent::actor_step): the agent-specific pieces
+    size_t actor_obs_row_bytes() const override { return (size_t)net.in_elems * (net.u8_input ? 1 : 4); }
+    int actor_n_actions() const override { return net.out_dim; }
+    const float* actor_q(const uint8_t* d_obs) override {   // Q(obs) for one observation already in HBM
+        if (ws_actor.max_batch < 1) net.alloc_workspace(ws_actor, 1, false);
+        const float* q = net.forward_small(ctx, qnet.p, d_obs, net.in_elems, 1, ws_actor);
+        if (!q) q = net.forward(ctx, qnet.p, d_obs, net.in_elems, 1, ws_actor);
+        return q;
+    }
+    // the explorer's fastrand draws, on the host and in the reference's order (dqn/explorer.rs:29-31,68-90; eval: base.rs:229-236)
+    ActorPick actor_pick() override {
+        ActorPick k;
         const int A = net.out_dim;
         if (train) {
             if (cfg.explorer == BB_EXPLORER_EPS_GREEDY) {
@@ -469,21 +387,14 @@ struct Dqn : Agent {
                 double eps = std::max(cfg.eps_start - d * (double)eps_n_opts, cfg.eps_final);
                 const bool is_random = fr.f64() < eps;
                 eps_n_opts += 1;
-                if (is_random) { sp.mode = 1; sp.forced = (long long)fr.u32_below((uint32_t)A); }
+                if (is_random) { k.mode = 1; k.forced = (long long)fr.u32_below((uint32_t)A); }
             } else {
-                sp.mode = 2; sp.u = fr.f64();
+                k.mode = 2; k.u = fr.f64();
             }
         } else if (fr.f32() < 0.01f) {
-            sp.mode = 1; sp.forced = (long long)fr.u64_below((uint64_t)A);
+            k.mode = 1; k.forced = (long long)fr.u64_below((uint64_t)A);
         }
-        dqn_select_kernel<<<1, 32, 0, ctx.stream>>>(sp);
-        BB_LAUNCHED();
-        ctx.phase = "policy"; ctx.layer = "explorer"; ctx.mark("dqn_select");
-        BB_CUDA(cudaEventRecord(ev_actor, ctx.stream));
-        BB_CUDA(cudaEventSynchronize(ev_actor));
-        *act_out = (int64_t)h_actor_act[0];
-        actor_prev = act_src;
-        actor_has_prev = true;
+        return k;
     }
 
     // Policy::sample, dqn/base.rs:211-241

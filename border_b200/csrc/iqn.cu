@@ -207,7 +207,7 @@ struct Iqn : Agent {
     Model iqn, iqn_tgt;
     IqnWs ws_online, ws_tgt, ws_act;
     int F, E, A;
-    float *d_loss_part = nullptr, *d_out = nullptr, *d_qmean = nullptr;
+    float *d_loss_part = nullptr, *d_out = nullptr, *d_qmean = nullptr, *d_qmean_actor = nullptr;
     float* d_inject[2] = {nullptr, nullptr};
     size_t inject_n[2] = {0, 0};
     uint64_t tau_ctr = 0, soft_update_counter = 0, eps_n_opts = 0;
@@ -268,7 +268,7 @@ struct Iqn : Agent {
         ws_online.release(); ws_tgt.release(); ws_act.release();
         iqn.release(); iqn_tgt.release();
         f_net.free_tables();
-        cudaFree(d_loss_part); cudaFree(d_out); cudaFree(d_qmean); cudaFree(d_inject[0]); cudaFree(d_inject[1]);
+        cudaFree(d_loss_part); cudaFree(d_out); cudaFree(d_qmean); cudaFree(d_qmean_actor); cudaFree(d_inject[0]); cudaFree(d_inject[1]);
         cudaFree(d_obs_in);
         if (h_obs_in) cudaFreeHost(h_obs_in);
         if (h_q) cudaFreeHost(h_q);
@@ -408,6 +408,30 @@ struct Iqn : Agent {
     }
 
     // Policy::sample (iqn/base.rs:204-228)
+    // ---- device-side actor path (Agent::actor_step): quantile mean on the device, explorer draws on the host
+    size_t actor_obs_row_bytes() const override { return (size_t)f_net.in_elems * (f_net.u8_input ? 1 : 4); }
+    int actor_n_actions() const override { return A; }
+    const float* actor_q(const uint8_t* d_obs) override {
+        const int N = n_percent_points(cfg.sample_percents_act, true);
+        ensure(ws_act, 1, N, false);
+        if (!d_qmean_actor) d_qmean_actor = dev_alloc<float>(A);
+        const float* z = forward(iqn, d_obs, 1, N, cfg.sample_percents_act, -1, ws_act);
+        iqn_mean_kernel<<<(A + 127) / 128, 128, 0, ctx.stream>>>(z, d_qmean_actor, 1, N, A);
+        BB_LAUNCHED();
+        return d_qmean_actor;
+    }
+    ActorPick actor_pick() override {   // IqnExplorer::EpsilonGreedy::action (iqn/explorer.rs:78-97); eval: argmax
+        ActorPick k;
+        if (train) {
+            double d = (cfg.eps_start - cfg.eps_final) / (double)cfg.final_step;
+            double eps = std::max(cfg.eps_start - d * (double)eps_n_opts, cfg.eps_final);
+            const bool is_random = fr.f64() < eps;
+            eps_n_opts += 1;
+            if (is_random) { k.mode = 1; k.forced = (long long)fr.u32_below((uint32_t)A); }
+        }
+        return k;
+    }
+
     void sample(const void* obs, size_t n, void* act_out) override {
         DeviceGuard g(device);
         BB_CHECK(n >= 1 && n <= 1024, "sample: n out of range");

@@ -15,7 +15,12 @@ from border_b200.replay import GenericTransitionBatch, SimpleReplayBuffer, Simpl
 
 def _walk(kind, explorer, train, steps=60, ep_len=7):
     rng = np.random.default_rng(5)
-    if kind == "cnn":
+    if kind == "iqn":
+        from border_b200.agents import Iqn, IqnConfig
+        shape, dtype, n_act = (4, 84, 84), np.uint8, 4
+        frames = rng.integers(0, 256, (steps + 2,) + shape, dtype=np.uint8)
+        resets = rng.integers(0, 256, (steps + 2,) + shape, dtype=np.uint8)
+    elif kind == "cnn":
         qcfg, shape, dtype, n_act = AtariCnnConfig(4, 6), (4, 84, 84), np.uint8, 6
         frames = rng.integers(0, 256, (steps + 2,) + shape, dtype=np.uint8)
         resets = rng.integers(0, 256, (steps + 2,) + shape, dtype=np.uint8)
@@ -27,6 +32,12 @@ def _walk(kind, explorer, train, steps=60, ep_len=7):
 
     def make():
         rb = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=64, seed=1))
+        if kind == "iqn":
+            ag = Iqn.build(IqnConfig(f_config=AtariCnnConfig(n_stack=4, out_dim=0, skip_linear=True),
+                                     m_config=MlpConfig(3136, [512], n_act), opt_config=OptimizerConfig(lr=1e-4), feature_dim=3136,
+                                     embed_dim=64, batch_size=8, train=train, sample_percents_act="Uniform32", explorer=explorer,
+                                     device=0, init_seed=3, explorer_seed=77))
+            return rb, ag
         ag = Dqn.build(DqnConfig(model_config=DqnModelConfig(q_config=qcfg, opt_config=OptimizerConfig(lr=1e-3)), batch_size=8,
                                  train=train, explorer=explorer, device=0, init_seed=3, explorer_seed=77))
         return rb, ag
@@ -69,6 +80,14 @@ def test_actor_step_softmax_and_eval_mlp():
     from border_b200.agents import Softmax
     _walk("mlp", Softmax(), True)
     _walk("mlp", EpsilonGreedy(), False)   # eval mode: 1 % random actions, argmax otherwise
+
+
+def test_actor_step_iqn_matches_sample_and_push():
+    """IQN: quantile mean + IqnExplorer::EpsilonGreedy (iqn/explorer.rs:78-97) through the same device path; the tau draws
+    of the acting forward (Uniform32) advance identically on both paths."""
+    acts = _walk("iqn", EpsilonGreedy(eps_start=0.4, eps_final=0.1, final_step=30), True, steps=24, ep_len=5)
+    assert len(set(acts)) > 1
+    _walk("iqn", EpsilonGreedy(), False, steps=10, ep_len=4)
 
 
 def test_actor_step_rejects_sac():
