@@ -195,7 +195,7 @@ struct Sac : Agent {
     NetWorkspace ws_qt;
     int ws_batch = 0;
     float *d_a = nullptr, *d_a_next = nullptr, *d_logp = nullptr, *d_logp_next = nullptr, *d_z = nullptr,
-          *d_xa = nullptr, *d_xa2 = nullptr, *d_dxa = nullptr, *d_qt = nullptr, *d_out = nullptr;
+          *d_xa = nullptr, *d_xa2 = nullptr, *d_xa_c = nullptr, *d_dxa = nullptr, *d_qt = nullptr, *d_out = nullptr;
     float* d_inject[2] = {nullptr, nullptr};
     size_t inject_n[2] = {0, 0};
     uint64_t noise_ctr = 0;
@@ -272,7 +272,7 @@ struct Sac : Agent {
         pi.release(); ent.release();
         for (auto& q : qnets) q.release();
         for (auto& q : qnets_tgt) q.release();
-        cudaFree(d_a); cudaFree(d_a_next); cudaFree(d_logp); cudaFree(d_logp_next); cudaFree(d_z); cudaFree(d_xa);
+        cudaFree(d_a); cudaFree(d_a_next); cudaFree(d_logp); cudaFree(d_logp_next); cudaFree(d_z); cudaFree(d_xa); cudaFree(d_xa_c);
         cudaFree(d_xa2); cudaFree(d_dxa); cudaFree(d_qt); cudaFree(d_out); cudaFree(d_inject[0]);
         cudaFree(d_inject[1]); cudaFree(d_in);
         if (h_in) cudaFreeHost(h_in);
@@ -304,7 +304,7 @@ struct Sac : Agent {
         q_net.alloc_workspace(ws_qt, B, false);
         for (float** p : {&d_a, &d_a_next, &d_z}) { cudaFree(*p); *p = dev_alloc<float>((size_t)B * act_dim); }
         for (float** p : {&d_logp, &d_logp_next}) { cudaFree(*p); *p = dev_alloc<float>(B); }
-        for (float** p : {&d_xa, &d_xa2}) { cudaFree(*p); *p = dev_alloc<float>((size_t)B * (obs_dim + act_dim)); }
+        for (float** p : {&d_xa, &d_xa2, &d_xa_c}) { cudaFree(*p); *p = dev_alloc<float>((size_t)B * (obs_dim + act_dim)); }
         cudaFree(d_dxa); d_dxa = dev_alloc<float>((size_t)n_critics * B * (obs_dim + act_dim));
         cudaFree(d_qt); d_qt = dev_alloc<float>((size_t)n_critics * B);
         ws_batch = B;
@@ -377,6 +377,20 @@ struct Sac : Agent {
         const float* next_obs = (const float*)bv.next_obs;
         const int D = obs_dim + act_dim;
 
+        // The critics' forward on the replayed actions (first half of update_critic, sac/base.rs:107-118) does not depend on
+        // the actor update -- the critics' parameters only change at the end of the step -- so it runs beside it on a side
+        // stream, into its own [obs, act] buffer.
+        const bool conc = ctx.concurrent();
+        const Ctx& cctx = conc ? *ctx.side[0] : ctx;
+        auto critic_forward = [&]() {
+            cctx.phase = "critic";
+            concat2_kernel<<<(B * D + 255) / 256, 256, 0, cctx.stream>>>(obs, obs_dim, (const float*)bv.act, act_dim, d_xa_c, B);
+            BB_LAUNCHED();
+            cctx.layer = "cat"; cctx.mark("concat");
+            for (int i = 0; i < n_critics; ++i) q_net.forward(cctx, qnets[i].p, d_xa_c, D, B, ws_qc[i]);
+        };
+        if (conc) { ctx.fork_to(cctx); critic_forward(); }
+
         // ---------------- update_actor (sac/base.rs:151-167)
         ctx.phase = "actor";
         action_logp(obs, B, ws_pi, 0, d_a, d_logp, d_z, d_xa);
@@ -406,10 +420,7 @@ struct Sac : Agent {
 
         // ---------------- update_critic (sac/base.rs:107-149)
         ctx.phase = "critic";
-        concat2_kernel<<<(B * D + 255) / 256, 256, 0, ctx.stream>>>(obs, obs_dim, (const float*)bv.act, act_dim, d_xa, B);
-        BB_LAUNCHED();
-        ctx.layer = "cat"; ctx.mark("concat");
-        for (int i = 0; i < n_critics; ++i) q_net.forward(ctx, qnets[i].p, d_xa, D, B, ws_qc[i]);
+        if (!conc) critic_forward();
         action_logp(next_obs, B, ws_pi_next, 1, d_a_next, d_logp_next, nullptr, d_xa2);  // with the updated pi
         QPtrs tq{};
         for (int i = 0; i < n_critics; ++i) {
@@ -417,13 +428,14 @@ struct Sac : Agent {
             BB_CUDA(cudaMemcpyAsync(d_qt + (size_t)i * B, q, (size_t)B * 4, cudaMemcpyDeviceToDevice, ctx.stream));
             tq.q[i] = d_qt + (size_t)i * B;
         }
+        if (conc) ctx.join_from(cctx);
         sac_critic_loss_kernel<<<1, 1024, 0, ctx.stream>>>(qptrs(ws_qc), tq, n_critics, d_logp_next, bv.reward,
                                                           bv.is_terminated, ent.p, B, (float)cfg.gamma,
                                                           (float)cfg.reward_scale, cfg.critic_loss, d_out);
         BB_LAUNCHED();
         ctx.layer = "loss"; ctx.mark("sac_critic_loss");
         for (int i = 0; i < n_critics; ++i) {  // separate Adam per critic (sac/base.rs:137-139)
-            q_net.backward(ctx, qnets[i].p, qnets[i].g, d_xa, D, B, ws_qc[i], nullptr, 0);
+            q_net.backward(ctx, qnets[i].p, qnets[i].g, d_xa_c, D, B, ws_qc[i], nullptr, 0);
             adam_step(ctx, qnets[i].p, qnets[i].g, qnets[i].m, qnets[i].v, qnets[i].n, qnets[i].hyper, qnets[i].step, nullptr, 1,
                       nullptr, nullptr, 0, &d_sc->q[i]);
         }

@@ -113,6 +113,109 @@ def run_dqn_mlp_trace(steps=5, B=32, lr=1e-3):
     return out
 
 
+def _digest(prefix, params, out):
+    """Compact, order-free summary of a parameter dict: sum, sum of |x| (float64) and the first 32 values of every tensor."""
+    for k, v in params.items():
+        a = v.detach().numpy().astype(np.float64).ravel()
+        out["%s.%s.sum" % (prefix, k)] = np.array([a.sum(), np.abs(a).sum()])
+        out["%s.%s.head" % (prefix, k)] = a[:32].astype(np.float32)
+
+
+def sac_setup(n_critics=2, units=(64, 64), seed=0, obs_dim=17, act_dim=8):
+    """SURVEY 8c G7 set-up (oracle side only): parameters, ring contents."""
+    import torch
+    from oracle import agent_oracle as ao
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator().manual_seed(seed)
+    n = 580
+    obs = rng.standard_normal((n, obs_dim)).astype(np.float32)
+    tr = (obs, rng.uniform(-1, 1, (n, act_dim)).astype(np.float32), rng.standard_normal((n, obs_dim)).astype(np.float32),
+          rng.standard_normal(n).astype(np.float32), (rng.random(n) < 0.1).astype(np.int8), np.zeros(n, np.int8))
+    pi_p = ao.mlp2_params(obs_dim, list(units), act_dim, gen)
+    q_ps = [ao.mlp_params(obs_dim + act_dim, list(units), 1, gen) for _ in range(n_critics)]
+    return rng, tr, pi_p, q_ps
+
+
+def run_sac_trace(steps=3, B=64, lr=3e-4):
+    """G7 (+ G5 at tau = 0.005): SAC (sac/base.rs:107-198) with two critics, EntCoefMode::Auto(-8, 3e-4), reward_scale 1.5,
+    injected z / z' (the double-exp std quirk is in the oracle's action_logp): losses, alpha, injected noise and parameter
+    digests of pi, both critics, both targets and log_alpha after `steps` updates."""
+    import torch
+    from oracle import agent_oracle as ao
+    rng, tr, pi_p, q_ps = sac_setup()
+    cap = 600
+    orc = ro.ReplayOracle(cap, 42, (17,), np.float32, (8,), np.float32)
+    orc.push(*tr)
+    mode = ("Auto", -8.0, 3e-4)
+    oracle = ao.SacOracle(pi_p, q_ps, 2, 3, lr, lr, B, 0.99, 0.005, mode, reward_scale=1.5, critic_loss="Mse")
+    out = {"z1": [], "z2": [], "loss_critic": [], "loss_actor": [], "ent_coef": []}
+    for _ in range(steps):
+        z1 = rng.standard_normal((B, 8)).astype(np.float32)
+        z2 = rng.standard_normal((B, 8)).astype(np.float32)
+        b = orc.batch(B)
+        tb = dict(obs=torch.from_numpy(b["obs"]), act=torch.from_numpy(b["act"]), next_obs=torch.from_numpy(b["next_obs"]),
+                  reward=torch.from_numpy(b["reward"]), is_terminated=torch.from_numpy(b["is_terminated"]))
+        ref = oracle.opt_(tb, torch.from_numpy(z1), torch.from_numpy(z2))
+        out["z1"].append(z1); out["z2"].append(z2)
+        for k in ("loss_critic", "loss_actor", "ent_coef"):
+            out[k].append(float(ref[k]))
+    out = {k: np.asarray(v) for k, v in out.items()}
+    _digest("pi", oracle.pi, out)
+    for i in range(2):
+        _digest("qnet_%d" % i, oracle.qnets[i], out)
+        _digest("qnet_tgt_%d" % i, oracle.qnets_tgt[i], out)
+    out["log_alpha"] = oracle.log_alpha.detach().numpy().copy()
+    return out
+
+
+def iqn_setup(n_act=4):
+    """SURVEY 8c G6 set-up (oracle side only): AtariCnn.skip_linear features, merge Mlp(3136 -> 512 -> A)."""
+    import torch
+    from oracle import agent_oracle as ao
+    rng = np.random.default_rng(11)
+    gen = torch.Generator().manual_seed(3)
+    f_params = ao.atari_cnn_params(4, 0, gen, skip_linear=True)
+    m_params = ao.mlp_params(3136, [512], n_act, gen)
+    params = ao.iqn_params(f_params, 3136, 64, m_params, gen)
+    n = 180
+    obs = rng.integers(0, 256, (n, 4, 84, 84), dtype=np.uint8)
+    nxt = rng.integers(0, 256, (n, 4, 84, 84), dtype=np.uint8)
+    tr = (obs, rng.integers(0, n_act, (n, 1)).astype(np.int64), nxt, rng.standard_normal(n).astype(np.float32),
+          (rng.random(n) < 0.2).astype(np.int8), np.zeros(n, np.int8))
+    return rng, tr, params
+
+
+def run_iqn_trace(steps=2, B=16, N=8, lr=1e-4):
+    """G6: IQN update (iqn/base.rs:63-170) with injected tau / tau' [B][N]: losses, the injected percent points and parameter
+    digests of the online and target models after `steps` updates (soft update every 2 opts, tau 0.5)."""
+    import torch
+    from oracle import agent_oracle as ao
+    rng, tr, params = iqn_setup()
+    orc = ro.ReplayOracle(200, 9, (4, 84, 84), np.uint8, (1,), np.int64)
+    orc.push(*tr)
+    psi_fn = lambda p, x: ao.atari_cnn_forward(p, x, skip_linear=True)
+    m_fn = lambda p, m: ao.mlp_forward(p, m, 2)
+    oracle = ao.IqnOracle(params, psi_fn, m_fn, 64, lr, B, 0.99, 0.5, 2)
+    out = {"t1": [], "t2": [], "loss": []}
+    for _ in range(steps):
+        t1 = rng.random((B, N), dtype=np.float32)
+        t2 = rng.random((B, N), dtype=np.float32)
+        b = orc.batch(B)
+        tb = dict(obs=torch.from_numpy(b["obs"]), act=torch.from_numpy(b["act"]), next_obs=torch.from_numpy(b["next_obs"]),
+                  reward=torch.from_numpy(b["reward"]), is_terminated=torch.from_numpy(b["is_terminated"]))
+        out["loss"].append(float(oracle.opt_(tb, torch.from_numpy(t1), torch.from_numpy(t2))))
+        out["t1"].append(t1); out["t2"].append(t2)
+    out = {k: np.asarray(v) for k, v in out.items()}
+    _digest("iqn", oracle.iqn, out)
+    _digest("iqn_tgt", oracle.iqn_tgt, out)
+    return out
+
+
+def write_agent_traces():
+    np.savez_compressed(os.path.join(HERE, "sac_trace.npz"), **run_sac_trace())
+    np.savez_compressed(os.path.join(HERE, "iqn_trace.npz"), **run_iqn_trace())
+
+
 def main():
     np.savez_compressed(os.path.join(HERE, "dqn_mlp_trace.npz"), **run_dqn_mlp_trace())
     r = ro.StdRng(42)
@@ -128,4 +231,5 @@ def write_uniform_ixs():
 
 if __name__ == "__main__":
     write_uniform_ixs()
+    write_agent_traces()
     main()
