@@ -276,8 +276,52 @@ class Trainer {  // trainer.rs:100-327
         st.total_seconds = std::chrono::duration<double>(clk::now() - t_all).count();
         return st;
     }
+    // Trainer::train_offline (trainer.rs:330-384): no environment and no sampling -- warmup_period = 0, opt_interval = 1, one
+    // optimisation step per loop trip on a buffer that already holds the dataset; env_steps still counts the trips.
+    TrainStat train_offline(Agent& agent, ReplayBufferBase& buffer, const std::string& save_dir = "") {
+        using clk = std::chrono::steady_clock;
+        cfg_.warmup_period = 0;                                     // trainer.rs:344-345
+        cfg_.opt_interval = 1;
+        agent.train();
+        TrainStat st;
+        auto t_all = clk::now();
+        for (;;) {
+            st.env_steps += 1;                                      // :350
+            auto t1 = clk::now();
+            if ((st.opt_steps + 1) % cfg_.record_agent_info_interval == 0) {   // train_step, trainer.rs:197-228
+                Record r = agent.opt_with_record(buffer);
+                st.records += 1;
+                st.last_loss = r.r.loss != 0.f ? r.r.loss : r.r.loss_critic;
+            } else {
+                agent.opt(buffer);
+            }
+            st.opt_steps += 1;
+            st.opt_seconds += std::chrono::duration<double>(clk::now() - t1).count();
+            if (cfg_.save_interval > 0 && cfg_.save_interval != kNever && st.opt_steps % cfg_.save_interval == 0 &&
+                !save_dir.empty()) {                                // post_process, trainer.rs:231-264 (no evaluator)
+                agent.save_params(save_dir + "/" + std::to_string(st.opt_steps));
+                st.saves += 1;
+            }
+            if (st.opt_steps == cfg_.max_opts) break;               // :380-382
+        }
+        st.total_seconds = std::chrono::duration<double>(clk::now() - t_all).count();
+        return st;
+    }
   private:
     TrainerConfig cfg_;
+};
+
+// a ReplayBufferBase over a bb_replay handle the caller owns (the offline dataset is loaded before training starts)
+class BorrowedReplayBuffer : public ReplayBufferBase {
+  public:
+    explicit BorrowedReplayBuffer(bb_replay* h) : h_(h) {}
+    void push(Transition&& tr) override {
+        check(bb_replay_push(h_, tr.obs.data(), tr.act.data(), tr.next_obs.data(), &tr.reward, &tr.is_terminated, &tr.is_truncated, 1, 0));
+    }
+    size_t len() const override { uint64_t n = 0; check(bb_replay_len(h_, &n)); return (size_t)n; }
+    bb_replay* handle() override { return h_; }
+  private:
+    bb_replay* h_;
 };
 
 // ----------------------------------------------------------------------------- async training

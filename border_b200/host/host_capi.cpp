@@ -124,6 +124,28 @@ int32_t bbh_train(int32_t algo, const void* agent_cfg, const bb_replay_cfg* repl
     BBH_END
 }
 
+int32_t bbh_train_offline(int32_t algo, const void* agent_cfg, bb_replay* dataset, const bbh_trainer_cfg* tc, const char* save_dir,
+                          bbh_train_stat* out) {
+    BBH_BEGIN
+    if (!agent_cfg || !dataset || !tc || !out) throw Error("null argument");
+    auto agent = make_agent(algo, agent_cfg);
+    BorrowedReplayBuffer buffer(dataset);
+    TrainerConfig cfg;
+    cfg.max_opts = (size_t)tc->max_opts;
+    cfg.record_agent_info_interval = nz(tc->record_agent_info_interval);
+    cfg.save_interval = nz(tc->save_interval);
+    Trainer trainer(cfg);
+    TrainStat st = trainer.train_offline(*agent, buffer, save_dir ? save_dir : "");
+    memset(out, 0, sizeof(*out));
+    out->env_steps = st.env_steps; out->opt_steps = st.opt_steps; out->records = st.records; out->saves = st.saves;
+    out->opt_seconds = st.opt_seconds; out->total_seconds = st.total_seconds;
+    out->last_loss = st.last_loss; out->buffer_len = buffer.len();
+    uint64_t n = 0;
+    check(bb_agent_n_opts(agent->handle(), &n));
+    out->agent_n_opts = n;
+    BBH_END
+}
+
 int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg, const bbh_env_cfg* env_cfg,
                         const bbh_trainer_cfg* tc, bbh_train_stat* out) {
     return bbh_train_async_ex(algo, agent_cfg, replay_cfg, env_cfg, tc, nullptr, nullptr, out);

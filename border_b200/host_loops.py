@@ -83,6 +83,17 @@ def train(algo, agent_cfg, replay_cfg, env_cfg, tcfg, save_dir=None):
     return _stat(st)
 
 
+def train_offline(algo, agent_cfg, dataset, tcfg, save_dir=None):
+    """Trainer::train_offline (border-core/src/trainer.rs:330-384) on a replay buffer that already holds the dataset."""
+    st = bbh_train_stat()
+    lib = host_lib()
+    lib.bbh_train_offline.restype = C.c_int32
+    lib.bbh_train_offline.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
+    _check(lib.bbh_train_offline(ALGO[algo], C.cast(C.pointer(agent_cfg), C.c_void_p), dataset.handle, C.byref(tcfg),
+                                 save_dir.encode() if save_dir else None, C.byref(st)))
+    return _stat(st)
+
+
 LEARNER_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_void_p)
 
 

@@ -46,6 +46,11 @@ void bbh_trainer_cfg_default(bbh_trainer_cfg* cfg);
  * B200 replay buffer. */
 int32_t bbh_train(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg, const bbh_env_cfg* env_cfg,
                   const bbh_trainer_cfg* trainer_cfg, const char* save_dir, bbh_train_stat* out);
+/* Trainer::train_offline (border-core/src/trainer.rs:330-384): max_opts optimisation steps on a replay buffer that already
+ * holds the dataset (the caller owns `dataset` and fills it with bb_replay_push); no environment, warmup_period = 0,
+ * opt_interval = 1; records / saves at the trainer's intervals. */
+int32_t bbh_train_offline(int32_t algo, const void* agent_cfg, bb_replay* dataset, const bbh_trainer_cfg* trainer_cfg,
+                          const char* save_dir, bbh_train_stat* out);
 /* train_async: n_actors actor threads (each its own agent + env, seed = actor id) -> learner. */
 int32_t bbh_train_async(int32_t algo, const void* agent_cfg, const bb_replay_cfg* replay_cfg,
                         const bbh_env_cfg* env_cfg, const bbh_trainer_cfg* trainer_cfg, bbh_train_stat* out);

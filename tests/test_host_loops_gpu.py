@@ -101,3 +101,21 @@ def test_train_async_learner_hook_phases():
     st = H.train_async("dqn", _dqn_mlp(16), _replay_cfg(1000, L.BB_F32, 4, L.BB_I64, 1), env, tc, on_learner=hook)
     assert st["opt_steps"] == 20
     assert seen == [(0, 0), (2, 0), (1, 20)]
+
+
+def test_train_offline_runs_max_opts_on_a_prefilled_dataset(tmp_path):
+    """trainer.rs:330-384: no sampling, one optimisation step per loop trip (warmup 0, opt_interval 1), env_steps counts the
+    trips, the dataset is untouched, records / saves keep the trainer's cadence."""
+    from border_b200.replay import GenericTransitionBatch, SimpleReplayBuffer, SimpleReplayBufferConfig
+    rng = np.random.default_rng(0)
+    n = 400
+    obs = rng.standard_normal((n, 4)).astype(np.float32)
+    ds = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=512, seed=3))
+    ds.push(GenericTransitionBatch(obs, rng.integers(0, 2, (n, 1)).astype(np.int64), obs + 0.1, rng.standard_normal(n).astype(np.float32),
+                                   np.zeros(n, np.int8), np.zeros(n, np.int8)))
+    tc = H.trainer_cfg(max_opts=30, opt_interval=7, warmup_period=1000, record_agent_info_interval=10, save_interval=15)
+    st = H.train_offline("dqn", _dqn_mlp(32), ds, tc, str(tmp_path))
+    assert st["opt_steps"] == 30 and st["agent_n_opts"] == 30 and st["env_steps"] == 30   # warmup / opt_interval are overridden
+    assert st["buffer_len"] == n and len(ds) == n
+    assert st["records"] == 3 and st["saves"] == 2 and np.isfinite(st["last_loss"]) and st["last_loss"] > 0
+    assert ds.state()["rng_words"] == 30 * 32                                             # 30 batches were drawn from the dataset
