@@ -335,6 +335,24 @@ def run_b200(args):
     hl.actor_steps(agent, rb, h_obs, h_next, h_rew, h_term, h_trunc, env_n)
     torch.cuda.synchronize()
     env_sps = world * env_n / (time.perf_counter() - t0)
+    # ... and vectorised: 8 environments per call (bb_actor_step_n; Policy::sample on a batch of n_procs observations)
+    env_sps_n8 = None
+    try:
+        agent.actor_reset()
+        o8 = np.ascontiguousarray(h_obs[:8])
+        r8, z8 = np.ones(8, np.float32), np.zeros(8, np.int8)
+        for _ in range(20):
+            agent.actor_step_n(rb, o8, r8, z8, z8)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        calls = max(100, env_n // 4)
+        for _ in range(calls):
+            agent.actor_step_n(rb, o8, r8, z8, z8)
+        torch.cuda.synchronize()
+        env_sps_n8 = world * 8 * calls / (time.perf_counter() - t0)
+        agent.actor_reset()
+    except Exception as e:
+        env_sps_n8 = repr(e)
 
     # ---- roofline of the dominant kernel, measured live with CUDA events after every kernel
     prof_runs = [agent.opt_profiled(rb) for _ in range(6)][1:]
@@ -461,7 +479,7 @@ def run_b200(args):
                "gpu_launches": launches,
                "env_steps_per_sec": env_sps,
                "env_steps": {"value": env_sps, "unit": "env-steps/s", "path": "bb_actor_step (device-side explorer, device->ring push)",
-                             "host_sample_plus_host_push": env_sps_host_push, "h2d_bytes_per_step": ROW + 16, "d2h_bytes_per_step": 8},
+                             "host_sample_plus_host_push": env_sps_host_push, "n_env8_bb_actor_step_n": env_sps_n8, "h2d_bytes_per_step": ROW + 16, "d2h_bytes_per_step": 8},
                "roofline": roof, "roofline_replay": roof_replay,
                "step_flop": STEP_FLOP, "step_tflops": STEP_FLOP / (ms / args.steps * 1e-3) / 1e12,
                "kernel_breakdown_ms": {k: round(v, 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:12]}}

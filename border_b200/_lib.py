@@ -148,6 +148,7 @@ _SIGS = {
     "bb_agent_exchange_trace": (C.c_int32, [_P, C.POINTER(C.c_uint32)]),
     "bb_actor_step": (C.c_int32, [_P, _P, _P, _P, C.c_float, C.c_int8, C.c_int8, C.POINTER(C.c_int64)]),
     "bb_actor_reset": (C.c_int32, [_P]),
+    "bb_actor_step_n": (C.c_int32, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32]),
     "bb_actor_step_dev": (C.c_int32, [_P, _P, _P, _P, C.c_float, C.c_int8, C.c_int8, C.POINTER(C.c_int64)]),
     "bb_atari_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "bb_atari_destroy": (C.c_int32, [_P]),

@@ -290,6 +290,20 @@ class Agent:
                                           int(is_terminated), int(is_truncated), C.byref(act)))
         return act.value
 
+    def actor_step_n(self, buffer, obs, reward, is_terminated, is_truncated, reset_obs=None, reset_mask=None):
+        """actor_step for n environments at once (obs [n, ...], the other arguments [n]); returns the n actions."""
+        obs = np.ascontiguousarray(obs)
+        n = obs.shape[0]
+        r = np.ascontiguousarray(reward, np.float32)
+        t = np.ascontiguousarray(is_terminated, np.int8)
+        tr = np.ascontiguousarray(is_truncated, np.int8)
+        ro = None if reset_obs is None else np.ascontiguousarray(reset_obs, obs.dtype)
+        rm = None if reset_mask is None else np.ascontiguousarray(reset_mask, np.int8)
+        out = np.empty(n, np.int64)
+        L.check(L.lib().bb_actor_step_n(self._h, buffer.handle, n, _p(obs), None if ro is None else _p(ro),
+                                        None if rm is None else _p(rm), _p(r), _p(t), _p(tr), _p(out), 0))
+        return out
+
     def actor_reset(self):
         L.check(L.lib().bb_actor_reset(self._h))
 

@@ -83,7 +83,7 @@ Agent::~Agent() {
     if (comm_ctx.stream) { cudaStreamSynchronize(comm_ctx.stream); cudaStreamDestroy(comm_ctx.stream); }
     if (comm_ctx.ev) cudaEventDestroy(comm_ctx.ev);
     cudaFree(xchg_ctr);
-    cudaFree(d_actor_obs[0]); cudaFree(d_actor_obs[1]); cudaFree(d_actor_act);
+    cudaFree(d_actor_obs[0]); cudaFree(d_actor_obs[1]); cudaFree(d_actor_obs[2]); cudaFree(d_actor_act); cudaFree(d_actor_misc);
     if (h_actor_stage) cudaFreeHost(h_actor_stage);
     if (h_actor_act) cudaFreeHost(h_actor_act);
     if (ev_actor) cudaEventDestroy(ev_actor);
@@ -108,89 +108,114 @@ void Agent::inject_noise(int, const float*, size_t) { throw Error("this agent ta
 // are made on the host in the reference's order and arrive as (mode, forced, u): 0 = argmax Q, 1 = the random action
 // `forced`, 2 = softmax(Q).multinomial(1) by inverse CDF on u.  The action goes to device memory (the next push reads it)
 // and to pinned host memory (the env reads it).
-struct SelectParams { const float* q; int A; int mode; long long forced; double u; long long* act_dev; long long* act_host; };
+struct SelectParams {
+    const float* q; int A; int n;
+    int mode[Agent::kActorMaxEnvs]; long long forced[Agent::kActorMaxEnvs]; double u[Agent::kActorMaxEnvs];
+    long long* act_dev; long long* act_host;
+};
 __global__ void actor_select_kernel(SelectParams s) {
-    if (threadIdx.x != 0) return;
+    const int i = threadIdx.x;
+    if (i >= s.n) return;
+    const float* q = s.q + (size_t)i * s.A;
     long long a = 0;
-    if (s.mode == 1) {
-        a = s.forced;
-    } else if (s.mode == 0) {
+    if (s.mode[i] == 1) {
+        a = s.forced[i];
+    } else if (s.mode[i] == 0) {
         int best = 0;
         for (int j = 1; j < s.A; ++j)
-            if (s.q[j] > s.q[best]) best = j;
+            if (q[j] > q[best]) best = j;
         a = best;
     } else {
-        float mx = s.q[0];
-        for (int j = 1; j < s.A; ++j) mx = fmaxf(mx, s.q[j]);
+        float mx = q[0];
+        for (int j = 1; j < s.A; ++j) mx = fmaxf(mx, q[j]);
         double z = 0;
-        for (int j = 0; j < s.A; ++j) z += exp((double)(s.q[j] - mx));
-        const double u = s.u * z;
+        for (int j = 0; j < s.A; ++j) z += exp((double)(q[j] - mx));
+        const double u = s.u[i] * z;
         double acc = 0;
         int pick = s.A - 1;
         for (int j = 0; j < s.A; ++j) {
-            acc += exp((double)(s.q[j] - mx));
+            acc += exp((double)(q[j] - mx));
             if (u < acc) { pick = j; break; }
         }
         a = pick;
     }
-    *s.act_dev = a;
-    *reinterpret_cast<volatile long long*>(s.act_host) = a;
+    s.act_dev[i] = a;
+    reinterpret_cast<volatile long long*>(s.act_host)[i] = a;
 }
 
 void Agent::grad_buffer(void** p, uint64_t* n) { *p = nullptr; *n = 0; }
-// bb_actor_step (border_b200.h): Sampler::sample_and_push with device-resident observations
-void Agent::actor_step(Replay& rb, const void* obs, const void* reset_obs, float reward, int8_t term, int8_t trunc,
-                       int64_t* act_out, bool obs_on_device) {
+
+// bb_actor_step[_n] (border_b200.h): Sampler::sample_and_push with device-resident observations, n environments per call
+void Agent::actor_step_n(Replay& rb, int n, const void* obs, const void* reset_obs, const int8_t* reset_mask, const float* reward,
+                         const int8_t* term, const int8_t* trunc, int64_t* act_out, bool obs_on_device) {
     DeviceGuard g(device);
     const size_t row = actor_obs_row_bytes();
     BB_CHECK(row > 0, "bb_actor_step: this agent has no device-side actor path (discrete-action agents only: DQN, IQN)");
+    BB_CHECK(n >= 1 && n <= kActorMaxEnvs, "bb_actor_step_n: 1..8 environments per call");
     BB_CHECK(rb.obs_row_bytes == row && rb.cfg.act_kind == BB_I64 && rb.cfg.act_elems == 1,
              "bb_actor_step: the replay rows do not match the network (obs row) / a scalar i64 action");
+    BB_CHECK(!actor_has_prev || n == actor_n, "bb_actor_step_n: the number of environments changed (call bb_actor_reset first)");
+    BB_CHECK((reset_obs == nullptr) == (reset_mask == nullptr), "bb_actor_step_n: reset_obs and reset_mask go together");
+    const size_t block = (size_t)kActorMaxEnvs * row;   // one observation buffer
     if (!d_actor_act) {
-        actor_row_pad = (row + 15) / 16 * 16;
-        for (int k = 0; k < 2; ++k) d_actor_obs[k] = dev_alloc<uint8_t>(actor_row_pad + 16);
-        d_actor_act = dev_alloc_zero<long long>(2);
-        BB_CUDA(cudaMallocHost(&h_actor_stage, 2 * (actor_row_pad + 16)));
-        BB_CUDA(cudaMallocHost(&h_actor_act, 16));
+        actor_row_pad = (block + 255) / 256 * 256;
+        for (int k = 0; k < 3; ++k) d_actor_obs[k] = dev_alloc<uint8_t>(actor_row_pad);
+        d_actor_misc = dev_alloc_zero<uint8_t>(64);
+        d_actor_act = dev_alloc_zero<long long>(kActorMaxEnvs);
+        BB_CUDA(cudaMallocHost(&h_actor_stage, 2 * actor_row_pad + 64));
+        BB_CUDA(cudaMallocHost(&h_actor_act, kActorMaxEnvs * sizeof(long long)));
         BB_CUDA(cudaEventCreateWithFlags(&ev_actor, cudaEventDisableTiming));
     }
-    // the transition's next_obs (+ reward / flags behind it) -> the slot that is not the previous observation
-    const int cur = actor_prev ^ 1;
+    const int prev = actor_prev, cur = (actor_prev + 1) % 3, alt = (actor_prev + 2) % 3;
+    // this step's observations (the transitions' next_obs) -> `cur`; reward / flags -> the misc block
     uint8_t* h = h_actor_stage;
-    memcpy(h + actor_row_pad, &reward, 4);
-    h[actor_row_pad + 4] = (uint8_t)term; h[actor_row_pad + 5] = (uint8_t)trunc;
+    uint8_t* hm = h_actor_stage + 2 * actor_row_pad;
+    memcpy(hm, reward, 4 * (size_t)n);
+    memcpy(hm + 32, term, (size_t)n);
+    memcpy(hm + 40, trunc, (size_t)n);
     if (obs_on_device) {   // e.g. the frame stack bb_atari_step left in HBM: only reward + flags cross PCIe
-        BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], obs, row, cudaMemcpyDeviceToDevice, ctx.stream));
-        BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur] + actor_row_pad, h + actor_row_pad, 16, cudaMemcpyHostToDevice, ctx.stream));
+        BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], obs, (size_t)n * row, cudaMemcpyDeviceToDevice, ctx.stream));
     } else {
-        memcpy(h, obs, row);
-        BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], h, actor_row_pad + 16, cudaMemcpyHostToDevice, ctx.stream));
+        memcpy(h, obs, (size_t)n * row);
+        BB_CUDA(cudaMemcpyAsync(d_actor_obs[cur], h, (size_t)n * row, cudaMemcpyHostToDevice, ctx.stream));
     }
     if (actor_has_prev) {
+        BB_CUDA(cudaMemcpyAsync(d_actor_misc, hm, 48, cudaMemcpyHostToDevice, ctx.stream));
         if (rb.stream != ctx.stream) stream_wait(rb.stream, ctx.stream);
-        const uint8_t* m = d_actor_obs[cur] + actor_row_pad;
-        rb.push(d_actor_obs[actor_prev], d_actor_act, d_actor_obs[cur], (const float*)m, (const int8_t*)(m + 4),
-                (const int8_t*)(m + 5), 1, true);
+        rb.push(d_actor_obs[prev], d_actor_act, d_actor_obs[cur], (const float*)d_actor_misc, (const int8_t*)(d_actor_misc + 32),
+                (const int8_t*)(d_actor_misc + 40), (size_t)n, true);
         if (rb.stream != ctx.stream) stream_wait(ctx.stream, rb.stream);
     }
+    // the observations the policy acts on: the uploaded ones, with the reset observation in place of every finished
+    // episode's last one (sampler.rs:128-137) -- a copy only when some episode ended
     int act_src = cur;
-    if (reset_obs) {   // the episode ended: the next action is for the reset observation (sampler.rs:128-137)
-        uint8_t* h2 = h_actor_stage + actor_row_pad + 16;
-        if (!obs_on_device) memcpy(h2, reset_obs, row);
-        BB_CUDA(cudaMemcpyAsync(d_actor_obs[actor_prev], obs_on_device ? reset_obs : h2, row,   // after the push read it
-                                obs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
-        act_src = actor_prev;
+    bool any_reset = false;
+    for (int i = 0; reset_mask && i < n; ++i) any_reset |= reset_mask[i] != 0;
+    if (any_reset) {
+        BB_CUDA(cudaMemcpyAsync(d_actor_obs[alt], d_actor_obs[cur], (size_t)n * row, cudaMemcpyDeviceToDevice, ctx.stream));
+        for (int i = 0; i < n; ++i) {
+            if (!reset_mask[i]) continue;
+            const uint8_t* src = (const uint8_t*)reset_obs + (size_t)i * row;
+            if (!obs_on_device) { memcpy(h + actor_row_pad + (size_t)i * row, src, row); src = h + actor_row_pad + (size_t)i * row; }
+            BB_CUDA(cudaMemcpyAsync(d_actor_obs[alt] + (size_t)i * row, src, row,
+                                    obs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
+        }
+        act_src = alt;
     }
-    const float* q = actor_q(d_actor_obs[act_src]);
-    const ActorPick k = actor_pick();
-    SelectParams sp{q, actor_n_actions(), k.mode, k.forced, k.u, d_actor_act, h_actor_act};
+    const float* q = actor_q(d_actor_obs[act_src], n);
+    ActorPick picks[kActorMaxEnvs];
+    actor_pick(n, picks);
+    SelectParams sp{};
+    sp.q = q; sp.A = actor_n_actions(); sp.n = n; sp.act_dev = d_actor_act; sp.act_host = h_actor_act;
+    for (int i = 0; i < n; ++i) { sp.mode[i] = picks[i].mode; sp.forced[i] = picks[i].forced; sp.u[i] = picks[i].u; }
     actor_select_kernel<<<1, 32, 0, ctx.stream>>>(sp);
     BB_LAUNCHED();
     ctx.phase = "policy"; ctx.layer = "explorer"; ctx.mark("actor_select");
     BB_CUDA(cudaEventRecord(ev_actor, ctx.stream));
     BB_CUDA(cudaEventSynchronize(ev_actor));
-    *act_out = (int64_t)h_actor_act[0];
+    for (int i = 0; i < n; ++i) act_out[i] = (int64_t)h_actor_act[i];
     actor_prev = act_src;
+    actor_n = n;
     actor_has_prev = true;
 }
 
@@ -554,6 +579,15 @@ int32_t bb_actor_step_dev(bb_agent* a, bb_replay* rb, const void* obs_dev, const
     BB_CHECK(rb && obs_dev && act_out, "null argument");
     bb::check_device_error("bb_actor_step_dev");
     A(a).actor_step(rb->impl, obs_dev, reset_obs_dev, reward, is_terminated, is_truncated, act_out, true);
+    BB_API_END
+}
+int32_t bb_actor_step_n(bb_agent* a, bb_replay* rb, int32_t n_envs, const void* obs, const void* reset_obs, const int8_t* reset_mask,
+                        const float* reward, const int8_t* is_terminated, const int8_t* is_truncated, int64_t* act_out,
+                        int32_t obs_on_device) {
+    BB_API_BEGIN
+    BB_CHECK(rb && obs && reward && is_terminated && is_truncated && act_out, "null argument");
+    bb::check_device_error("bb_actor_step_n");
+    A(a).actor_step_n(rb->impl, n_envs, obs, reset_obs, reset_mask, reward, is_terminated, is_truncated, act_out, obs_on_device != 0);
     BB_API_END
 }
 int32_t bb_actor_reset(bb_agent* a) {

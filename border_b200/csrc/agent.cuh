@@ -119,23 +119,35 @@ struct Agent {
     virtual void sample(const void* obs, size_t n, void* act_out) = 0;
     // Sampler::sample_and_push (border-core/src/trainer/sampler.rs:99-144) with the observation crossing PCIe once:
     // see bb_actor_step in border_b200.h.  Discrete-action agents only.
-    // The generic loop is Agent::actor_step; a discrete-action agent supplies its observation row size, action count, the
-    // policy forward for one device-resident observation and the explorer's host-side draws.
+    // The generic loop is Agent::actor_step_n; a discrete-action agent supplies its observation row size, action count, the
+    // policy forward for device-resident observations and the explorer's host-side draws.
+    static constexpr int kActorMaxEnvs = 8;                                       // environments per call (vectorised Sampler)
     struct ActorPick { int mode = 0; long long forced = 0; double u = 0.0; };   // 0 argmax, 1 forced action, 2 softmax on u
     virtual size_t actor_obs_row_bytes() const { return 0; }                     // 0 = no device-side actor path
     virtual int actor_n_actions() const { return 0; }
-    virtual const float* actor_q(const uint8_t* d_obs) { (void)d_obs; return nullptr; }
-    virtual ActorPick actor_pick() { return ActorPick{}; }
+    // Q values [n][A] for n observations already in HBM (contiguous rows), on ctx.stream
+    virtual const float* actor_q(const uint8_t* d_obs, int n) { (void)d_obs; (void)n; return nullptr; }
+    // the explorer's host-side draws for n observations, in the order Policy::sample(obs[n]) makes them
+    virtual void actor_pick(int n, ActorPick* out) { for (int i = 0; i < n; ++i) out[i] = ActorPick{}; }
+    // n environments at once: obs [n][row]; reset_obs [n][row] + reset_mask[n] (or both null); reward / term / trunc [n]
+    void actor_step_n(Replay& rb, int n, const void* obs, const void* reset_obs, const int8_t* reset_mask, const float* reward,
+                      const int8_t* term, const int8_t* trunc, int64_t* act_out, bool obs_on_device);
     void actor_step(Replay& rb, const void* obs, const void* reset_obs, float reward, int8_t term, int8_t trunc,
-                    int64_t* act_out, bool obs_on_device = false);
+                    int64_t* act_out, bool obs_on_device = false) {
+        const int8_t one = 1;
+        actor_step_n(rb, 1, obs, reset_obs, reset_obs ? &one : nullptr, &reward, &term, &trunc, act_out, obs_on_device);
+    }
     void actor_reset() { actor_has_prev = false; }
-    // the last two observations and the last action stay on the device
-    uint8_t* d_actor_obs[2] = {nullptr, nullptr};
-    uint8_t* h_actor_stage = nullptr;   // pinned: [obs row | reward, term, trunc] x 2 (transition obs, reset obs)
-    long long* d_actor_act = nullptr;
+    // three rotating observation buffers ([kActorMaxEnvs][row] each): the previous step's acting observations (obs of the
+    // transitions being pushed), this step's uploaded observations (their next_obs), and -- only when an episode ended --
+    // the acting observations of this step (uploaded rows with the reset observations written over them)
+    uint8_t* d_actor_obs[3] = {nullptr, nullptr, nullptr};
+    uint8_t* d_actor_misc = nullptr;    // reward f32[8] | term i8[8] | trunc i8[8]
+    uint8_t* h_actor_stage = nullptr;   // pinned: obs rows | reset rows | misc
+    long long* d_actor_act = nullptr;   // [kActorMaxEnvs]
     long long* h_actor_act = nullptr;   // pinned, written by the explorer kernel
     size_t actor_row_pad = 0;
-    int actor_prev = 0;
+    int actor_prev = 0, actor_n = 0;
     bool actor_has_prev = false;
     cudaEvent_t ev_actor = nullptr;
     virtual Model* sync_model_src() = 0;  // which VarStore SyncModel ships (DQN qnet, SAC pi)

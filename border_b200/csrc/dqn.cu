@@ -371,30 +371,32 @@ struct Dqn : Agent {
     // ---- device-side actor path (Agent::actor_step): the agent-specific pieces
     size_t actor_obs_row_bytes() const override { return (size_t)net.in_elems * (net.u8_input ? 1 : 4); }
     int actor_n_actions() const override { return net.out_dim; }
-    const float* actor_q(const uint8_t* d_obs) override {   // Q(obs) for one observation already in HBM
-        if (ws_actor.max_batch < 1) net.alloc_workspace(ws_actor, 1, false);
-        const float* q = net.forward_small(ctx, qnet.p, d_obs, net.in_elems, 1, ws_actor);
-        if (!q) q = net.forward(ctx, qnet.p, d_obs, net.in_elems, 1, ws_actor);
+    const float* actor_q(const uint8_t* d_obs, int n) override {   // Q(obs) [n][A] for observations already in HBM
+        if (ws_actor.max_batch < kActorMaxEnvs) net.alloc_workspace(ws_actor, kActorMaxEnvs, false);
+        const float* q = net.forward_small(ctx, qnet.p, d_obs, net.in_elems, n, ws_actor);
+        if (!q) q = net.forward(ctx, qnet.p, d_obs, net.in_elems, n, ws_actor);
         return q;
     }
-    // the explorer's fastrand draws, on the host and in the reference's order (dqn/explorer.rs:29-31,68-90; eval: base.rs:229-236)
-    ActorPick actor_pick() override {
-        ActorPick k;
+    // the explorer's fastrand draws, on the host and in the order Dqn::sample makes them for n observations
+    // (dqn/explorer.rs:29-31,68-90: one epsilon draw per call, one action draw per process; eval: base.rs:229-236)
+    void actor_pick(int n, ActorPick* out) override {
         const int A = net.out_dim;
+        for (int i = 0; i < n; ++i) out[i] = ActorPick{};
         if (train) {
             if (cfg.explorer == BB_EXPLORER_EPS_GREEDY) {
                 double d = (cfg.eps_start - cfg.eps_final) / (double)cfg.final_step;
                 double eps = std::max(cfg.eps_start - d * (double)eps_n_opts, cfg.eps_final);
                 const bool is_random = fr.f64() < eps;
                 eps_n_opts += 1;
-                if (is_random) { k.mode = 1; k.forced = (long long)fr.u32_below((uint32_t)A); }
+                if (is_random)
+                    for (int i = 0; i < n; ++i) { out[i].mode = 1; out[i].forced = (long long)fr.u32_below((uint32_t)A); }
             } else {
-                k.mode = 2; k.u = fr.f64();
+                for (int i = 0; i < n; ++i) { out[i].mode = 2; out[i].u = fr.f64(); }
             }
-        } else if (fr.f32() < 0.01f) {
-            k.mode = 1; k.forced = (long long)fr.u64_below((uint64_t)A);
+        } else {
+            for (int i = 0; i < n; ++i)
+                if (fr.f32() < 0.01f) { out[i].mode = 1; out[i].forced = (long long)fr.u64_below((uint64_t)A); }
         }
-        return k;
     }
 
     // Policy::sample, dqn/base.rs:211-241

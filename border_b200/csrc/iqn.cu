@@ -411,25 +411,25 @@ struct Iqn : Agent {
     // ---- device-side actor path (Agent::actor_step): quantile mean on the device, explorer draws on the host
     size_t actor_obs_row_bytes() const override { return (size_t)f_net.in_elems * (f_net.u8_input ? 1 : 4); }
     int actor_n_actions() const override { return A; }
-    const float* actor_q(const uint8_t* d_obs) override {
+    const float* actor_q(const uint8_t* d_obs, int n) override {
         const int N = n_percent_points(cfg.sample_percents_act, true);
-        ensure(ws_act, 1, N, false);
-        if (!d_qmean_actor) d_qmean_actor = dev_alloc<float>(A);
-        const float* z = forward(iqn, d_obs, 1, N, cfg.sample_percents_act, -1, ws_act);
-        iqn_mean_kernel<<<(A + 127) / 128, 128, 0, ctx.stream>>>(z, d_qmean_actor, 1, N, A);
+        ensure(ws_act, std::max(n, ws_act.B), N, false);
+        if (!d_qmean_actor) d_qmean_actor = dev_alloc<float>((size_t)kActorMaxEnvs * A);
+        const float* z = forward(iqn, d_obs, n, N, cfg.sample_percents_act, -1, ws_act);
+        iqn_mean_kernel<<<(n * A + 127) / 128, 128, 0, ctx.stream>>>(z, d_qmean_actor, n, N, A);
         BB_LAUNCHED();
         return d_qmean_actor;
     }
-    ActorPick actor_pick() override {   // IqnExplorer::EpsilonGreedy::action (iqn/explorer.rs:78-97); eval: argmax
-        ActorPick k;
+    void actor_pick(int n, ActorPick* out) override {   // IqnExplorer::EpsilonGreedy::action (iqn/explorer.rs:78-97); eval: argmax
+        for (int i = 0; i < n; ++i) out[i] = ActorPick{};
         if (train) {
             double d = (cfg.eps_start - cfg.eps_final) / (double)cfg.final_step;
             double eps = std::max(cfg.eps_start - d * (double)eps_n_opts, cfg.eps_final);
             const bool is_random = fr.f64() < eps;
             eps_n_opts += 1;
-            if (is_random) { k.mode = 1; k.forced = (long long)fr.u32_below((uint32_t)A); }
+            if (is_random)
+                for (int i = 0; i < n; ++i) { out[i].mode = 1; out[i].forced = (long long)fr.u32_below((uint32_t)A); }
         }
-        return k;
     }
 
     void sample(const void* obs, size_t n, void* act_out) override {

@@ -298,6 +298,13 @@ int32_t bb_actor_step(bb_agent* a, bb_replay* rb, const void* obs, const void* r
  * cross PCIe.  The pointers must stay valid and unchanged until the call returns (it synchronises). */
 int32_t bb_actor_step_dev(bb_agent* a, bb_replay* rb, const void* obs_dev, const void* reset_obs_dev, float reward,
                           int8_t is_terminated, int8_t is_truncated, int64_t* act_out);
+/* The vectorised form: `n_envs` (1..8) environments per call, as Policy::sample on a batch of n_procs observations does in
+ * the reference (dqn/explorer.rs:68-90: one epsilon draw per call, one action draw per process).  obs [n][row], reward /
+ * is_terminated / is_truncated [n]; reset_obs [n][row] + reset_mask [n] (rows with mask 0 are ignored) or both NULL;
+ * act_out [n].  The n transitions are pushed in environment order.  obs_on_device != 0: obs / reset_obs are device pointers. */
+int32_t bb_actor_step_n(bb_agent* a, bb_replay* rb, int32_t n_envs, const void* obs, const void* reset_obs, const int8_t* reset_mask,
+                        const float* reward, const int8_t* is_terminated, const int8_t* is_truncated, int64_t* act_out,
+                        int32_t obs_on_device);
 int32_t bb_actor_reset(bb_agent* a);   /* forget the previous observation (new Sampler / after a manual env.reset) */
 /* Agent::opt / opt_with_record (record may be NULL => no device->host copy at all). */
 int32_t bb_agent_opt(bb_agent* a, bb_replay* rb, bb_record* record);

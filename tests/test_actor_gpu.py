@@ -90,6 +90,55 @@ def test_actor_step_iqn_matches_sample_and_push():
     _walk("iqn", EpsilonGreedy(), False, steps=10, ep_len=4)
 
 
+@pytest.mark.parametrize("kind,explorer", [("cnn", EpsilonGreedy(eps_start=0.5, eps_final=0.2, final_step=20)), ("mlp", None)])
+def test_actor_step_n_vectorised_envs_match_batched_sample_and_push(kind, explorer):
+    """n_envs = 5 per call: the actions equal Policy::sample on the batch of 5 observations (one epsilon draw per call, one
+    action draw per process, dqn/explorer.rs:68-90) and the ring holds the 5 transitions of every step in environment order;
+    episodes end at different steps per environment (reset observations replace only those rows)."""
+    from border_b200.agents import Softmax
+    rng = np.random.default_rng(9)
+    n, steps = 5, 14
+    if kind == "cnn":
+        qcfg, shape, dtype, n_act = AtariCnnConfig(4, 6), (4, 84, 84), np.uint8, 6
+        frames = rng.integers(0, 256, (steps + 2, n) + shape, dtype=np.uint8)
+        resets = rng.integers(0, 256, (steps + 2, n) + shape, dtype=np.uint8)
+    else:
+        qcfg, shape, dtype, n_act = MlpConfig(4, [64, 64], 3), (4,), np.float32, 3
+        frames = rng.standard_normal((steps + 2, n) + shape).astype(np.float32)
+        resets = rng.standard_normal((steps + 2, n) + shape).astype(np.float32)
+        explorer = Softmax()
+    rewards = rng.standard_normal((steps + 2, n)).astype(np.float32)
+    done = (rng.random((steps + 2, n)) < 0.25).astype(np.int8)
+
+    def make():
+        rb = SimpleReplayBuffer.build(SimpleReplayBufferConfig(capacity=128, seed=1))
+        rb.allocate(shape, dtype, (1,), np.int64)
+        ag = Dqn.build(DqnConfig(model_config=DqnModelConfig(q_config=qcfg, opt_config=OptimizerConfig(lr=1e-3)), batch_size=8,
+                                 train=True, explorer=explorer, device=0, init_seed=3, explorer_seed=77))
+        return rb, ag
+
+    rb_a, ag_a = make()
+    acts_a, prev = [], frames[0].copy()
+    for t in range(steps):
+        a = ag_a.sample(prev)[:, 0]
+        acts_a.append(a.tolist())
+        rb_a.push(GenericTransitionBatch(prev, a[:, None].astype(np.int64), frames[t + 1], rewards[t], done[t], np.zeros(n, np.int8)))
+        prev = np.where(done[t].reshape((n,) + (1,) * len(shape)) != 0, resets[t], frames[t + 1])
+    rb_b, ag_b = make()
+    zeros = np.zeros(n, np.int8)
+    acts_b = [ag_b.actor_step_n(rb_b, frames[0], np.zeros(n, np.float32), zeros, zeros).tolist()]
+    for t in range(steps):
+        any_done = bool(done[t].any())
+        acts_b.append(ag_b.actor_step_n(rb_b, frames[t + 1], rewards[t], done[t], zeros, reset_obs=resets[t] if any_done else None,
+                                        reset_mask=done[t] if any_done else None).tolist())
+    assert acts_a == acts_b[:steps]
+    assert len(rb_a) == len(rb_b) == steps * n
+    for _ in range(2):
+        ba, bb = rb_a.batch(48), rb_b.batch(48)
+        for k in ("obs", "act", "next_obs", "reward", "is_terminated", "is_truncated", "ix_sample"):
+            assert np.array_equal(getattr(ba, k), getattr(bb, k)), k
+
+
 def test_actor_step_rejects_sac():
     from border_b200 import _lib as L
     from border_b200.agents import Sac, SacConfig

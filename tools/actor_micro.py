@@ -17,6 +17,11 @@ def t(fn, n=2000, w=50):
     for i in range(n): fn(i)
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e6
 print("actor_step            %.1f us" % t(lambda i: ag.actor_step(rb, obs[i % 16], 0.5, 0, 0)))
+o8 = np.ascontiguousarray(obs[:8]); r8 = np.ones(8, np.float32); z8 = np.zeros(8, np.int8)
+ag.actor_reset()
+us8 = t(lambda i: ag.actor_step_n(rb, o8, r8, z8, z8), n=500)
+print("actor_step_n (8 envs)  %.1f us per call = %.0f env-steps/s" % (us8, 8e6 / us8))
+ag.actor_reset()
 print("sample (host explorer) %.1f us" % t(lambda i: ag.sample(obs[i % 16][None])))
 tr = GenericTransitionBatch(obs[:1], np.zeros((1, 1), np.int64), obs[1:2], np.ones(1, np.float32), np.zeros(1, np.int8), np.zeros(1, np.int8))
 print("host push             %.1f us" % t(lambda i: rb.push(tr)))
